@@ -1,0 +1,148 @@
+/*
+ * oracle.c — CPU oracle for the NeRF-or-nothing MipNeRF hot path (see oracle.h).
+ * TEST INFRASTRUCTURE ONLY; never linked into or called by the product library.
+ * Build: oracle/Makefile  (gcc -O3 -fopenmp -ffp-contract=off -march=x86-64-v3).
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <omp.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ config / topology */
+
+void orc_default_config(orc_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->n_samples = 128; c->n_levels = 2;
+  c->net_depth = 8; c->net_width = 256; c->net_depth_condition = 1; c->net_width_condition = 128;
+  c->skip_layer = 4; c->deg_point = 16; c->deg_view = 4;
+  c->white_bkgd = 1; c->adam_eps_mode = 0; c->last_sample_mode = 0; c->randomized = 1;
+  c->density_bias = 0.0; c->rgb_padding = 0.0; /* CUDA-kernel arithmetic (A-D15) */
+  c->coarse_loss_mult = 0.1; c->resample_padding = 0.01;
+}
+int orc_num_layers(const orc_config* c) { return c->net_depth + c->net_depth_condition + 2; }
+
+/* Layer table of SURVEY §2.3: ANU/AcceleratedMLP.cpp:131-154 == SN/MLP.cs:72-77. */
+void orc_layer_shapes(const orc_config* c, int* out, int* in_a, int* in_b) {
+  const int D = c->net_depth, C = c->net_depth_condition, W = c->net_width, Wc = c->net_width_condition;
+  const int P = 6 * c->deg_point, Dd = 3 + 6 * c->deg_view;
+  out[0] = W; in_a[0] = P; in_b[0] = 0;
+  for (int i = 1; i < D; i++) {
+    out[i] = W; in_a[i] = W;
+    in_b[i] = (c->skip_layer > 0 && i % c->skip_layer == 0) ? P : 0;
+  }
+  out[D] = 1; in_a[D] = W; in_b[D] = 0;
+  out[D + 1] = Wc; in_a[D + 1] = W; in_b[D + 1] = Dd;
+  for (int i = 1; i < C; i++) { out[D + 1 + i] = Wc; in_a[D + 1 + i] = Wc; in_b[D + 1 + i] = 0; }
+  out[D + C + 1] = 3; in_a[D + C + 1] = Wc; in_b[D + C + 1] = 0;
+}
+void orc_layer_sizes(const orc_config* c, int* sizes) {
+  int out[64], ia[64], ib[64];
+  const int L = orc_num_layers(c);
+  orc_layer_shapes(c, out, ia, ib);
+  for (int l = 0; l < L; l++) { sizes[l] = out[l] * (ia[l] + ib[l]); sizes[L + l] = out[l]; }
+}
+long orc_num_params(const orc_config* c) {
+  int sizes[128];
+  long n = 0;
+  orc_layer_sizes(c, sizes);
+  for (int l = 0; l < 2 * orc_num_layers(c); l++) n += sizes[l];
+  return n;
+}
+int orc_max_threads(void) { return omp_get_max_threads(); }
+void orc_set_threads(int n) { omp_set_num_threads(n); }
+
+/* ------------------------------------------------------------------ Philox4x32-10 */
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_sampling_uniforms(uint64_t seed, uint32_t step, uint32_t level, uint32_t ray0, int n_rays,
+                           int n, float* u) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int r = 0; r < n_rays; r++)
+    for (int i = 0; i < n; i++) {
+      const uint32_t ctr[4] = {ray0 + (uint32_t)r, (uint32_t)i, step, level};
+      uint32_t o[4];
+      orc_philox4x32_10(ctr, key, o);
+      u[(long)r * n + i] = (float)(o[0] >> 8) * (1.0f / 16777216.0f);
+    }
+}
+
+/* Glorot-uniform weights (SN/MipHelpers.cs:675: sqrt(6/(in+out))*(2u-1)), zero biases
+ * (SN/MLP.cs:78). Deterministic: counter = (flat index, 0, 0, 0x610), key = seed. */
+void orc_init_params(const orc_config* c, uint64_t seed, float* params) {
+  int out[64], ia[64], ib[64];
+  const int L = orc_num_layers(c);
+  orc_layer_shapes(c, out, ia, ib);
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  long off = 0;
+  for (int l = 0; l < L; l++) {
+    const int in = ia[l] + ib[l];
+    const float lim = sqrtf(6.0f / (float)(in + out[l]));
+    for (long i = 0; i < (long)out[l] * in; i++, off++) {
+      const uint32_t ctr[4] = {(uint32_t)off, 0u, 0u, 0x610u};
+      uint32_t o[4];
+      orc_philox4x32_10(ctr, key, o);
+      const float uu = (float)(o[0] >> 8) * (1.0f / 16777216.0f);
+      params[off] = lim * (uu * 2.0f - 1.0f);
+    }
+  }
+  for (int l = 0; l < L; l++)
+    for (int j = 0; j < out[l]; j++) params[off++] = 0.0f;
+}
+
+/* SN/MipHelpers.cs:758-773, float arithmetic. */
+float orc_learning_rate_decay(int step, float lr_init, float lr_final, int max_steps,
+                              int lr_delay_steps, float lr_delay_mult) {
+  float delay_rate = 1.0f;
+  if (lr_delay_steps > 0) {
+    float p = (float)step / (float)lr_delay_steps;
+    p = p < 0.0f ? 0.0f : (p > 1.0f ? 1.0f : p);
+    delay_rate = lr_delay_mult + (1.0f - lr_delay_mult) * sinf(0.5f * 3.14159265358979323846f * p);
+  }
+  float t = (float)step / (float)max_steps;
+  t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+  const float log_lerp = expf(logf(lr_init) * (1.0f - t) + logf(lr_final) * t);
+  return delay_rate * log_lerp;
+}
+
+/* ------------------------------------------------------------------ the two precisions */
+
+#define REAL float
+#define SUF _f32
+#define R_EXP expf
+#define R_LOG logf
+#define R_SIN sinf
+#define R_COS cosf
+#define R_SQRT sqrtf
+#define R_POW powf
+#include "oracle_impl.h"
+#undef REAL
+#undef SUF
+#undef R_EXP
+#undef R_LOG
+#undef R_SIN
+#undef R_COS
+#undef R_SQRT
+#undef R_POW
+
+#define REAL double
+#define SUF _f64
+#define R_EXP exp
+#define R_LOG log
+#define R_SIN sin
+#define R_COS cos
+#define R_SQRT sqrt
+#define R_POW pow
+#include "oracle_impl.h"
