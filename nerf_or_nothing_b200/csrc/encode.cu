@@ -1,0 +1,213 @@
+// encode.cu — conical frustum -> Gaussian (cast_rays, .cu:292-317) and integrated positional encoding +
+// direction encoding (encode_input_data, .cu:187-221); SURVEY Appendix B.1/B.2.
+//
+// HBM-bound elementwise work (roofline: write 6*deg_point*4 B/sample when materialised).  The reference
+// maps adjacent lanes to different rays (uncoalesced) and scatters 4-byte stores with stride 96; here a
+// block stages a [32 samples x 6*deg] tile in shared memory and streams it out with 128-bit stores.
+// The fused kernel goes straight from t-values to encodings and can emit the bf16 hi/lo planes the
+// tcgen05 MLP consumes, so mean/cov never touch HBM.
+#include "kernels.cuh"
+
+namespace nerf {
+namespace {
+
+struct Gauss { float mx, my, mz, cx, cy, cz; };
+
+// B.1 in the reference's operation order (.cu:298-316), with explicitly rounded (never FMA-contracted)
+// ops: IPE multiplies the mean by up to 2^15, so a 1-ulp difference in the mean would show up as ~1e-2 rad
+// in the highest frequency.  With this the Gaussian is bit-identical to the CPU oracle's for the same t.
+__device__ __forceinline__ Gauss frustum_to_gaussian(float t0, float t1, float radius, float3 o, float3 d) {
+#define M_(a, b) __fmul_rn(a, b)
+#define A_(a, b) __fadd_rn(a, b)
+#define S_(a, b) __fsub_rn(a, b)
+#define D_(a, b) __fdiv_rn(a, b)
+  const float mu = D_(A_(t0, t1), 2.f), hw = D_(S_(t1, t0), 2.f);
+  const float mu2 = M_(mu, mu), hw2 = M_(hw, hw);
+  const float den = A_(M_(3.f, mu2), hw2);
+  const float t_mean = A_(mu, D_(M_(M_(2.f, mu), hw2), den));                                         // .cu:306
+  const float t_var = S_(D_(hw2, 3.f), D_(M_(D_(4.f, 15.f), M_(M_(hw2, hw2), S_(M_(12.f, mu2), hw2))), M_(den, den)));  // .cu:307
+  const float r_var = M_(M_(radius, radius),
+                         S_(A_(D_(mu2, 4.f), M_(D_(5.f, 12.f), hw2)), D_(M_(D_(4.f, 15.f), M_(hw2, hw2)), den)));       // .cu:308
+  const float ddx = M_(d.x, d.x), ddy = M_(d.y, d.y), ddz = M_(d.z, d.z);
+  const float dmag = fmaxf(1e-10f, A_(A_(ddx, ddy), ddz));                                            // .cu:311
+  Gauss g;
+  g.mx = A_(M_(d.x, t_mean), o.x); g.my = A_(M_(d.y, t_mean), o.y); g.mz = A_(M_(d.z, t_mean), o.z);  // .cu:310
+  g.cx = A_(M_(t_var, ddx), M_(r_var, S_(1.f, D_(ddx, dmag))));                                       // .cu:313-316
+  g.cy = A_(M_(t_var, ddy), M_(r_var, S_(1.f, D_(ddy, dmag))));
+  g.cz = A_(M_(t_var, ddz), M_(r_var, S_(1.f, D_(ddz, dmag))));
+#undef M_
+#undef A_
+#undef S_
+#undef D_
+  return g;
+}
+
+// exp(-.5*var*4^f) * {sin,cos}(mean*2^f)  (.cu:185-186,196-204).  Scaling by 2^f is exact, so the
+// argument is exactly the reference's; when the attenuation underflows to 0 the product is 0 and the
+// (slow, huge-argument) sincos is skipped.
+__device__ __forceinline__ void ipe_pair(float mean, float var, float scale, float& s, float& c) {
+  const float e = expf(__fmul_rn(-0.5f, __fmul_rn(__fmul_rn(var, scale), scale)));
+  if (e == 0.f) { s = 0.f; c = 0.f; return; }
+  float sn, cs;
+  sincosf(mean * scale, &sn, &cs);
+  s = e * sn; c = e * cs;
+}
+
+__global__ void k_cast_rays(const float* __restrict__ t, const float* __restrict__ o, const float* __restrict__ d,
+                            const float* __restrict__ radii, int R, int S, float* __restrict__ means,
+                            float* __restrict__ covs) {
+  const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (long)R * S) return;
+  const int r = (int)(m / S), s = (int)(m % S);
+  const float3 oo = make_float3(o[r * 3], o[r * 3 + 1], o[r * 3 + 2]);
+  const float3 dd = make_float3(d[r * 3], d[r * 3 + 1], d[r * 3 + 2]);
+  const Gauss g = frustum_to_gaussian(t[(long)r * (S + 1) + s], t[(long)r * (S + 1) + s + 1], radii[r], oo, dd);
+  means[m * 3] = g.mx; means[m * 3 + 1] = g.my; means[m * 3 + 2] = g.mz;
+  covs[m * 3] = g.cx; covs[m * 3 + 1] = g.cy; covs[m * 3 + 2] = g.cz;
+}
+
+constexpr int kTileSamples = 32;  // samples per block iteration
+constexpr int kFreqLanes = 8;     // threads cooperating on one sample (each takes deg/8 frequencies)
+
+// FUSED=true : inputs t,o,d,radii.   FUSED=false: inputs means,covs (per-stage entry).
+template <bool FUSED>
+__global__ void __launch_bounds__(kTileSamples * kFreqLanes)
+k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ o,
+             const float* __restrict__ d, const float* __restrict__ radii, long M, int S, int deg,
+             float* __restrict__ enc_f32, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+             int pitch_h) {
+  extern __shared__ float tile[];  // [kTileSamples][P]
+  const int P = 6 * deg;
+  const int ls = threadIdx.x / kFreqLanes, fl = threadIdx.x % kFreqLanes;
+  const long m0 = (long)blockIdx.x * kTileSamples;
+  const long m = m0 + ls;
+  if (m < M) {
+    Gauss g;
+    if (FUSED) {
+      const int r = (int)(m / S), s = (int)(m % S);
+      const float3 oo = make_float3(o[r * 3], o[r * 3 + 1], o[r * 3 + 2]);
+      const float3 dd = make_float3(d[r * 3], d[r * 3 + 1], d[r * 3 + 2]);
+      g = frustum_to_gaussian(in0[(long)r * (S + 1) + s], in0[(long)r * (S + 1) + s + 1], radii[r], oo, dd);
+    } else {
+      g.mx = in0[m * 3]; g.my = in0[m * 3 + 1]; g.mz = in0[m * 3 + 2];
+      g.cx = in1[m * 3]; g.cy = in1[m * 3 + 1]; g.cz = in1[m * 3 + 2];
+    }
+    for (int f = fl; f < deg; f += kFreqLanes) {
+      const float scale = (float)(1u << f);  // .cu:196
+      float* e = tile + ls * P + f * 6;
+      ipe_pair(g.mx, g.cx, scale, e[0], e[3]);
+      ipe_pair(g.my, g.cy, scale, e[1], e[4]);
+      ipe_pair(g.mz, g.cz, scale, e[2], e[5]);
+    }
+  }
+  __syncthreads();
+  const int rows = (int)min((long)kTileSamples, M - m0);
+  const int n = rows * P;
+  if (enc_f32) {  // rows are contiguous in global memory: one linear, 128-bit coalesced copy
+    float* dst = enc_f32 + m0 * P;
+    if ((P & 3) == 0) {
+      for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(tile + i);
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = tile[i];
+    }
+  }
+  if (hi) {  // bf16 split planes: x ~= hi + lo  (lo optional)
+    for (int i = threadIdx.x * 2; i < n; i += blockDim.x * 2) {
+      const int row = i / P, col = i % P;  // P even, so (col, col+1) stay in one row
+      const float a = tile[i], b = tile[i + 1];
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      const long off = (m0 + row) * pitch_h + col;
+      *reinterpret_cast<__nv_bfloat162*>(hi + off) = __nv_bfloat162(ah, bh);
+      if (lo)
+        *reinterpret_cast<__nv_bfloat162*>(lo + off) =
+            __nv_bfloat162(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+    }
+    // zero the K padding columns [P, pitch_h) once per row so padded K-blocks contribute nothing
+    const int padc = pitch_h - P;
+    for (int i = threadIdx.x; i < rows * padc; i += blockDim.x) {
+      const long off = (m0 + i / padc) * pitch_h + P + i % padc;
+      hi[off] = __float2bfloat16_rn(0.f);
+      if (lo) lo[off] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+// direction PE per SAMPLE: [d, sin(2^0 d), cos(2^0 d), ...] (SN/MipHelpers.cs:337-356, A-D10), from the
+// per-ray direction.  One thread per (sample, scale j in [-1, deg)).
+__global__ void k_encode_dir(const float* __restrict__ d, long M, int S, int deg, float* __restrict__ f32,
+                             int pitch_f, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                             int pitch_h) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = deg + 1;
+  if (idx >= M * per) return;
+  const long m = idx / per;
+  const int j = (int)(idx % per) - 1;
+  const int r = (int)(m / S);
+  const float x = d[r * 3], y = d[r * 3 + 1], z = d[r * 3 + 2];
+  float v[6];
+  int col, cnt;
+  if (j < 0) { v[0] = x; v[1] = y; v[2] = z; col = 0; cnt = 3; }
+  else {
+    const float sc = (float)(1u << j);
+    sincosf(x * sc, &v[0], &v[3]); sincosf(y * sc, &v[1], &v[4]); sincosf(z * sc, &v[2], &v[5]);
+    col = 3 + 6 * j; cnt = 6;
+  }
+  const int Dd = 3 + 6 * deg;
+  for (int i = 0; i < cnt; i++) {
+    if (f32) f32[m * pitch_f + col + i] = v[i];
+    if (hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+      hi[m * pitch_h + col + i] = h;
+      if (lo) lo[m * pitch_h + col + i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+    }
+  }
+  if (j < 0) {  // zero the padding columns
+    if (f32) for (int c = Dd; c < pitch_f; c++) f32[m * pitch_f + c] = 0.f;
+    if (hi) for (int c = Dd; c < pitch_h; c++) { hi[m * pitch_h + c] = __float2bfloat16_rn(0.f); if (lo) lo[m * pitch_h + c] = __float2bfloat16_rn(0.f); }
+  }
+}
+
+}  // namespace
+
+int launch_cast_rays(const float* t, const float* o, const float* d, const float* radii, int R, int S,
+                     float* means, float* covs, cudaStream_t st) {
+  const long M = (long)R * S;
+  k_cast_rays<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(t, o, d, radii, R, S, means, covs);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_encode_input_data(const float* means, const float* covs, const float* dirs, float* enc_pos,
+                             float* enc_dir, int R, int S, int deg_point, int deg_view, cudaStream_t st) {
+  const long M = (long)R * S;
+  const size_t smem = (size_t)kTileSamples * 6 * deg_point * sizeof(float);
+  k_encode_pos<false><<<(unsigned)cdiv(M, kTileSamples), kTileSamples * kFreqLanes, smem, st>>>(
+      means, covs, nullptr, nullptr, nullptr, M, S, deg_point, enc_pos, nullptr, nullptr, 0);
+  NERF_CHECK_LAUNCH();
+  if (enc_dir) {
+    const long n = M * (deg_view + 1);
+    k_encode_dir<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(dirs, M, S, deg_view, enc_dir, 3 + 6 * deg_view, nullptr,
+                                                         nullptr, 0);
+    NERF_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int launch_cast_encode_fused(const float* t, const float* o, const float* d, const float* radii, int R, int S,
+                             int deg_point, int deg_view, EncodeOut out, cudaStream_t st) {
+  const long M = (long)R * S;
+  const size_t smem = (size_t)kTileSamples * 6 * deg_point * sizeof(float);
+  k_encode_pos<true><<<(unsigned)cdiv(M, kTileSamples), kTileSamples * kFreqLanes, smem, st>>>(
+      t, nullptr, o, d, radii, M, S, deg_point, out.enc_pos_f32, out.pos_hi, out.pos_lo, out.pos_pitch_h);
+  NERF_CHECK_LAUNCH();
+  if (out.enc_dir_f32 || out.dir_hi) {
+    const long n = M * (deg_view + 1);
+    k_encode_dir<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(d, M, S, deg_view, out.enc_dir_f32, out.dir_pitch_f32,
+                                                         out.dir_hi, out.dir_lo, out.dir_pitch_h);
+    NERF_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace nerf

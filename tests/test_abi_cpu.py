@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/nerfb200.h
+declares, its config struct matches the Python mirror, and — with no GPU — every constructor fails loudly
+instead of falling back to a CPU path."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+import nerf_or_nothing_b200 as nb
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    hdr = (ROOT / "include" / "nerfb200.h").read_text()
+    names = set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", hdr))
+    names.discard("nerf_output_gradient_cb")
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    l = nb.lib()
+    names = _declared()
+    assert len(names) >= 50
+    missing = [n for n in sorted(names) if not hasattr(l, n)]
+    assert not missing, missing
+    assert names == set(nb.EXPORTED_SYMBOLS)
+
+
+def test_config_struct_layout_and_defaults():
+    c = nb.default_config()
+    # reference compile-time constants: ANU/helpers.h:16-20, ANU/AcceleratedMLP.h:10-19
+    assert (c.n_rays, c.n_samples, c.n_levels) == (1024, 128, 2)
+    assert (c.net_depth, c.net_width, c.net_depth_condition, c.net_width_condition, c.skip_layer) == (8, 256, 1, 128, 4)
+    assert (c.deg_point, c.deg_view) == (16, 4)
+    assert abs(c.coarse_loss_mult - 0.1) < 1e-7 and abs(c.resample_padding - 0.01) < 1e-7
+    assert c.density_bias == 0.0 and c.rgb_padding == 0.0 and c.white_bkgd == 1
+    assert c.seed == 7 and ctypes.sizeof(c) == 96
+
+
+def test_header_cites_reference_for_every_group():
+    hdr = (ROOT / "include" / "nerfb200.h").read_text()
+    for cite in ("ANU/AcceleratedMipNeRF.cpp:52-144", "ANU/AcceleratedMLP.cpp:214-255", "ANU/AcceleratedMLP.cpp:256-321",
+                 "ANU/AcceleratedAdamOptimizer.h:5-20", "ANU/AcceleratedGradientCalculator.h:8-17",
+                 "ANU/OutputRetriever.h:7-11", ".cu:318-344", ".cu:362-402", ".cu:403-416", ".cu:187-221", ".cu:292-317"):
+        assert cite in hdr, cite
+
+
+def test_no_cpu_fallback_without_gpu():
+    n = ctypes.c_int()
+    nb.lib().nerf_device_count(ctypes.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(nb.NerfError, match="no CPU path"):
+        nb.AcceleratedMipNeRF()
+    with pytest.raises(nb.NerfError, match="no CPU path"):
+        nb.AcceleratedAdamOptimizer([16, 4])
+    with pytest.raises(nb.NerfError, match="no CPU path"):
+        nb.AcceleratedGradientCalculator(8)
+    # per-stage entry points refuse too (null pointers are never dereferenced without a device)
+    assert nb.lib().nerf_adam_optimizer_step(None, None, None, None, 0.1, 0.9, 0.999, 1.0, 1.0, 4, 0) == 100002
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "nerf_or_nothing_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".h") and p.is_file():
+            txt = p.read_text()
+            assert "oracle/" not in txt.replace("test oracle", "") or "never" in txt or "oracle draws" in txt, p
+            assert "import oracle" not in txt and "from oracle" not in txt, p
+
+
+def test_lr_schedule_matches_oracle():
+    from oracle import oracle as orc
+
+    for step in (0, 1, 100, 2500, 50000, 1000000):
+        assert abs(nb.learning_rate_decay(step) - orc.learning_rate_decay(step)) <= 1e-6 * orc.learning_rate_decay(step) + 1e-12
