@@ -35,3 +35,14 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    try:
+        from tests import gpu_util
+
+        gpu_util.release()
+    except Exception:
+        pass

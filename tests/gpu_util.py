@@ -8,8 +8,17 @@ import nerf_or_nothing_b200 as nb
 from oracle import oracle as orc
 
 
+_KEEP = []  # device tensors stay alive until the end of the test: `ptr(dev(x))` must not dangle
+
+
 def dev(a, dtype=np.float32):
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+    _KEEP.append(t)
+    return t
+
+
+def release():
+    _KEEP.clear()
 
 
 def empty(*shape):

