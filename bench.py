@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — train rays/sec (fwd + bwd + Adam) of the MipNeRF hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|fp32_tc|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic 800x800 Blender-shape scene, 4096-ray batch PER GPU, 128+128 samples,
+8x256 MipNeRF MLP (546 948 params), fp32 training.  One "step" = one pass of the hot path over one ray batch:
+sample t -> cast_rays+IPE -> MLP fwd -> compositing (both levels) -> MSE gradient -> compositing bwd -> MLP bwd ->
+[NCCL allreduce of the 2.19 MB gradient when N > 1] -> Adam.  Rays shard across ranks (weak scaling: 4096 rays/GPU;
+N=8 is the 32 768-ray global batch of configs[2]).
+
+`value`  device-resident inputs, timed with CUDA events on the library's stream, max over ranks.
+`e2e`    the same steps through the reference-facing call with HOST arrays (H2D inside, loss read back each step).
+`roofline` the dominant kernel family, timed live inside the timed region with in-stream CUDA events.
+`cpu_baseline` / `--impl reference`: the CPU restatement of the reference's C# path (oracle/, kind "port" — the C#
+cannot be built here), all host threads, on a bounded ray sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+RAYS_PER_GPU = 4096
+N_SAMPLES = 128
+METRIC = "train rays/sec (fwd+bwd+Adam)"
+UNIT = "rays/s"
+
+
+def model_kw():
+    return dict(n_samples=N_SAMPLES, net_depth=8, net_width=256, net_depth_condition=1, net_width_condition=128,
+                skip_layer=4, deg_point=16, deg_view=4)
+
+
+def layer_table():
+    D, W, Wc, P, Dd = 8, 256, 128, 96, 27
+    layers = [(W, P, 0)] + [(W, W, P if i % 4 == 0 else 0) for i in range(1, D)] + [(1, W, 0), (Wc, W, Dd), (3, Wc, 0)]
+    return layers
+
+
+def algorithmic_work(R, S, levels=2):
+    """Per-step algorithmic FLOPs / bytes of each kernel family."""
+    M = R * S * levels
+    lay = layer_table()
+    dense = [l for l in lay if l[0] > 4]
+    heads = [l for l in lay if l[0] <= 4]
+    fwd = 2 * M * sum(o * (a + b) for o, a, b in dense)
+    wgrad = fwd
+    dgrad = 2 * M * sum(o * a for i, (o, a, b) in enumerate(dense) if i > 0)  # no gradient into the encodings
+    n_params = sum(o * (a + b) + o for o, a, b in lay)
+    return {
+        "mlp_fwd_gemm": ("TFLOP/s", fwd), "mlp_wgrad_gemm": ("TFLOP/s", wgrad), "mlp_dgrad_gemm": ("TFLOP/s", dgrad),
+        "mlp_fwd_heads": ("GB/s", M * 4 * (256 + 128 + 4)), "mlp_bwd_heads": ("GB/s", M * 4 * (2 * (256 + 128) + 128 + 4 + 4)),
+        "composite_fwd": ("GB/s", M * 24 + levels * R * 32), "composite_bwd": ("GB/s", M * 36 + levels * R * 24),
+        "cast_rays+encode": ("GB/s", M * (4 + 96 * 4 + 28 * 4) + levels * R * 32),
+        "adam": ("GB/s", n_params * 28), "sample_t_vals": ("GB/s", M * 8), "loss_gradient": ("GB/s", levels * R * 40),
+    }, n_params
+
+
+def config_dict(R, world, precision):
+    n_params = sum(o * (a + b) + o for o, a, b in layer_table())
+    return {"workload": f"configs[1]: 800x800 Blender-shape scene, {R}-ray batch per GPU, {N_SAMPLES}+{N_SAMPLES} samples, "
+                        f"8x256 MipNeRF MLP ({n_params} params), fp32 training",
+            "rays_per_gpu": R, "global_batch": world * R, "precision": precision,
+            "parallelism": f"ray-sharded dp{world}" if world > 1 else "single GPU",
+            "l2": "per-step working set (activation cache, >4 GB) exceeds the 126 MB L2; no flush needed"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        if not sm:  # region shorter than the sampling period: take every sample we have
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+
+def cpu_port_rate(target_seconds, rank0=True):
+    """rays/s of the CPU port (oracle) for one training step (gradient + Adam) on a bounded ray sample."""
+    from oracle import oracle as orc  # the ONLY use of oracle/ in this file: the CPU baseline being measured
+    from nerf_or_nothing_b200.scene import synthetic_rays
+
+    ocfg = orc.default_config(**model_kw())
+    params = orc.init_params(ocfg, 7)
+    threads = orc.max_threads()
+
+    def run(n, seed):
+        rays, pix = synthetic_rays(n, width=800, height=800, seed=seed)
+        u = np.stack([orc.sampling_uniforms(99, 0, lv, 0, n, N_SAMPLES + 1) for lv in range(2)])
+        t0 = time.perf_counter()
+        o = orc.train_gradient(ocfg, params, rays, pix, u, prec="f32")
+        orc.adam_step(params, o["grads"], np.zeros_like(params), np.zeros_like(params), 5e-4, 1, 0, prec="f32")
+        return time.perf_counter() - t0
+
+    probe_n = max(threads, 8)
+    dt = run(probe_n, 1)
+    n = int(max(probe_n, min(4096, target_seconds * probe_n / max(dt, 1e-3))))
+    n = max(threads, n // threads * threads)
+    return run, n, threads
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU path (C# restated in C, oracle/ — kind "port") on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    run, n, threads = cpu_port_rate(min(12.0, budget))
+    for i in range(args.warmup):
+        run(n, 10 + i)
+    t = [run(n, 100 + i) for i in range(args.steps)]
+    ms = 1e3 * float(np.mean(t))
+    value = n / (ms / 1e3)
+    sample = f"{n} of {RAYS_PER_GPU} rays per step (same config), gradient + Adam, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": dict(config_dict(args.rays, max(1, args.gpus), args.precision), rays_timed_per_step=n),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+
+def ours_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import nerf_or_nothing_b200 as nb
+    from nerf_or_nothing_b200.scene import synthetic_rays
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    R, S = args.rays, N_SAMPLES
+    cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[args.precision], device=local, **model_kw())
+    model = nb.AcceleratedMipNeRF(cfg)
+    opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes(), device=local)
+    if world > 1:
+        idt = torch.zeros(nb.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        model.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    stream = torch.cuda.ExternalStream(model.stream())
+
+    # a pool of distinct ray batches: host copies for e2e, device copies for `value`
+    pool = 4
+    host_batches, dev_batches = [], []
+    for b in range(pool):
+        rays, pix = synthetic_rays(R, width=800, height=800, seed=2024 + 1000 * rank + b)
+        hb = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"], pix)
+        host_batches.append(hb)
+        dev_batches.append(tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb))
+    lr = nb.learning_rate_decay(1000)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def dev_step(i):
+        model.train_step_dev(opt, *dev_batches[i % pool], R, lr, want_loss=False)
+
+    for i in range(args.warmup):
+        dev_step(i)
+    model.set_profiling(True)
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = model.launch_count()
+    t0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        dev_step(i)
+    e1.record(stream)
+    model.synchronize()
+    t1 = time.time()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = model.launch_count() - l0
+    clk = clocks.stop(t0, t1)
+    prof = model.read_profile()
+    model.set_profiling(False)
+    tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt.item()) / args.steps
+    value = world * R / (ms_step / 1e3)
+
+    # e2e: host arrays in, loss out, every step
+    for i in range(min(3, args.warmup)):
+        model.train_step(opt, *host_batches[i % pool], lr, want_loss=True)
+    sync_all()
+    w0 = time.perf_counter()
+    loss = 0.0
+    for i in range(args.steps):
+        loss = model.train_step(opt, *host_batches[i % pool], lr, want_loss=True)
+    model.synchronize()
+    w1 = time.perf_counter()
+    te = torch.tensor([(w1 - w0) * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * R / (float(te.item()) / args.steps / 1e3)
+    h2d = R * 13 * 4
+    d2h = (1 + cfg.n_levels) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tc_peak, peak_src = peaks()
+    work, n_params = algorithmic_work(R, S)
+    kernels = {}
+    for name, (ms, nl) in prof.items():
+        unit, amount = work.get(name, ("GB/s", 0))
+        per_step_ms = ms / args.steps
+        ach = (amount / 1e12 if unit == "TFLOP/s" else amount / 1e9) / (per_step_ms / 1e3) if per_step_ms > 0 and amount else None
+        peak = tc_peak if unit == "TFLOP/s" else hbm_peak
+        kernels[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": nl / args.steps,
+                         "achieved": None if ach is None else round(ach, 2), "unit": unit,
+                         "frac": None if ach is None else round(ach / peak, 4)}
+    top = max((k for k in kernels if kernels[k]["achieved"] is not None), key=lambda k: kernels[k]["ms_per_step"])
+    tk = kernels[top]
+    roofline = {"kernel": top, "bound": "tensor" if tk["unit"] == "TFLOP/s" else "hbm", "achieved": tk["achieved"],
+                "peak": tc_peak if tk["unit"] == "TFLOP/s" else hbm_peak, "unit": tk["unit"], "frac": tk["frac"],
+                "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": round(tk["ms_per_step"] / max(1.0, tk["launches_per_step"]), 5),
+                "share_of_step": round(tk["ms_per_step"] / ms_step, 4)}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        run, n, threads = cpu_port_rate(15.0)
+        dt = run(n, 7)
+        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n} of {R} rays, one training step (gradient + Adam), fp32, {dt:.1f} s"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "fp32_tc": "f32 (bf16x3 tensor-core split)", "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": config_dict(R, world, args.precision),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": cpu_baseline, "loss_last_step": loss,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NERF_BENCH_PRECISION", "fp32"), choices=["fp32", "fp32_tc", "bf16"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours_arm(args)
+
+
+if __name__ == "__main__":
+    main()
