@@ -1,0 +1,71 @@
+// gemm_tc.cuh — interface of the tcgen05/TMEM GEMM used by the tensor-core MLP engine (mlp_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kernels.cuh"
+
+namespace nerf {
+
+constexpr int TC_MAX_KB = 30;
+
+// One launch = one output tile per CTA:  C(128 x BN) = sum over k-blocks of A_blk * B_blk^T, fp32 accumulate in TMEM.
+// Operands are bf16 "planes" in global memory (x ~= hi [+ lo]) described by TMA tensor maps; a k-block names
+// which A plane / B plane it multiplies, so conjoined inputs (two K segments) and the bf16x3 split passes
+// (hi*hi + hi*lo + lo*hi) are just longer k-block lists over the same kernel.
+struct alignas(64) TcParams {
+  CUtensorMap maps[8];  // [0..3] A-side planes, [4..7] B-side planes
+  // ---- K-major mode (forward, dgrad): grid = (ceil(M/128), ceil(N/BN))
+  struct KB { int8_t a, b; int16_t a_col, b_col; } kb[TC_MAX_KB];
+  int n_kb;
+  // ---- MN-major mode (wgrad): grid = (out_rows/128, ceil(out_cols/BN), splits); reduction over the rows of the planes
+  int n_pass;
+  int8_t pass_a[4], pass_b[4];
+  int a_col0;      // column of the A plane where this launch's output rows start (usually 0)
+  int split_len;   // reduction rows per split (multiple of 64)
+  long red_len;    // total reduction length (rows of the planes = samples)
+  // ---- common
+  long M;          // K-major: rows of the output
+  int BN;          // UMMA N = tile width (multiple of 16, <= 256)
+  int n_valid;     // columns of the output that exist (stores are clipped to it)
+  int rows_valid;  // MN-major: output rows that exist
+  int n_stages;
+  // ---- epilogue
+  int epi;  // 0: forward (bias, activation, planes out); 1: dgrad (rank-1, relu mask, planes out); 2: fp32 partial
+  const float* bias;
+  int act;
+  const float* r1;            // [M]
+  const float* v1;            // [n_valid]
+  const __nv_bfloat16* mask;  // [M, ld_mask] (> 0 keeps)
+  int ld_mask;
+  __nv_bfloat16 *out_hi, *out_lo;  // lo may be null (bf16 mode)
+  int ld_out;
+  float* out_f32;     // epi 2: [split][rows][ld_f32]
+  int ld_f32;
+  long split_stride;  // floats between splits
+};
+
+int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);
+int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st);
+int tc_smem_bytes(int BN, int n_stages);
+int tc_pick_stages(int BN, int n_kblocks);
+
+// helpers on bf16 planes ------------------------------------------------------------------------------
+// fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]
+int launch_f32_to_planes(const float* src, int src_pitch, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                         int dst_pitch, int dst_cols, bool transpose, long dst_rows_t, cudaStream_t st);
+// heads on planes (N <= 4)
+int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, const float* W, const float* b,
+                           float* Y, long M, int N, int K, cudaStream_t st);
+int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const __nv_bfloat16* mask, int ld_mask,
+                             __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st);
+int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
+                             long M, int N, int K, float* workspace, cudaStream_t st);
+// db[n] += sum_m (hi + lo)[m, n]
+int launch_colsum_planes(const __nv_bfloat16* h, const __nv_bfloat16* l, int ld, long M, int N, float* db, float* workspace,
+                         cudaStream_t st);
+// out[i*ldo + coff + j] += sum_z ws[z*stride + i*ldw + j]
+int launch_reduce_partials(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo,
+                           int coff, cudaStream_t st);
+
+}  // namespace nerf

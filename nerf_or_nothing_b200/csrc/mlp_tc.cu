@@ -1,5 +1,345 @@
-// mlp_tc.cu — tcgen05/TMEM MLP engine (placeholder until gemm_tc.cu lands in this round).
+// mlp_tc.cu — tensor-core MLP engine: every dense layer of the MipNeRF MLP forward, dgrad and wgrad
+// on the tcgen05 GEMM of gemm_tc.cu.  NERF_PRECISION_BF16_TC keeps one bf16 plane per tensor;
+// NERF_PRECISION_FP32_TC keeps hi/lo planes (x = hi + lo) and multiplies with the 3-term split.
+//
+// Orchestration is the same chain as AcceleratedMLP::get_output / get_gradient (ANU/AcceleratedMLP.cpp:214-321):
+//   forward   Y_i planes are written by the GEMM epilogue (bias + ReLU fused) and are at once the next layer's
+//             operand, the ReLU mask of the backward pass and the wgrad operand — nothing else is cached;
+//   backward  dZ planes ping-pong between two buffers; dgrad's epilogue fuses the ReLU mask of the layer below and
+//             the density head's rank-1 contribution; wgrad reads dZ and X "transposed" (MN-major UMMA operands),
+//             splits the sample dimension over CTAs and reduces the fp32 partials in a fixed order.
+// The N=1 / N=3 heads stay on CUDA cores (too thin for a UMMA tile) but read the same planes.
+#include <algorithm>
+#include <cstring>
+
+#include "gemm_tc.cuh"
 #include "mlp.cuh"
+
 namespace nerf {
-MlpEngine* make_tc_mlp(bool) { return nullptr; }
+namespace {
+
+struct Plane {
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  int pitch = 0;  // elements per row (multiple of 64)
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+class TcMlp : public MlpEngine {
+ public:
+  explicit TcMlp(bool split3) : split_(split3) {}
+  ~TcMlp() override {
+    for (void* p : owned_) cudaFree(p);
+  }
+
+  int init(const MlpShape& shape, long max_rows, int n_levels) override {
+    s_ = shape; max_rows_ = max_rows;
+    if (s_.W % 64 || s_.Wc % 64 || s_.W > 512 || s_.Wc > 512) {
+      set_error("tensor-core MLP needs widths that are multiples of 64 and <= 512 (got %d / %d)", s_.W, s_.Wc);
+      return 100001;
+    }
+    pos_pitch_ = round_up(s_.P, 64);
+    dir_pitch_ = round_up(s_.Dd, 64);
+    levels_.resize(n_levels);
+    for (auto& lv : levels_) {
+      NERF_TRY(alloc_plane(&lv.enc_pos, max_rows, pos_pitch_));
+      NERF_TRY(alloc_plane(&lv.enc_dir, max_rows, dir_pitch_));
+      lv.acts.resize(s_.D + s_.C);
+      for (int i = 0; i < s_.D + s_.C; i++) NERF_TRY(alloc_plane(&lv.acts[i], max_rows, i < s_.D ? s_.W : s_.Wc));
+    }
+    const int mw = s_.W > s_.Wc ? s_.W : s_.Wc;
+    NERF_TRY(alloc_plane(&dz_[0], max_rows, mw));
+    NERF_TRY(alloc_plane(&dz_[1], max_rows, mw));
+    wp_.resize(s_.L); wtp_.resize(s_.L);
+    size_t ws = 1 << 20;
+    for (int l = 0; l < s_.L; l++) {
+      const LayerInfo& L = s_.layers[l];
+      if (L.out <= 4) { ws = std::max(ws, (size_t)cdiv(max_rows, 1024) * L.out * (L.in_a + 1) + 64); continue; }
+      NERF_TRY(alloc_plane(&wp_[l], L.out, round_up(L.in_a + L.in_b, 64)));
+      if (needs_dgrad(l)) NERF_TRY(alloc_plane(&wtp_[l], L.in_a, L.out));
+      for (int src = 0; src < 2; src++) {
+        const int K = src == 0 ? L.in_a : L.in_b;
+        if (K <= 0) continue;
+        int splits; long split_len;
+        wgrad_split(L.out, K, max_rows, &splits, &split_len);
+        ws = std::max(ws, (size_t)splits * L.out * round_up(K, 4));
+      }
+      ws = std::max(ws, (size_t)cdiv(max_rows, 2048) * L.out + 64);
+    }
+    NERF_CUDA(cudaMalloc(&ws_, ws * sizeof(float)));
+    owned_.push_back(ws_);
+    bytes_ += ws * sizeof(float);
+    return 0;
+  }
+
+  EncodeOut encode_targets(int level) override {
+    EncodeOut o;
+    o.pos_hi = levels_[level].enc_pos.hi; o.pos_lo = levels_[level].enc_pos.lo; o.pos_pitch_h = pos_pitch_;
+    o.dir_hi = levels_[level].enc_dir.hi; o.dir_lo = levels_[level].enc_dir.lo; o.dir_pitch_h = dir_pitch_;
+    return o;
+  }
+
+  int import_encodings(int level, const float* enc_pos, const float* enc_dir, long M, cudaStream_t st) override {
+    Level& lv = levels_[level];
+    NERF_TRY(launch_f32_to_planes(enc_pos, s_.P, M, s_.P, lv.enc_pos.hi, lv.enc_pos.lo, pos_pitch_, pos_pitch_, false, 0, st));
+    return launch_f32_to_planes(enc_dir, s_.Dd, M, s_.Dd, lv.enc_dir.hi, lv.enc_dir.lo, dir_pitch_, dir_pitch_, false, 0, st);
+  }
+
+  // refresh the bf16 weight planes (and their transposes for dgrad) from the fp32 master parameters
+  int prepare(const float* params, cudaStream_t st) override {
+    ProfScope ps(PC_CAST, st);
+    for (int l = 0; l < s_.L; l++) {
+      const LayerInfo& L = s_.layers[l];
+      if (L.out <= 4) continue;
+      const int K = L.in_a + L.in_b;
+      NERF_TRY(launch_f32_to_planes(params + L.w_off, K, L.out, K, wp_[l].hi, wp_[l].lo, wp_[l].pitch, wp_[l].pitch, false, 0, st));
+      if (needs_dgrad(l))  // WT[k, n] = W[n, k] for k < in_a
+        NERF_TRY(launch_f32_to_planes(params + L.w_off, K, L.out, L.in_a, wtp_[l].hi, wtp_[l].lo, wtp_[l].pitch, L.out, true, L.in_a, st));
+    }
+    return 0;
+  }
+
+  int forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
+    Level& lv = levels_[level];
+    const int D = s_.D, C = s_.C;
+    const Plane* h = &lv.enc_pos;
+    int kh = s_.P;
+    for (int i = 0; i < D; i++) {
+      const LayerInfo& L = s_.layers[i];
+      ProfScope ps(PC_MLP_FWD, st);
+      NERF_TRY(gemm_fwd(*h, kh, L.in_b ? &lv.enc_pos : nullptr, L.in_b, L.in_a, wp_[i], params + L.b_off, lv.acts[i], M, L.out, st));
+      h = &lv.acts[i]; kh = s_.W;
+    }
+    {
+      const LayerInfo& L = s_.layers[D];
+      ProfScope ps(PC_MLP_HEADS_FWD, st);
+      NERF_TRY(launch_thin_fwd_planes(h->hi, h->lo, h->pitch, params + L.w_off, params + L.b_off, raw_density, M, 1, s_.W, st));
+    }
+    const Plane* c = h;
+    int kc = s_.W;
+    for (int i = 0; i < C; i++) {
+      const int l = D + 1 + i;
+      const LayerInfo& L = s_.layers[l];
+      ProfScope ps(PC_MLP_FWD, st);
+      NERF_TRY(gemm_fwd(*c, kc, L.in_b ? &lv.enc_dir : nullptr, L.in_b, L.in_a, wp_[l], params + L.b_off, lv.acts[D + i], M, L.out, st));
+      c = &lv.acts[D + i]; kc = s_.Wc;
+    }
+    {
+      const LayerInfo& L = s_.layers[D + C + 1];
+      ProfScope ps(PC_MLP_HEADS_FWD, st);
+      NERF_TRY(launch_thin_fwd_planes(c->hi, c->lo, c->pitch, params + L.w_off, params + L.b_off, raw_rgb, M, 3, s_.Wc, st));
+    }
+    return 0;
+  }
+
+  int backward(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
+               cudaStream_t st) override {
+    Level& lv = levels_[level];
+    const int D = s_.D, C = s_.C, W = s_.W, Wc = s_.Wc;
+    Plane* cur = &dz_[0];
+    Plane* nxt = &dz_[1];
+    {  // rgb head
+      const LayerInfo& L = s_.layers[D + C + 1];
+      const Plane& x = lv.acts[D + C - 1];
+      ProfScope ps(PC_MLP_HEADS_BWD, st);
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st));
+      NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, x.hi, x.pitch, cur->hi, cur->lo, cur->pitch, st));
+    }
+    for (int i = C - 1; i >= 0; i--) {
+      const int l = D + 1 + i;
+      const LayerInfo& L = s_.layers[l];
+      const Plane& in = i == 0 ? lv.acts[D - 1] : lv.acts[D + i - 1];
+      {
+        ProfScope ps(PC_MLP_WGRAD, st);
+        NERF_TRY(gemm_wgrad(*cur, in, L.in_a, L.in_b ? &lv.enc_dir : nullptr, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
+      }
+      ProfScope ps(PC_MLP_DGRAD, st);
+      if (i > 0) {
+        NERF_TRY(gemm_dgrad(*cur, wtp_[l], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.acts[D + i - 1], st));
+      } else {
+        const LayerInfo& Ld = s_.layers[D];
+        NERF_TRY(gemm_dgrad(*cur, wtp_[l], *nxt, M, L.out, L.in_a, d_raw_density, params + Ld.w_off, lv.acts[D - 1], st));
+      }
+      Plane* t = cur; cur = nxt; nxt = t;
+    }
+    {
+      const LayerInfo& L = s_.layers[D];
+      const Plane& x = lv.acts[D - 1];
+      ProfScope ps(PC_MLP_HEADS_BWD, st);
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_density, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 1, W, ws_, st));
+    }
+    for (int i = D - 1; i >= 0; i--) {
+      const LayerInfo& L = s_.layers[i];
+      const Plane& in = i == 0 ? lv.enc_pos : lv.acts[i - 1];
+      {
+        ProfScope ps(PC_MLP_WGRAD, st);
+        NERF_TRY(gemm_wgrad(*cur, in, L.in_a, L.in_b ? &lv.enc_pos : nullptr, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
+      }
+      if (i > 0) {
+        ProfScope ps(PC_MLP_DGRAD, st);
+        NERF_TRY(gemm_dgrad(*cur, wtp_[i], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.acts[i - 1], st));
+        Plane* t = cur; cur = nxt; nxt = t;
+      }
+    }
+    return 0;
+  }
+
+  size_t bytes_allocated() const override { return bytes_; }
+
+ private:
+  struct Level {
+    Plane enc_pos, enc_dir;
+    std::vector<Plane> acts;
+  };
+
+  bool needs_dgrad(int l) const { return (l > 0 && l < s_.D) || (l > s_.D && l <= s_.D + s_.C); }
+
+  int alloc_plane(Plane* p, long rows, int pitch) {
+    const size_t bytes = (size_t)rows * pitch * sizeof(__nv_bfloat16);
+    NERF_CUDA(cudaMalloc(&p->hi, bytes));
+    owned_.push_back(p->hi);
+    NERF_CUDA(cudaMemset(p->hi, 0, bytes));
+    bytes_ += bytes;
+    if (split_) {
+      NERF_CUDA(cudaMalloc(&p->lo, bytes));
+      owned_.push_back(p->lo);
+      NERF_CUDA(cudaMemset(p->lo, 0, bytes));
+      bytes_ += bytes;
+    }
+    p->pitch = pitch;
+    return 0;
+  }
+
+  // passes of the split product: (A plane, B plane) with 0 = hi, 1 = lo
+  int passes(int (*pa)[2]) const {
+    pa[0][0] = 0; pa[0][1] = 0;
+    if (!split_) return 1;
+    pa[1][0] = 0; pa[1][1] = 1;
+    pa[2][0] = 1; pa[2][1] = 0;
+    return 3;
+  }
+
+  // Y = relu([A1|A2] W^T + b): K-major, grid (M/128, N/BN)
+  int gemm_fwd(const Plane& a1, int k1, const Plane* a2, int k2, int w_col2, const Plane& w, const float* bias, const Plane& out,
+               long M, int N, cudaStream_t st) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = N > 256 ? 256 : N;
+    NERF_TRY(tc_make_tmap(&p.maps[0], a1.hi, M, a1.pitch, a1.pitch, 128));
+    if (split_) NERF_TRY(tc_make_tmap(&p.maps[1], a1.lo, M, a1.pitch, a1.pitch, 128));
+    if (a2) {
+      NERF_TRY(tc_make_tmap(&p.maps[2], a2->hi, M, a2->pitch, a2->pitch, 128));
+      if (split_) NERF_TRY(tc_make_tmap(&p.maps[3], a2->lo, M, a2->pitch, a2->pitch, 128));
+    }
+    NERF_TRY(tc_make_tmap(&p.maps[4], w.hi, N, w.pitch, w.pitch, BN));
+    if (split_) NERF_TRY(tc_make_tmap(&p.maps[5], w.lo, N, w.pitch, w.pitch, BN));
+    int pa[3][2];
+    const int np = passes(pa);
+    int n = 0;
+    for (int seg = 0; seg < (a2 ? 2 : 1); seg++) {
+      const int K = seg == 0 ? k1 : k2;
+      const int bcol0 = seg == 0 ? 0 : w_col2;
+      for (int kc = 0; kc < K; kc += 64)
+        for (int q = 0; q < np; q++) {
+          if (n >= TC_MAX_KB) { set_error("tc gemm: too many k-blocks"); return 100001; }
+          p.kb[n].a = (int8_t)(seg * 2 + pa[q][0]);
+          p.kb[n].b = (int8_t)(4 + pa[q][1]);
+          p.kb[n].a_col = (int16_t)kc;
+          p.kb[n].b_col = (int16_t)(bcol0 + kc);
+          n++;
+        }
+    }
+    p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = N; p.n_stages = tc_pick_stages(BN, n);
+    p.epi = 0; p.bias = bias; p.act = ACT_RELU;
+    p.out_hi = out.hi; p.out_lo = out.lo; p.ld_out = out.pitch;
+    return tc_launch(p, false, dim3((unsigned)cdiv(M, 128), (unsigned)cdiv(N, BN), 1), st);
+  }
+
+  // dX[M, k1] = mask(dZ[M,N] * WT^T (+ r1 v1^T)):  A = dZ planes (K-major over n), B = WT planes [k1, N]
+  int gemm_dgrad(const Plane& dz, const Plane& wt, const Plane& out, long M, int N, int k1, const float* r1, const float* v1,
+                 const Plane& mask, cudaStream_t st) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = k1 > 256 ? 256 : k1;
+    NERF_TRY(tc_make_tmap(&p.maps[0], dz.hi, M, N, dz.pitch, 128));
+    if (split_) NERF_TRY(tc_make_tmap(&p.maps[1], dz.lo, M, N, dz.pitch, 128));
+    NERF_TRY(tc_make_tmap(&p.maps[4], wt.hi, k1, N, wt.pitch, BN));
+    if (split_) NERF_TRY(tc_make_tmap(&p.maps[5], wt.lo, k1, N, wt.pitch, BN));
+    int pa[3][2];
+    const int np = passes(pa);
+    int n = 0;
+    for (int kc = 0; kc < N; kc += 64)
+      for (int q = 0; q < np; q++) {
+        if (n >= TC_MAX_KB) { set_error("tc gemm: too many k-blocks"); return 100001; }
+        p.kb[n].a = (int8_t)pa[q][0];
+        p.kb[n].b = (int8_t)(4 + pa[q][1]);
+        p.kb[n].a_col = (int16_t)kc;
+        p.kb[n].b_col = (int16_t)kc;
+        n++;
+      }
+    p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = k1; p.n_stages = tc_pick_stages(BN, n);
+    p.epi = 1; p.r1 = r1; p.v1 = v1; p.mask = mask.hi; p.ld_mask = mask.pitch;
+    p.out_hi = out.hi; p.out_lo = out.lo; p.ld_out = out.pitch;
+    return tc_launch(p, false, dim3((unsigned)cdiv(M, 128), (unsigned)cdiv(k1, BN), 1), st);
+  }
+
+  static void wgrad_split(int N, int K, long M, int* splits, long* split_len) {
+    const int BN = K > 256 ? 256 : round_up(K, 64);
+    const long tiles = cdiv(N, 128) * cdiv(K, BN);
+    long s = cdiv(2 * 148, tiles);
+    const long maxs = cdiv(M, 256);
+    if (s > maxs) s = maxs;
+    if (s < 1) s = 1;
+    *split_len = cdiv(cdiv(M, s), 64) * 64;
+    *splits = (int)cdiv(M, *split_len);
+  }
+
+  // dW[N, k1+k2] += dZ^T [X1|X2]; db += colsum(dZ).  MN-major operands, reduction over the M samples split over CTAs.
+  int gemm_wgrad(const Plane& dz, const Plane& x1, int k1, const Plane* x2, int k2, float* dW, float* db, long M, int N,
+                 cudaStream_t st) {
+    const int ldw = k1 + k2;
+    for (int src = 0; src < 2; src++) {
+      const Plane* x = src == 0 ? &x1 : x2;
+      const int K = src == 0 ? k1 : k2, coff = src == 0 ? 0 : k1;
+      if (!x || K <= 0) continue;
+      TcParams p;
+      memset(&p, 0, sizeof(p));
+      const int BN = K > 256 ? 256 : round_up(K, 64);
+      const int xcols = round_up(K, 64) <= x->pitch ? round_up(K, 64) : x->pitch;
+      NERF_TRY(tc_make_tmap(&p.maps[0], dz.hi, M, N, dz.pitch, 64));
+      if (split_) NERF_TRY(tc_make_tmap(&p.maps[1], dz.lo, M, N, dz.pitch, 64));
+      NERF_TRY(tc_make_tmap(&p.maps[4], x->hi, M, xcols, x->pitch, 64));
+      if (split_) NERF_TRY(tc_make_tmap(&p.maps[5], x->lo, M, xcols, x->pitch, 64));
+      int pa[3][2];
+      p.n_pass = passes(pa);
+      for (int q = 0; q < p.n_pass; q++) { p.pass_a[q] = (int8_t)pa[q][0]; p.pass_b[q] = (int8_t)(4 + pa[q][1]); }
+      int splits; long split_len;
+      wgrad_split(N, K, M, &splits, &split_len);
+      const int ldf = round_up(K, 4);
+      p.split_len = (int)split_len; p.red_len = M; p.BN = BN; p.n_valid = K; p.rows_valid = N;
+      p.n_stages = tc_pick_stages(BN, 1 << 20);
+      p.epi = 2; p.out_f32 = ws_; p.ld_f32 = ldf; p.split_stride = (long)N * ldf;
+      NERF_TRY(tc_launch(p, true, dim3((unsigned)cdiv(N, 128), (unsigned)cdiv(K, BN), (unsigned)splits), st));
+      NERF_TRY(launch_reduce_partials(ws_, splits, p.split_stride, N, K, ldf, dW, ldw, coff, st));
+    }
+    if (db) NERF_TRY(launch_colsum_planes(dz.hi, dz.lo, dz.pitch, M, N, db, ws_, st));
+    return 0;
+  }
+
+  bool split_;
+  MlpShape s_;
+  long max_rows_ = 0;
+  int pos_pitch_ = 0, dir_pitch_ = 0;
+  std::vector<Level> levels_;
+  Plane dz_[2];
+  std::vector<Plane> wp_, wtp_;
+  float* ws_ = nullptr;
+  size_t bytes_ = 0;
+  std::vector<void*> owned_;
+};
+
+}  // namespace
+
+MlpEngine* make_tc_mlp(bool split3) { return new TcMlp(split3); }
+
 }  // namespace nerf
