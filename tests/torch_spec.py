@@ -91,3 +91,24 @@ def total_loss(cfg, shapes, params, rays, pixels, t_levels):
         loss = loss + mult * (lm * ((comp - pixels) ** 2).sum(-1)).sum() / lm.sum()
         comps.append(comp)
     return loss, comps
+
+
+def relu_margin(cfg, shapes, params, enc_pos, enc_dir):
+    """Per-sample min |z| over every hidden (ReLU) unit, in fp64.  A forward perturbation eps flips the ReLU mask of
+    the units with |z| < eps; the gradient is discontinuous there, so gradient parity is only well defined on samples
+    whose margin exceeds the forward error of the path under test."""
+    Ws, bs = layer_views(cfg, shapes, params)
+    D, Cn = cfg.net_depth, cfg.net_depth_condition
+    h = enc_pos
+    margin = torch.full((enc_pos.shape[0],), float("inf"), dtype=enc_pos.dtype)
+    for i in range(D):
+        x = torch.cat([h, enc_pos], -1) if (cfg.skip_layer > 0 and i % cfg.skip_layer == 0 and i > 0) else h
+        z = x @ Ws[i].T + bs[i]
+        margin = torch.minimum(margin, z.abs().min(-1).values)
+        h = torch.relu(z)
+    c = torch.cat([h, enc_dir], -1)
+    for i in range(Cn):
+        z = c @ Ws[D + 1 + i].T + bs[D + 1 + i]
+        margin = torch.minimum(margin, z.abs().min(-1).values)
+        c = torch.relu(z)
+    return margin
