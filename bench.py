@@ -209,11 +209,9 @@ def ours_arm(args):
     model = nb.AcceleratedMipNeRF(cfg)
     opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes(), device=local)
     if world > 1:
-        idt = torch.zeros(nb.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(nb.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        model.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        from nerf_or_nothing_b200 import dist as nd
+
+        nd.attach(model, device="cuda")  # rank 0's NCCL unique id -> every rank; library allreduces the flat gradient
     stream = torch.cuda.ExternalStream(model.stream())
 
     # a pool of distinct ray batches: host copies for e2e, device copies for `value`

@@ -336,7 +336,7 @@ class AcceleratedMipNeRF:
         n, names = C.c_int(), (C.c_char_p * 32)()
         ms, launches = (C.c_double * 32)(), (C.c_long * 32)()
         check(lib().nerf_mipnerf_read_profile(self._h, 32, C.byref(n), names, ms, launches, int(reset)))
-        return {names[i].decode(): (ms[i], launches[i]) for i in range(n.value) if launches[i] > 0}
+        return {names[i].decode(): (ms[i], launches[i]) for i in range(n.value) if launches[i] > 0 or ms[i] > 0}
 
     def launch_count(self):
         n = C.c_long()
