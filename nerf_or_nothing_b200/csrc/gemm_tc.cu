@@ -41,7 +41,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <bool MN_MAJOR>
-__global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __grid_constant__ TcParams p) {
+  constexpr int kTmemCols = MN_MAJOR ? 512 : 256;  // wgrad keeps 16 extra columns for the bias gradient
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], done_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -50,33 +51,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(const __grid_constant__
   const int BN = p.BN;
   const int stage_bytes = kABytes + BN * 128;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ones = smem + (size_t)p.n_stages * stage_bytes;  // MN-major only: 8 KB of bf16 1.0
 
-  // tile coordinates and k-block count
-  long row0;   // K-major: first output row (sample); MN-major: first output row (= column of the A planes)
-  int col0;    // first output column
-  int n_kb;    // pipeline iterations
+  const long row0 = (long)blockIdx.x * 128;  // first output row
+  const int col0 = blockIdx.y * BN;          // first output column
+  int n_kb;                                  // pipeline iterations
   long red0 = 0;
   if (!MN_MAJOR) {
-    row0 = (long)blockIdx.x * 128;
-    col0 = blockIdx.y * BN;
     n_kb = p.n_kb;
   } else {
-    row0 = (long)blockIdx.x * 128;
-    col0 = blockIdx.y * BN;
     red0 = (long)blockIdx.z * p.split_len;
     long red1 = red0 + p.split_len;
     if (red1 > p.red_len) red1 = p.red_len;
     const long nblk = red1 > red0 ? (red1 - red0 + 63) / 64 : 0;
     n_kb = (int)nblk * p.n_pass;
   }
+  const bool want_bias = MN_MAJOR && p.bias_out != nullptr && blockIdx.y == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
+  if (MN_MAJOR) {
+    for (int i = threadIdx.x; i < 2048; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
   if (warp == 4) {
-    tmem_alloc<256>(&tmem_base_smem);
+    tmem_alloc<kTmemCols>(&tmem_base_smem);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < 8; i++) prefetch_tmap(&p.maps[i]);
@@ -116,6 +118,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, BN, MN_MAJOR, MN_MAJOR);
+      const uint32_t idesc_bias = make_idesc_bf16(128, 16, true, true);
+      const uint32_t ones_base = smem_u32(ones);
+      bool bias_started = false;
       for (int i = 0; i < n_kb; i++) {
         const int s = i % p.n_stages;
         const uint32_t ph = (i / p.n_stages) & 1;
@@ -135,29 +140,39 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(const __grid_constant__
           }
           umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
+        if (MN_MAJOR && want_bias && p.pass_b[i % p.n_pass] == 4) {
+          // db[n] += sum_m dZ[m, n]: the same A tile against a constant tile of ones (N = 16), TMEM columns 256..271
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint64_t da = make_smem_desc(a_base + k * 2048, 8192, 1024);
+            const uint64_t d1 = make_smem_desc(ones_base + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base + 256, da, d1, idesc_bias, (bias_started || k > 0) ? 1u : 0u);
+          }
+          bias_started = true;
+        }
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
       }
       umma_commit(&done_bar);  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3: TMEM lanes 32w..32w+31)
-    const long row = row0 + threadIdx.x;
+    const int tr = threadIdx.x;  // row inside the tile
+    const long row = row0 + tr;
     if (n_kb > 0) {
       mbar_wait(&done_bar, 0);
       tc_fence_after_sync();
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (n_kb > 0) {
-        tmem_ld_32x32(t_lane + c0, r);
-        tmem_ld_wait();
-      } else {
+    if (MN_MAJOR) {
+      // raw fp32 partial: out[split][row][col] (+ the bias column)
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        if (n_kb > 0) { tmem_ld_32x32(t_lane + c0, r); tmem_ld_wait(); }
+        else {
 #pragma unroll
-        for (int j = 0; j < 32; j++) r[j] = 0u;
-      }
-      const int col = col0 + c0;
-      if (p.epi == 2) {  // raw fp32 partial: out[split][row][col]
+          for (int j = 0; j < 32; j++) r[j] = 0u;
+        }
+        const int col = col0 + c0;
         if (row < p.rows_valid) {
           float* dst = p.out_f32 + (long)blockIdx.z * p.split_stride + row * p.ld_f32 + col;
 #pragma unroll
@@ -171,61 +186,131 @@ __global__ void __launch_bounds__(kThreads, 2) k_tc_gemm(const __grid_constant__
             }
           }
         }
-        continue;
       }
-      if (row >= p.M || col >= p.n_valid) continue;
-      float v[32];
-      if (p.epi == 0) {  // Z = acc + b (.cu:45), Y = act(Z)
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float z = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col + j) : 0.f);
-          v[j] = p.act == ACT_RELU ? fmaxf(z, 0.f) : z;
+      if (want_bias) {
+        uint32_t r[32];
+        if (n_kb > 0) { tmem_ld_32x32(t_lane + 256, r); tmem_ld_wait(); }
+        else r[0] = 0u;
+        if (row < p.rows_valid) p.bias_out[(long)blockIdx.z * p.bias_split_stride + row] = __uint_as_float(r[0]);
+      }
+    } else {
+      // planes out through shared memory + TMA stores: 6 slots of 16 KB (64 columns x 128 rows, 128B-swizzled) in
+      // the now idle stage ring; one bulk group per 64 output columns (hi box [+ lo box])
+      uint8_t* stg = smem;
+      const bool row_ok = row < p.M;
+      const float ri = (p.epi == 1 && p.r1 && row_ok) ? __ldg(p.r1 + row) : 0.f;
+      const int n_groups = BN / 64;
+      float head_acc[3] = {0.f, 0.f, 0.f};
+      for (int g = 0; g < n_groups; g++) {
+        const int slot = (g % 3) * 2;
+        if (g >= 3) {
+          if (threadIdx.x == 0) tma_store_wait_read<2>();
+          named_barrier_sync(1, 128);
         }
-      } else {  // dgrad: (+ r1[m] v1[k]) then the ReLU mask of the layer below (.cu:99)
-        const float ri = p.r1 ? __ldg(p.r1 + row) : 0.f;
-        uint32_t mk[16];
-        if (p.mask) {
-          const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.ld_mask + col);
+        uint8_t* row_hi = stg + (size_t)slot * 16384 + tr * 128;
+        uint8_t* row_lo = row_hi + 16384;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          const int c0 = g * 64 + half * 32;
+          const int col = col0 + c0;
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + c0, r);
+          tmem_ld_wait();
+          float v[32];
+          if (p.epi == 0) {  // Z = acc + b (.cu:45), Y = act(Z)
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float z = __uint_as_float(r[j]) + ((p.bias && col + j < p.n_valid) ? __ldg(p.bias + col + j) : 0.f);
+              v[j] = p.act == ACT_RELU ? fmaxf(z, 0.f) : z;
+            }
+            if (p.bits_out) {
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; j++) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+              if (row_ok && col < p.n_valid) p.bits_out[row * p.ld_bits + (col >> 5)] = bits;
+            }
+            if (p.head_n > 0 && col < p.n_valid) {
+#pragma unroll
+              for (int n = 0; n < 3; n++) {
+                if (n < p.head_n) {
+                  const float* hw = p.head_w + (long)n * p.n_valid + col;
+                  float a = head_acc[n];
+#pragma unroll
+                  for (int j = 0; j < 32; j++) a = fmaf(v[j], __ldg(hw + j), a);
+                  head_acc[n] = a;
+                }
+              }
+            }
+          } else {  // dgrad: (+ r1[m] v1[k]) then the ReLU mask of the layer below (.cu:99)
+            uint32_t mk[16];
+            const bool use_bits = p.mask_bits != nullptr;
+            const uint32_t mbits = (use_bits && row_ok && col < p.n_valid) ? __ldg(p.mask_bits + row * p.ld_bits + (col >> 5)) : 0u;
+            const bool use_mask = p.mask != nullptr && !use_bits;
+            if (use_mask && row_ok && col < p.n_valid) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.ld_mask + col);
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const uint4 t = __ldg(mp + q);
+                mk[q * 4] = t.x; mk[q * 4 + 1] = t.y; mk[q * 4 + 2] = t.z; mk[q * 4 + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; q++) mk[q] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float x = __uint_as_float(r[j]);
+              if (p.r1 && col + j < p.n_valid) x = fmaf(ri, __ldg(p.v1 + col + j), x);
+              if (use_bits) x = ((mbits >> j) & 1u) ? x : 0.f;
+              if (use_mask) {
+                const uint32_t w = mk[j >> 1];
+                const uint32_t h = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                x = ((h & 0x8000u) == 0 && (h & 0x7FFFu) != 0) ? x : 0.f;
+              }
+              v[j] = x;
+            }
+          }
+          // bf16 split planes: hi = bf16(v), lo = bf16(v - hi); 16-byte chunk c of row r lives at chunk c ^ (r & 7)
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            const uint4 t = __ldg(mp + q);
-            mk[q * 4] = t.x; mk[q * 4 + 1] = t.y; mk[q * 4 + 2] = t.z; mk[q * 4 + 3] = t.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float x = __uint_as_float(r[j]);
-          if (p.r1) x = fmaf(ri, __ldg(p.v1 + col + j), x);
-          if (p.mask) {
-            const uint32_t w = mk[j >> 1];
-            const uint16_t h = (j & 1) ? (uint16_t)(w >> 16) : (uint16_t)(w & 0xFFFF);
-            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-            x = ((h & 0x8000u) == 0 && (h & 0x7FFFu) != 0) ? x : 0.f;
-          }
-          v[j] = x;
-        }
-      }
-      // bf16 split planes: hi = bf16(v), lo = bf16(v - hi)
-      uint4* oh = reinterpret_cast<uint4*>(p.out_hi + row * p.ld_out + col);
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        oh[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+            const int chunk = (half * 4 + q) ^ (tr & 7);
+            *reinterpret_cast<uint4*>(row_hi + (chunk << 4)) =
+                make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                            pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-      if (p.out_lo) {
-        uint4* ol = reinterpret_cast<uint4*>(p.out_lo + row * p.ld_out + col);
+          }
+          if (p.out_lo) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+            for (int j = 0; j < 32; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          ol[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+            for (int q = 0; q < 4; q++) {
+              const int chunk = (half * 4 + q) ^ (tr & 7);
+              *reinterpret_cast<uint4*>(row_lo + (chunk << 4)) =
+                  make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                              pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+            }
+          }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+        named_barrier_sync(1, 128);
+        if (threadIdx.x == 0) {
+          tma_store_2d(&p.maps[6], stg + (size_t)slot * 16384, col0 + g * 64, (int)row0);
+          if (p.out_lo) tma_store_2d(&p.maps[7], stg + (size_t)(slot + 1) * 16384, col0 + g * 64, (int)row0);
+          tma_store_commit();
+        }
       }
+      if (p.epi == 0 && p.head_n > 0 && row_ok) {
+#pragma unroll
+        for (int n = 0; n < 3; n++)
+          if (n < p.head_n) p.head_out[row * p.head_n + n] = head_acc[n] + (p.head_b ? __ldg(p.head_b + n) : 0.f);
+      }
+      if (threadIdx.x == 0) tma_store_wait_read<0>();  // shared memory must outlive the bulk reads
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<256>(tmem_base);
+  if (warp == 4) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ plane helpers
@@ -285,39 +370,109 @@ k_thin_fwd_planes(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __r
   }
 }
 
+// dX[m, k..k+7] = mask * sum_n dz[m,n] W[n,k]: one thread per 8 consecutive columns, 16-byte plane stores
 __global__ void k_thin_dgrad_planes(const float* __restrict__ dZ, const float* __restrict__ W, long M, int N, int K,
-                                    const __nv_bfloat16* __restrict__ mask, int ldm, __nv_bfloat16* __restrict__ oh,
+                                    const uint32_t* __restrict__ mask_bits, int ld_bits, __nv_bfloat16* __restrict__ oh,
                                     __nv_bfloat16* __restrict__ ol, int ldo) {
+  const int k8 = K >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * K) return;
-  const long m = idx / K;
-  const int k = (int)(idx % K);
-  float v = 0.f;
-  for (int n = 0; n < N; n++) v = fmaf(__ldg(dZ + m * N + n), __ldg(W + n * K + k), v);
-  if (mask) v = __bfloat162float(mask[m * ldm + k]) > 0.f ? v : 0.f;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  oh[m * ldo + k] = h;
-  if (ol) ol[m * ldo + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+  if (idx >= M * k8) return;
+  const long m = idx / k8;
+  const int k = (int)(idx % k8) * 8;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int n = 0; n < N; n++) {
+    const float g = __ldg(dZ + m * N + n);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + n * K + k));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + n * K + k + 4));
+    v[0] = fmaf(g, w0.x, v[0]); v[1] = fmaf(g, w0.y, v[1]); v[2] = fmaf(g, w0.z, v[2]); v[3] = fmaf(g, w0.w, v[3]);
+    v[4] = fmaf(g, w1.x, v[4]); v[5] = fmaf(g, w1.y, v[5]); v[6] = fmaf(g, w1.z, v[6]); v[7] = fmaf(g, w1.w, v[7]);
+  }
+  if (mask_bits) {
+    const uint32_t bits = __ldg(mask_bits + m * ld_bits + (k >> 5)) >> (k & 31);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+  }
+  *reinterpret_cast<uint4*>(oh + m * ldo + k) =
+      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  if (ol) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+    *reinterpret_cast<uint4*>(ol + m * ldo + k) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
 }
 
+// Thin-head wgrad partials: dW[n, k] = sum_m dz[m, n] x[m, k] over this block's rows.  Each warp walks rows
+// (stride 8 within the block's range), each lane owns 8 consecutive columns (16-byte plane loads), 4 rows in flight;
+// the 8 warps are then summed through shared memory.  part[block][n*K + k], partb[block][n].   K <= 256.
 __global__ void __launch_bounds__(256)
-k_thin_wgrad_planes_partial(const float* __restrict__ dZ, const __nv_bfloat16* __restrict__ xh,
-                            const __nv_bfloat16* __restrict__ xl, int ldx, long M, int N, int K, long chunk,
-                            float* __restrict__ part, float* __restrict__ partb) {
+k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int ldx,
+                            const float* __restrict__ dZ, long M, int N, int K, long chunk, float* __restrict__ part,
+                            float* __restrict__ partb) {
+  __shared__ float red[8][3][256 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long m0 = (long)blockIdx.x * chunk, m1 = min(M, m0 + chunk);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long m = m0; m < m1; m++) {
-      const float x = plane_val(xh, xl, m * ldx + k);
+  const int k = lane * 8;
+  const bool active = k < K;
+  float acc[3][8];
 #pragma unroll
-      for (int n = 0; n < 4; n++)
-        if (n < N) acc[n] = fmaf(__ldg(dZ + m * N + n), x, acc[n]);
+  for (int n = 0; n < 3; n++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[n][j] = 0.f;
+  float bsum[3] = {0.f, 0.f, 0.f};
+  for (long m = m0 + warp; m < m1; m += 32) {  // rows m, m+8, m+16, m+24 in flight
+    uint4 h[4], l[4];
+    float g[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long mm = m + 8 * u;
+      const bool ok = mm < m1;
+      h[u] = (ok && active) ? __ldg(reinterpret_cast<const uint4*>(xh + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
+      l[u] = (ok && active && xl) ? __ldg(reinterpret_cast<const uint4*>(xl + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int n = 0; n < 3; n++) g[u][n] = (ok && n < N) ? __ldg(dZ + mm * N + n) : 0.f;
     }
-    for (int n = 0; n < N; n++) part[(long)blockIdx.x * N * K + n * K + k] = acc[n];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w}, lw[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        x[2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+        x[2 * q + 1] = __uint_as_float(hw[q] & 0xFFFF0000u) + __uint_as_float(lw[q] & 0xFFFF0000u);
+      }
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[n][j] = fmaf(g[u][n], x[j], acc[n][j]);
+        bsum[n] += g[u][n];
+      }
+    }
   }
+#pragma unroll
+  for (int n = 0; n < 3; n++)
+    if (n < N && active)
+#pragma unroll
+      for (int j = 0; j < 8; j++) red[warp][n][k + j] = acc[n][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    const int n = i / K, kk = i % K;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[w][n][kk];
+    part[(long)blockIdx.x * N * K + i] = s;
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+      if (n < N) red[warp][n][0] = bsum[n];
+  }
+  __syncthreads();
   if (threadIdx.x < N) {
     float s = 0.f;
-    for (long m = m0; m < m1; m++) s += __ldg(dZ + m * N + threadIdx.x);
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[w][threadIdx.x][0];
     partb[(long)blockIdx.x * N + threadIdx.x] = s;
   }
 }
@@ -388,11 +543,16 @@ int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
-int tc_smem_bytes(int BN, int n_stages) { return n_stages * (kABytes + BN * 128) + 1024; }
+int tc_smem_bytes(int BN, int n_stages, bool mn_major) {
+  const int ring = n_stages * (kABytes + BN * 128);
+  // K-major: the epilogue restages the output tile in 6 x 16 KB slots of the ring; MN-major: + 8 KB tile of ones
+  return (mn_major ? ring + 8192 : (ring > 6 * 16384 ? ring : 6 * 16384)) + 1024;
+}
 
-int tc_pick_stages(int BN, int n_kblocks) {
-  // two CTAs per SM: <= ~110 KB each
-  int s = (110 * 1024 - 1024) / (kABytes + BN * 128);
+int tc_pick_stages(int BN, int n_kblocks, bool mn_major) {
+  // K-major: two CTAs per SM (<= ~110 KB each); MN-major (wgrad, HBM-bound): one CTA per SM, deep ring
+  const int budget = mn_major ? 200 * 1024 : 110 * 1024;
+  int s = (budget - 1024 - (mn_major ? 8192 : 0)) / (kABytes + BN * 128);
   if (s > kMaxStages) s = kMaxStages;
   if (s > n_kblocks && n_kblocks > 0) s = n_kblocks;
   return s < 1 ? 1 : s;
@@ -402,12 +562,14 @@ int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_err = cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
   if (p.BN % 16 || p.BN < 16 || p.BN > 256 || p.n_stages < 1 || p.n_stages > kMaxStages) { set_error("tc_launch: bad BN=%d stages=%d", p.BN, p.n_stages); return 100001; }
-  const size_t smem = (size_t)tc_smem_bytes(p.BN, p.n_stages);
+  if (mn_major && p.BN % 64) { set_error("tc_launch: MN-major needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
+  if (!mn_major && p.BN % 64) { set_error("tc_launch: K-major epilogue needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
+  const size_t smem = (size_t)tc_smem_bytes(p.BN, p.n_stages, mn_major);
   if (mn_major) k_tc_gemm<true><<<grid, kThreads, smem, st>>>(p);
   else k_tc_gemm<false><<<grid, kThreads, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
@@ -432,9 +594,10 @@ int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int
   return 0;
 }
 
-int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const __nv_bfloat16* mask, int ld_mask,
+int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const uint32_t* mask_bits, int ld_bits,
                              __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st) {
-  k_thin_dgrad_planes<<<(unsigned)cdiv(M * K, 256), 256, 0, st>>>(dZ, W, M, N, K, mask, ld_mask, oh, ol, ldo);
+  if (K % 8 || ((uintptr_t)W & 15)) { set_error("thin_dgrad_planes: K=%d / W alignment", K); return 100001; }
+  k_thin_dgrad_planes<<<(unsigned)cdiv(M * (K / 8), 256), 256, 0, st>>>(dZ, W, M, N, K, mask_bits, ld_bits, oh, ol, ldo);
   NERF_CHECK_LAUNCH();
   return 0;
 }
@@ -447,14 +610,21 @@ int launch_reduce_partials(const float* ws, int splits, long split_stride, int r
   return 0;
 }
 
+long thin_wgrad_chunk(long M) {  // ~4 blocks per SM, at least 256 rows each
+  long c = cdiv(M, 148 * 4);
+  c = cdiv(c, 32) * 32;
+  return c < 256 ? 256 : c;
+}
+
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
                              long M, int N, int K, float* workspace, cudaStream_t st) {
   if (N > 4) { set_error("thin_wgrad_planes: N=%d", N); return 100001; }
-  const long chunk = 1024;
+  if (N > 3 || K > 256 || K % 8) { set_error("thin_wgrad_planes: N=%d K=%d unsupported", N, K); return 100001; }
+  const long chunk = thin_wgrad_chunk(M);
   const int chunks = (int)cdiv(M, chunk);
   float* part = workspace;
   float* partb = workspace + (size_t)chunks * N * K;
-  k_thin_wgrad_planes_partial<<<chunks, 256, 0, st>>>(dZ, xh, xl, ldx, M, N, K, chunk, part, partb);
+  k_thin_wgrad_planes_partial<<<chunks, 256, 0, st>>>(xh, xl, ldx, dZ, M, N, K, chunk, part, partb);
   NERF_CHECK_LAUNCH();
   NERF_TRY(launch_reduce_partials(part, chunks, (long)N * K, N, K, K, dW, K, 0, st));
   if (db) NERF_TRY(launch_reduce_partials(partb, chunks, N, 1, N, N, db, N, 0, st));

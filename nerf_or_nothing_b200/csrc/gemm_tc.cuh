@@ -14,7 +14,7 @@ constexpr int TC_MAX_KB = 30;
 // which A plane / B plane it multiplies, so conjoined inputs (two K segments) and the bf16x3 split passes
 // (hi*hi + hi*lo + lo*hi) are just longer k-block lists over the same kernel.
 struct alignas(64) TcParams {
-  CUtensorMap maps[8];  // [0..3] A-side planes, [4..7] B-side planes
+  CUtensorMap maps[8];  // [0..3] A-side planes, [4..5] B-side planes, [6..7] output planes (K-major epilogue TMA stores)
   // ---- K-major mode (forward, dgrad): grid = (ceil(M/128), ceil(N/BN))
   struct KB { int8_t a, b; int16_t a_col, b_col; } kb[TC_MAX_KB];
   int n_kb;
@@ -43,12 +43,23 @@ struct alignas(64) TcParams {
   float* out_f32;     // epi 2: [split][rows][ld_f32]
   int ld_f32;
   long split_stride;  // floats between splits
+  float* bias_out;    // epi 2, optional: [split][rows] column sums of the A operand (bias gradient)
+  long bias_split_stride;
+  // ReLU masks as bit planes: 1 bit per output element instead of re-reading the 2-byte activation in dgrad
+  uint32_t* bits_out;         // epi 0, optional: [M, ld_bits] words, bit j of word c <=> Y[m, 32c + j] > 0
+  const uint32_t* mask_bits;  // epi 1, optional (replaces `mask`)
+  int ld_bits;
+  // thin head fused into the forward epilogue (needs the whole row in one CTA: gridDim.y == 1)
+  const float* head_w;  // [head_n, n_valid]
+  const float* head_b;  // [head_n]
+  float* head_out;      // [M, head_n]
+  int head_n;           // 0..3
 };
 
 int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);
 int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st);
-int tc_smem_bytes(int BN, int n_stages);
-int tc_pick_stages(int BN, int n_kblocks);
+int tc_smem_bytes(int BN, int n_stages, bool mn_major);
+int tc_pick_stages(int BN, int n_kblocks, bool mn_major);
 
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]
@@ -57,7 +68,7 @@ int launch_f32_to_planes(const float* src, int src_pitch, long rows, int cols, _
 // heads on planes (N <= 4)
 int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, const float* W, const float* b,
                            float* Y, long M, int N, int K, cudaStream_t st);
-int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const __nv_bfloat16* mask, int ld_mask,
+int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const uint32_t* mask_bits, int ld_bits,
                              __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st);
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
                              long M, int N, int K, float* workspace, cudaStream_t st);

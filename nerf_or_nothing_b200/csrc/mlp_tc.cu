@@ -45,7 +45,15 @@ class TcMlp : public MlpEngine {
       NERF_TRY(alloc_plane(&lv.enc_pos, max_rows, pos_pitch_));
       NERF_TRY(alloc_plane(&lv.enc_dir, max_rows, dir_pitch_));
       lv.acts.resize(s_.D + s_.C);
-      for (int i = 0; i < s_.D + s_.C; i++) NERF_TRY(alloc_plane(&lv.acts[i], max_rows, i < s_.D ? s_.W : s_.Wc));
+      lv.bits.resize(s_.D + s_.C);
+      for (int i = 0; i < s_.D + s_.C; i++) {
+        const int w = i < s_.D ? s_.W : s_.Wc;
+        NERF_TRY(alloc_plane(&lv.acts[i], max_rows, w));
+        const size_t nb = (size_t)max_rows * (w / 32) * sizeof(uint32_t);
+        NERF_CUDA(cudaMalloc(&lv.bits[i], nb));
+        owned_.push_back(lv.bits[i]);
+        bytes_ += nb;
+      }
     }
     const int mw = s_.W > s_.Wc ? s_.W : s_.Wc;
     NERF_TRY(alloc_plane(&dz_[0], max_rows, mw));
@@ -54,7 +62,7 @@ class TcMlp : public MlpEngine {
     size_t ws = 1 << 20;
     for (int l = 0; l < s_.L; l++) {
       const LayerInfo& L = s_.layers[l];
-      if (L.out <= 4) { ws = std::max(ws, (size_t)cdiv(max_rows, 1024) * L.out * (L.in_a + 1) + 64); continue; }
+      if (L.out <= 4) { ws = std::max(ws, (size_t)cdiv(max_rows, 256) * L.out * (L.in_a + 1) + 64); continue; }
       NERF_TRY(alloc_plane(&wp_[l], L.out, round_up(L.in_a + L.in_b, 64)));
       if (needs_dgrad(l)) NERF_TRY(alloc_plane(&wtp_[l], L.in_a, L.out));
       for (int src = 0; src < 2; src++) {
@@ -62,7 +70,7 @@ class TcMlp : public MlpEngine {
         if (K <= 0) continue;
         int splits; long split_len;
         wgrad_split(L.out, K, max_rows, &splits, &split_len);
-        ws = std::max(ws, (size_t)splits * L.out * round_up(K, 4));
+        ws = std::max(ws, (size_t)splits * L.out * (round_up(K, 4) + 1) + 64);
       }
       ws = std::max(ws, (size_t)cdiv(max_rows, 2048) * L.out + 64);
     }
@@ -107,10 +115,15 @@ class TcMlp : public MlpEngine {
     for (int i = 0; i < D; i++) {
       const LayerInfo& L = s_.layers[i];
       ProfScope ps(PC_MLP_FWD, st);
-      NERF_TRY(gemm_fwd(*h, kh, L.in_b ? &lv.enc_pos : nullptr, L.in_b, L.in_a, wp_[i], params + L.b_off, lv.acts[i], M, L.out, st));
+      Head hd;
+      if (i == D - 1 && fuse_heads()) {  // density head (N=1) rides in the last trunk layer's epilogue
+        const LayerInfo& Lh = s_.layers[D];
+        hd.w = params + Lh.w_off; hd.b = params + Lh.b_off; hd.out = raw_density; hd.n = 1;
+      }
+      NERF_TRY(gemm_fwd(*h, kh, L.in_b ? &lv.enc_pos : nullptr, L.in_b, L.in_a, wp_[i], params + L.b_off, lv.acts[i], lv.bits[i], hd, M, L.out, st));
       h = &lv.acts[i]; kh = s_.W;
     }
-    {
+    if (!fuse_heads()) {
       const LayerInfo& L = s_.layers[D];
       ProfScope ps(PC_MLP_HEADS_FWD, st);
       NERF_TRY(launch_thin_fwd_planes(h->hi, h->lo, h->pitch, params + L.w_off, params + L.b_off, raw_density, M, 1, s_.W, st));
@@ -121,10 +134,15 @@ class TcMlp : public MlpEngine {
       const int l = D + 1 + i;
       const LayerInfo& L = s_.layers[l];
       ProfScope ps(PC_MLP_FWD, st);
-      NERF_TRY(gemm_fwd(*c, kc, L.in_b ? &lv.enc_dir : nullptr, L.in_b, L.in_a, wp_[l], params + L.b_off, lv.acts[D + i], M, L.out, st));
+      Head hd;
+      if (i == C - 1 && fuse_heads()) {  // rgb head (N=3) rides in the last condition layer's epilogue
+        const LayerInfo& Lh = s_.layers[D + C + 1];
+        hd.w = params + Lh.w_off; hd.b = params + Lh.b_off; hd.out = raw_rgb; hd.n = 3;
+      }
+      NERF_TRY(gemm_fwd(*c, kc, L.in_b ? &lv.enc_dir : nullptr, L.in_b, L.in_a, wp_[l], params + L.b_off, lv.acts[D + i], lv.bits[D + i], hd, M, L.out, st));
       c = &lv.acts[D + i]; kc = s_.Wc;
     }
-    {
+    if (!fuse_heads()) {
       const LayerInfo& L = s_.layers[D + C + 1];
       ProfScope ps(PC_MLP_HEADS_FWD, st);
       NERF_TRY(launch_thin_fwd_planes(c->hi, c->lo, c->pitch, params + L.w_off, params + L.b_off, raw_rgb, M, 3, s_.Wc, st));
@@ -143,7 +161,7 @@ class TcMlp : public MlpEngine {
       const Plane& x = lv.acts[D + C - 1];
       ProfScope ps(PC_MLP_HEADS_BWD, st);
       NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st));
-      NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, x.hi, x.pitch, cur->hi, cur->lo, cur->pitch, st));
+      NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st));
     }
     for (int i = C - 1; i >= 0; i--) {
       const int l = D + 1 + i;
@@ -155,10 +173,10 @@ class TcMlp : public MlpEngine {
       }
       ProfScope ps(PC_MLP_DGRAD, st);
       if (i > 0) {
-        NERF_TRY(gemm_dgrad(*cur, wtp_[l], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.acts[D + i - 1], st));
+        NERF_TRY(gemm_dgrad(*cur, wtp_[l], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.bits[D + i - 1], st));
       } else {
         const LayerInfo& Ld = s_.layers[D];
-        NERF_TRY(gemm_dgrad(*cur, wtp_[l], *nxt, M, L.out, L.in_a, d_raw_density, params + Ld.w_off, lv.acts[D - 1], st));
+        NERF_TRY(gemm_dgrad(*cur, wtp_[l], *nxt, M, L.out, L.in_a, d_raw_density, params + Ld.w_off, lv.bits[D - 1], st));
       }
       Plane* t = cur; cur = nxt; nxt = t;
     }
@@ -177,7 +195,7 @@ class TcMlp : public MlpEngine {
       }
       if (i > 0) {
         ProfScope ps(PC_MLP_DGRAD, st);
-        NERF_TRY(gemm_dgrad(*cur, wtp_[i], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.acts[i - 1], st));
+        NERF_TRY(gemm_dgrad(*cur, wtp_[i], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.bits[i - 1], st));
         Plane* t = cur; cur = nxt; nxt = t;
       }
     }
@@ -190,7 +208,9 @@ class TcMlp : public MlpEngine {
   struct Level {
     Plane enc_pos, enc_dir;
     std::vector<Plane> acts;
+    std::vector<uint32_t*> bits;  // ReLU masks of acts[i] as bit planes [M, width/32]
   };
+  struct Head { const float* w = nullptr; const float* b = nullptr; float* out = nullptr; int n = 0; };
 
   bool needs_dgrad(int l) const { return (l > 0 && l < s_.D) || (l > s_.D && l <= s_.D + s_.C); }
 
@@ -220,8 +240,10 @@ class TcMlp : public MlpEngine {
   }
 
   // Y = relu([A1|A2] W^T + b): K-major, grid (M/128, N/BN)
+  bool fuse_heads() const { return s_.W <= 256 && s_.Wc <= 256; }  // the head needs the whole row in one CTA
+
   int gemm_fwd(const Plane& a1, int k1, const Plane* a2, int k2, int w_col2, const Plane& w, const float* bias, const Plane& out,
-               long M, int N, cudaStream_t st) {
+               uint32_t* bits, const Head& head, long M, int N, cudaStream_t st) {
     TcParams p;
     memset(&p, 0, sizeof(p));
     const int BN = N > 256 ? 256 : N;
@@ -249,15 +271,19 @@ class TcMlp : public MlpEngine {
           n++;
         }
     }
-    p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = N; p.n_stages = tc_pick_stages(BN, n);
+    NERF_TRY(tc_make_tmap(&p.maps[6], out.hi, M, N, out.pitch, 128));
+    if (out.lo) NERF_TRY(tc_make_tmap(&p.maps[7], out.lo, M, N, out.pitch, 128));
+    p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = N; p.n_stages = tc_pick_stages(BN, n, false);
     p.epi = 0; p.bias = bias; p.act = ACT_RELU;
+    p.bits_out = bits; p.ld_bits = N / 32;
+    p.head_w = head.w; p.head_b = head.b; p.head_out = head.out; p.head_n = head.n;
     p.out_hi = out.hi; p.out_lo = out.lo; p.ld_out = out.pitch;
     return tc_launch(p, false, dim3((unsigned)cdiv(M, 128), (unsigned)cdiv(N, BN), 1), st);
   }
 
   // dX[M, k1] = mask(dZ[M,N] * WT^T (+ r1 v1^T)):  A = dZ planes (K-major over n), B = WT planes [k1, N]
   int gemm_dgrad(const Plane& dz, const Plane& wt, const Plane& out, long M, int N, int k1, const float* r1, const float* v1,
-                 const Plane& mask, cudaStream_t st) {
+                 const uint32_t* mask_bits, cudaStream_t st) {
     TcParams p;
     memset(&p, 0, sizeof(p));
     const int BN = k1 > 256 ? 256 : k1;
@@ -277,8 +303,10 @@ class TcMlp : public MlpEngine {
         p.kb[n].b_col = (int16_t)kc;
         n++;
       }
-    p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = k1; p.n_stages = tc_pick_stages(BN, n);
-    p.epi = 1; p.r1 = r1; p.v1 = v1; p.mask = mask.hi; p.ld_mask = mask.pitch;
+    NERF_TRY(tc_make_tmap(&p.maps[6], out.hi, M, k1, out.pitch, 128));
+    if (out.lo) NERF_TRY(tc_make_tmap(&p.maps[7], out.lo, M, k1, out.pitch, 128));
+    p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = k1; p.n_stages = tc_pick_stages(BN, n, false);
+    p.epi = 1; p.r1 = r1; p.v1 = v1; p.mask_bits = mask_bits; p.ld_bits = k1 / 32;
     p.out_hi = out.hi; p.out_lo = out.lo; p.ld_out = out.pitch;
     return tc_launch(p, false, dim3((unsigned)cdiv(M, 128), (unsigned)cdiv(k1, BN), 1), st);
   }
@@ -317,12 +345,15 @@ class TcMlp : public MlpEngine {
       wgrad_split(N, K, M, &splits, &split_len);
       const int ldf = round_up(K, 4);
       p.split_len = (int)split_len; p.red_len = M; p.BN = BN; p.n_valid = K; p.rows_valid = N;
-      p.n_stages = tc_pick_stages(BN, 1 << 20);
+      p.n_stages = tc_pick_stages(BN, 1 << 20, true);
       p.epi = 2; p.out_f32 = ws_; p.ld_f32 = ldf; p.split_stride = (long)N * ldf;
+      const bool bias_here = db != nullptr && src == 0;  // db = colsum(dZ) rides along as a 16-column MMA against ones
+      float* bias_ws = ws_ + (size_t)splits * N * ldf;
+      if (bias_here) { p.bias_out = bias_ws; p.bias_split_stride = N; }
       NERF_TRY(tc_launch(p, true, dim3((unsigned)cdiv(N, 128), (unsigned)cdiv(K, BN), (unsigned)splits), st));
       NERF_TRY(launch_reduce_partials(ws_, splits, p.split_stride, N, K, ldf, dW, ldw, coff, st));
+      if (bias_here) NERF_TRY(launch_reduce_partials(bias_ws, splits, N, 1, N, N, db, N, 0, st));
     }
-    if (db) NERF_TRY(launch_colsum_planes(dz.hi, dz.lo, dz.pitch, M, N, db, ws_, st));
     return 0;
   }
 
