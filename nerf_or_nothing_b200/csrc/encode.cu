@@ -42,15 +42,29 @@ __device__ __forceinline__ Gauss frustum_to_gaussian(float t0, float t1, float r
   return g;
 }
 
-// exp(-.5*var*4^f) * {sin,cos}(mean*2^f)  (.cu:185-186,196-204).  Scaling by 2^f is exact, so the
-// argument is exactly the reference's; when the attenuation underflows to 0 the product is 0 and the
-// (slow, huge-argument) sincos is skipped.
-__device__ __forceinline__ void ipe_pair(float mean, float var, float scale, float& s, float& c) {
-  const float e = expf(__fmul_rn(-0.5f, __fmul_rn(__fmul_rn(var, scale), scale)));
-  if (e == 0.f) { s = 0.f; c = 0.f; return; }
-  float sn, cs;
-  sincosf(mean * scale, &sn, &cs);
-  s = e * sn; c = e * cs;
+// exp(-.5*var*4^f) * {sin,cos}(mean*2^f)  (.cu:185-186,196-204).
+// The argument mean*2^f reaches 2^15*|x| ~ 2e5 rad, where sincosf falls into its slow Payne-Hanek path.  Instead the
+// mean is converted ONCE per axis to half-turns v = mean/pi as a float-float (vh + vl, ~2^-48 relative); scaling by
+// 2^f is exact, sincospif reduces its argument exactly, and the tiny tail vl*2^f enters through a second-order
+// rotation.  Result: ~2 ulp of the correctly rounded sin/cos of the reference's exact argument, at a fixed cost.
+struct HalfTurns { float hi, lo; };
+__device__ __forceinline__ HalfTurns to_half_turns(float mean) {
+  const float kInvPiHi = 0.31830987334251404f, kInvPiLo = 1.2841276486597053e-08f;
+  HalfTurns v;
+  v.hi = __fmul_rn(mean, kInvPiHi);
+  v.lo = __fmaf_rn(mean, kInvPiHi, -v.hi) + mean * kInvPiLo;
+  return v;
+}
+__device__ __forceinline__ void ipe_pair(HalfTurns v, float var, float scale, float& s, float& c) {
+  const float x = __fmul_rn(0.5f, __fmul_rn(__fmul_rn(var, scale), scale));  // .5*var*4^f, the reference's rounding
+  if (x > 87.f) { s = 0.f; c = 0.f; return; }                               // exp(-x) < 1.2e-38: below fp32 normals
+  const float e = exp2f(-1.4426950216293335f * x);
+  float s0, c0;
+  sincospif(v.hi * scale, &s0, &c0);  // exact scaling; sin/cos(pi * a)
+  const float d = 3.1415927410125732f * (v.lo * scale);
+  const float q = fmaf(-0.5f * d, d, 1.0f);
+  s = e * fmaf(d, c0, s0 * q);
+  c = e * fmaf(-d, s0, c0 * q);
 }
 
 __global__ void k_cast_rays(const float* __restrict__ t, const float* __restrict__ o, const float* __restrict__ d,
@@ -92,12 +106,13 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
       g.mx = in0[m * 3]; g.my = in0[m * 3 + 1]; g.mz = in0[m * 3 + 2];
       g.cx = in1[m * 3]; g.cy = in1[m * 3 + 1]; g.cz = in1[m * 3 + 2];
     }
+    const HalfTurns hx = to_half_turns(g.mx), hy = to_half_turns(g.my), hz = to_half_turns(g.mz);
     for (int f = fl; f < deg; f += kFreqLanes) {
       const float scale = (float)(1u << f);  // .cu:196
       float* e = tile + ls * P + f * 6;
-      ipe_pair(g.mx, g.cx, scale, e[0], e[3]);
-      ipe_pair(g.my, g.cy, scale, e[1], e[4]);
-      ipe_pair(g.mz, g.cz, scale, e[2], e[5]);
+      ipe_pair(hx, g.cx, scale, e[0], e[3]);
+      ipe_pair(hy, g.cy, scale, e[1], e[4]);
+      ipe_pair(hz, g.cz, scale, e[2], e[5]);
     }
   }
   __syncthreads();
@@ -134,37 +149,46 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
 }
 
 // direction PE per SAMPLE: [d, sin(2^0 d), cos(2^0 d), ...] (SN/MipHelpers.cs:337-356, A-D10), from the
-// per-ray direction.  One thread per (sample, scale j in [-1, deg)).
-__global__ void k_encode_dir(const float* __restrict__ d, long M, int S, int deg, float* __restrict__ f32,
-                             int pitch_f, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                             int pitch_h) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = deg + 1;
-  if (idx >= M * per) return;
-  const long m = idx / per;
-  const int j = (int)(idx % per) - 1;
-  const int r = (int)(m / S);
-  const float x = d[r * 3], y = d[r * 3 + 1], z = d[r * 3 + 2];
-  float v[6];
-  int col, cnt;
-  if (j < 0) { v[0] = x; v[1] = y; v[2] = z; col = 0; cnt = 3; }
-  else {
-    const float sc = (float)(1u << j);
-    sincosf(x * sc, &v[0], &v[3]); sincosf(y * sc, &v[1], &v[4]); sincosf(z * sc, &v[2], &v[5]);
-    col = 3 + 6 * j; cnt = 6;
-  }
+// per-ray direction.  One block per ray: the 3+6*deg values are computed once into shared memory (as the fp32 row
+// and/or the zero-padded bf16 hi/lo rows), then replicated to the ray's S sample rows with 16-byte stores.
+__global__ void __launch_bounds__(128)
+k_encode_dir(const float* __restrict__ d, int R, int S, int deg, float* __restrict__ f32, int pitch_f,
+             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int pitch_h) {
+  __shared__ __align__(16) float row_f[64];
+  __shared__ __align__(16) __nv_bfloat16 row_h[64], row_l[64];
+  const int r = blockIdx.x;
   const int Dd = 3 + 6 * deg;
-  for (int i = 0; i < cnt; i++) {
-    if (f32) f32[m * pitch_f + col + i] = v[i];
-    if (hi) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-      hi[m * pitch_h + col + i] = h;
-      if (lo) lo[m * pitch_h + col + i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float v = 0.f;
+    if (c < 3) v = d[r * 3 + c];
+    else if (c < Dd) {
+      const int j = (c - 3) / 6, k = (c - 3) % 6;
+      const float x = d[r * 3 + (k % 3)] * (float)(1u << j);
+      v = k < 3 ? sinf(x) : cosf(x);
+    }
+    row_f[c] = v;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    row_h[c] = h;
+    row_l[c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+  __syncthreads();
+  const long m0 = (long)r * S;
+  if (f32) {
+    for (int i = threadIdx.x; i < S * pitch_f; i += blockDim.x) {
+      const int c = i % pitch_f;
+      f32[m0 * pitch_f + i] = c < Dd ? row_f[c] : 0.f;
     }
   }
-  if (j < 0) {  // zero the padding columns
-    if (f32) for (int c = Dd; c < pitch_f; c++) f32[m * pitch_f + c] = 0.f;
-    if (hi) for (int c = Dd; c < pitch_h; c++) { hi[m * pitch_h + c] = __float2bfloat16_rn(0.f); if (lo) lo[m * pitch_h + c] = __float2bfloat16_rn(0.f); }
+  if (hi) {  // pitch_h is a multiple of 64 elements; columns >= 64 (if any) are zero
+    const int chunks = pitch_h >> 3;  // 16-byte chunks per row
+    for (int i = threadIdx.x; i < S * chunks; i += blockDim.x) {
+      const int s = i / chunks, c = i % chunks;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      const uint4 vh = c < 8 ? reinterpret_cast<const uint4*>(row_h)[c] : z;
+      reinterpret_cast<uint4*>(hi + (m0 + s) * pitch_h)[c] = vh;
+      if (lo) reinterpret_cast<uint4*>(lo + (m0 + s) * pitch_h)[c] = c < 8 ? reinterpret_cast<const uint4*>(row_l)[c] : z;
+    }
   }
 }
 
@@ -186,9 +210,8 @@ int launch_encode_input_data(const float* means, const float* covs, const float*
       means, covs, nullptr, nullptr, nullptr, M, S, deg_point, enc_pos, nullptr, nullptr, 0);
   NERF_CHECK_LAUNCH();
   if (enc_dir) {
-    const long n = M * (deg_view + 1);
-    k_encode_dir<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(dirs, M, S, deg_view, enc_dir, 3 + 6 * deg_view, nullptr,
-                                                         nullptr, 0);
+    if (3 + 6 * deg_view > 64) { set_error("encode: deg_view too large"); return 100001; }
+    k_encode_dir<<<(unsigned)R, 128, 0, st>>>(dirs, R, S, deg_view, enc_dir, 3 + 6 * deg_view, nullptr, nullptr, 0);
     NERF_CHECK_LAUNCH();
   }
   return 0;
@@ -202,9 +225,9 @@ int launch_cast_encode_fused(const float* t, const float* o, const float* d, con
       t, nullptr, o, d, radii, M, S, deg_point, out.enc_pos_f32, out.pos_hi, out.pos_lo, out.pos_pitch_h);
   NERF_CHECK_LAUNCH();
   if (out.enc_dir_f32 || out.dir_hi) {
-    const long n = M * (deg_view + 1);
-    k_encode_dir<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(d, M, S, deg_view, out.enc_dir_f32, out.dir_pitch_f32,
-                                                         out.dir_hi, out.dir_lo, out.dir_pitch_h);
+    if (3 + 6 * deg_view > 64) { set_error("encode: deg_view too large"); return 100001; }
+    k_encode_dir<<<(unsigned)R, 128, 0, st>>>(d, R, S, deg_view, out.enc_dir_f32, out.dir_pitch_f32, out.dir_hi, out.dir_lo,
+                                              out.dir_pitch_h);
     NERF_CHECK_LAUNCH();
   }
   return 0;

@@ -21,6 +21,7 @@
 // hi*hi + hi*lo + lo*hi (error ~2^-17 per product), expressed as three k-blocks per K slice.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_tc.cuh"
@@ -313,6 +314,223 @@ __global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __
   if (warp == 4) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// Persistent K-major variant (forward / dgrad): one CTA per SM walks row tiles tile = blockIdx.x + i * gridDim.x.
+// The TMA producer streams k-blocks of the NEXT tile while the epilogue of the current one runs: the accumulator is
+// double-buffered in TMEM (2 x 256 columns, tfull/tempty mbarriers), the operand ring is 3-4 stages deep and never
+// drains at tile boundaries.  Each epilogue warp owns its 32 rows end to end — TMEM load, math, restaging into its own
+// 128B-swizzled 32-row boxes and its own TMA bulk stores — so the four warps never synchronise with each other; the
+// per-column constants (bias / rank-1 vector / head weights) are staged once per CTA in shared memory.
+constexpr int kConstFloats = 4 * 512;  // bias|v1 [512] + head weights [3][512]
+
+__device__ __forceinline__ void store_planes_32(uint8_t* row_hi, uint8_t* row_lo, bool with_lo, int half, int swz, float (&v)[32]) {
+  // hi = bf16(v) packed in pairs (one cvt per pair); lo = bf16(v - hi) with hi rebuilt from the packed bits (no 2nd cvt)
+  uint32_t hw[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) hw[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    *reinterpret_cast<uint4*>(row_hi + (((half * 4 + q) ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+  if (with_lo) {
+    uint32_t lw[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++)
+      lw[q] = pack_bf16(v[2 * q] - __uint_as_float(hw[q] << 16), v[2 * q + 1] - __uint_as_float(hw[q] & 0xFFFF0000u));
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      *reinterpret_cast<uint4*>(row_lo + (((half * 4 + q) ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_tc_gemm_persist(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_const[kConstFloats];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const int stage_bytes = kABytes + BN * 128;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stg = smem + (size_t)p.n_stages * stage_bytes;  // per warp: 2 slot pairs x (hi 4 KB + lo 4 KB)
+
+  const int n_row_tiles = (int)((p.M + 127) / 128);
+  const int n_col_tiles = (p.n_valid + BN - 1) / BN;
+  const int n_tiles = n_row_tiles * n_col_tiles;
+  const int n_kb = p.n_kb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    fence_barrier_init();
+  }
+  {  // per-column constants -> shared memory (zero beyond n_valid)
+    const float* vec = p.epi == 0 ? p.bias : p.v1;
+    for (int i = threadIdx.x; i < 512; i += kThreads) s_const[i] = (vec && i < p.n_valid) ? __ldg(vec + i) : 0.f;
+    for (int i = threadIdx.x; i < 3 * 512; i += kThreads) {
+      const int n = i / 512, c = i % 512;
+      s_const[512 + i] = (p.epi == 0 && n < p.head_n && c < p.n_valid) ? __ldg(p.head_w + (long)n * p.n_valid + c) : 0.f;
+    }
+  }
+  if (warp == 4) {
+    tmem_alloc<512>(&tmem_base_smem);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) prefetch_tmap(&p.maps[i]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = (tile / n_col_tiles) * 128, col0 = (tile % n_col_tiles) * BN;
+        for (int i = 0; i < n_kb; i++, it++) {
+          const int s = it % p.n_stages;
+          const uint32_t ph = (it / p.n_stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          const TcParams::KB kb = p.kb[i];
+          tma_load_2d(a_dst, &p.maps[kb.a], kb.a_col, row0, &full_bar[s]);            // box {64, 128}
+          tma_load_2d(a_dst + kABytes, &p.maps[kb.b], kb.b_col, col0, &full_bar[s]);  // box {64, BN}
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+        const uint32_t b = t & 1;
+        mbar_wait(&tempty_bar[b], ((t >> 1) & 1) ^ 1);  // all four epilogue warps have drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + b * 256;
+        for (int i = 0; i < n_kb; i++, it++) {
+          const int s = it % p.n_stages;
+          const uint32_t ph = (it / p.n_stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_base = a_base + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(acc, make_smem_desc(a_base + k * 32, 16, 1024), make_smem_desc(b_base + k * 32, 16, 1024), idesc,
+                      (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp w owns rows 32w..32w+31
+    const int n_groups = BN / 64;
+    const int swz = lane & 7;
+    const bool with_lo = p.out_lo != nullptr;
+    uint8_t* wstg = stg + (size_t)warp * 16384;
+    uint32_t t = 0, gc = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
+      const int row0 = (tile / n_col_tiles) * 128, col0 = (tile % n_col_tiles) * BN;
+      const long row = (long)row0 + threadIdx.x;
+      const bool row_ok = row < p.M;
+      const uint32_t b = t & 1;
+      mbar_wait(&tfull_bar[b], (t >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t t_lane = tmem_base + b * 256 + ((uint32_t)(warp * 32) << 16);
+      const float ri = (p.epi == 1 && p.r1 && row_ok) ? __ldg(p.r1 + row) : 0.f;
+      float head_acc[3] = {0.f, 0.f, 0.f};
+      for (int g = 0; g < n_groups; g++, gc++) {
+        uint8_t* slot_hi = wstg + (size_t)(gc & 1) * 8192;
+        uint8_t* slot_lo = slot_hi + 4096;
+        if (gc >= 2) {
+          if (lane == 0) tma_store_wait_read<1>();  // this warp's group that used the slot pair has been read out
+          __syncwarp();
+        }
+        uint8_t* row_hi = slot_hi + lane * 128;
+        uint8_t* row_lo = slot_lo + lane * 128;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          const int c0 = g * 64 + half * 32;
+          const int col = col0 + c0;  // multiple of 32; n_valid is a multiple of 32
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + c0, r);
+          tmem_ld_wait();
+          float v[32];
+          const float4* cv = reinterpret_cast<const float4*>(s_const + col);
+          if (p.epi == 0) {  // Z = acc + b (.cu:45), Y = relu(Z)
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const float4 bb = cv[q];
+              v[4 * q] = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f);
+              v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
+              v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f);
+              v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
+            }
+            if (p.bits_out) {  // v >= 0, so v > 0 <=> its bit pattern is non-zero
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; j++) bits |= (__float_as_uint(v[j]) != 0u ? 1u : 0u) << j;
+              if (row_ok) p.bits_out[row * p.ld_bits + (col >> 5)] = bits;
+            }
+#pragma unroll
+            for (int n = 0; n < 3; n++) {
+              if (n < p.head_n) {
+                const float4* hv = reinterpret_cast<const float4*>(s_const + 512 + n * 512 + col);
+                float a = head_acc[n];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                  const float4 w = hv[q];
+                  a = fmaf(v[4 * q], w.x, a); a = fmaf(v[4 * q + 1], w.y, a);
+                  a = fmaf(v[4 * q + 2], w.z, a); a = fmaf(v[4 * q + 3], w.w, a);
+                }
+                head_acc[n] = a;
+              }
+            }
+          } else {  // dgrad: (+ r1[m] v1[k]) then the ReLU mask of the layer below (.cu:99), read as a bit plane
+            const uint32_t mbits = p.mask_bits ? (row_ok ? __ldg(p.mask_bits + row * p.ld_bits + (col >> 5)) : 0u) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const float4 vv = cv[q];
+              const float w4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const int j = 4 * q + e;
+                const float x = fmaf(ri, w4[e], __uint_as_float(r[j]));  // ri = 0 when there is no rank-1 term
+                v[j] = ((mbits >> j) & 1u) ? x : 0.f;
+              }
+            }
+          }
+          store_planes_32(row_hi, row_lo, with_lo, half, swz, v);
+        }
+        if (g == n_groups - 1) tc_fence_before_sync();  // this warp's last TMEM read of the tile is done
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (g == n_groups - 1) mbar_arrive(&tempty_bar[b]);
+          tma_store_2d(&p.maps[6], slot_hi, col0 + g * 64, row0 + warp * 32);  // box {64, 32}
+          if (with_lo) tma_store_2d(&p.maps[7], slot_lo, col0 + g * 64, row0 + warp * 32);
+          tma_store_commit();
+        }
+      }
+      if (p.epi == 0 && p.head_n > 0 && row_ok) {
+#pragma unroll
+        for (int n = 0; n < 3; n++)
+          if (n < p.head_n) p.head_out[row * p.head_n + n] = head_acc[n] + (p.head_b ? __ldg(p.head_b + n) : 0.f);
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ plane helpers
 
 __global__ void k_f32_to_planes(const float* __restrict__ src, int sp, long rows, int cols, __nv_bfloat16* __restrict__ hi,
@@ -558,7 +776,19 @@ int tc_pick_stages(int BN, int n_kblocks, bool mn_major) {
   return s < 1 ? 1 : s;
 }
 
-int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st) {
+static int persist_stages(int BN) {
+  const int budget = 227 * 1024 - (kConstFloats * 4 + 256) - 1024 - 4 * 16384;  // 227 KB per CTA minus static smem
+  int s = budget / (kABytes + BN * 128);
+  return s > kMaxStages ? kMaxStages : (s < 1 ? 1 : s);
+}
+static bool use_persistent() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NERF_TC_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+int tc_launch(const TcParams& p_in, bool mn_major, dim3 grid, cudaStream_t st) {
+  TcParams p = p_in;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -569,6 +799,25 @@ int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st) {
   if (p.BN % 16 || p.BN < 16 || p.BN > 256 || p.n_stages < 1 || p.n_stages > kMaxStages) { set_error("tc_launch: bad BN=%d stages=%d", p.BN, p.n_stages); return 100001; }
   if (mn_major && p.BN % 64) { set_error("tc_launch: MN-major needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
   if (!mn_major && p.BN % 64) { set_error("tc_launch: K-major epilogue needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
+  if (!mn_major) {
+    static std::once_flag once2;
+    static cudaError_t e2 = cudaSuccess;
+    static int sms = 148;
+    std::call_once(once2, [] {
+      e2 = cudaFuncSetAttribute(k_tc_gemm_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (kConstFloats * 4 + 256));
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    });
+    if (e2 != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e2)); return (int)e2; }
+    if (p.n_valid % 32 || p.n_valid > 512) { set_error("tc_launch: n_valid=%d must be a multiple of 32, <= 512", p.n_valid); return 100001; }
+    p.n_stages = persist_stages(p.BN);
+    const size_t smem_p = (size_t)p.n_stages * (kABytes + p.BN * 128) + 4 * 16384 + 1024;
+    const int tiles = (int)(grid.x * grid.y);
+    k_tc_gemm_persist<<<tiles < sms ? tiles : sms, kThreads, smem_p, st>>>(p);
+    NERF_CHECK_LAUNCH();
+    return 0;
+  }
   const size_t smem = (size_t)tc_smem_bytes(p.BN, p.n_stages, mn_major);
   if (mn_major) k_tc_gemm<true><<<grid, kThreads, smem, st>>>(p);
   else k_tc_gemm<false><<<grid, kThreads, smem, st>>>(p);

@@ -271,8 +271,8 @@ class TcMlp : public MlpEngine {
           n++;
         }
     }
-    NERF_TRY(tc_make_tmap(&p.maps[6], out.hi, M, N, out.pitch, 128));
-    if (out.lo) NERF_TRY(tc_make_tmap(&p.maps[7], out.lo, M, N, out.pitch, 128));
+    NERF_TRY(tc_make_tmap(&p.maps[6], out.hi, M, N, out.pitch, 32));  // per-warp 32-row store boxes
+    if (out.lo) NERF_TRY(tc_make_tmap(&p.maps[7], out.lo, M, N, out.pitch, 32));
     p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = N; p.n_stages = tc_pick_stages(BN, n, false);
     p.epi = 0; p.bias = bias; p.act = ACT_RELU;
     p.bits_out = bits; p.ld_bits = N / 32;
@@ -303,8 +303,8 @@ class TcMlp : public MlpEngine {
         p.kb[n].b_col = (int16_t)kc;
         n++;
       }
-    NERF_TRY(tc_make_tmap(&p.maps[6], out.hi, M, k1, out.pitch, 128));
-    if (out.lo) NERF_TRY(tc_make_tmap(&p.maps[7], out.lo, M, k1, out.pitch, 128));
+    NERF_TRY(tc_make_tmap(&p.maps[6], out.hi, M, k1, out.pitch, 32));
+    if (out.lo) NERF_TRY(tc_make_tmap(&p.maps[7], out.lo, M, k1, out.pitch, 32));
     p.n_kb = n; p.M = M; p.BN = BN; p.n_valid = k1; p.n_stages = tc_pick_stages(BN, n, false);
     p.epi = 1; p.r1 = r1; p.v1 = v1; p.mask_bits = mask_bits; p.ld_bits = k1 / 32;
     p.out_hi = out.hi; p.out_lo = out.lo; p.ld_out = out.pitch;
