@@ -296,9 +296,13 @@ def ours_arm(args):
                          "frac": None if ach is None else round(ach / peak, 4)}
     top = max((k for k in kernels if kernels[k]["achieved"] is not None), key=lambda k: kernels[k]["ms_per_step"])
     tk = kernels[top]
+    traffic = None
+    tpath = ROOT / "profiles" / "ncu_traffic.json"
+    if tpath.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        traffic = json.loads(tpath.read_text()).get(args.precision, {}).get(top, {}).get("dram_bytes_per_launch")
     roofline = {"kernel": top, "bound": "tensor" if tk["unit"] == "TFLOP/s" else "hbm", "achieved": tk["achieved"],
                 "peak": tc_peak if tk["unit"] == "TFLOP/s" else hbm_peak, "unit": tk["unit"], "frac": tk["frac"],
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(tk["ms_per_step"] / max(1.0, tk["launches_per_step"]), 5),
                 "share_of_step": round(tk["ms_per_step"] / ms_step, 4)}
 
@@ -324,19 +328,100 @@ def ours_arm(args):
         dist.destroy_process_group()
 
 
+def render_arm(args):
+    """configs[3]: full-image 800x800 render (640 000 rays, 128+128 samples), forward only, rays split over the ranks;
+    no collective.  value = render rays/s with the rays resident on the device; e2e = host arrays in, host image out."""
+    import torch
+    import torch.distributed as dist
+
+    import nerf_or_nothing_b200 as nb
+    from nerf_or_nothing_b200 import dist as nd
+    from nerf_or_nothing_b200.scene import synthetic_rays
+
+    rank, world, local = nd.env_rank_world()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    total = 640000
+    lo, hi = nd.shard_range(total, rank, world)
+    n = hi - lo
+    chunk = 16384
+    cfg = nb.default_config(n_rays=chunk, precision=nb.PRECISIONS[args.precision], device=local, randomized=0, **model_kw())
+    model = nb.AcceleratedMipNeRF(cfg)
+    rays, _ = synthetic_rays(n, width=800, height=800, n_views=1, seed=7 + rank)
+    hb = [rays[k] for k in ("origins", "directions", "radii", "nears", "fars")]
+    db = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb]
+    rgb, depth, acc = torch.empty(n, 3, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    stream = torch.cuda.ExternalStream(model.stream())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup // 3)):
+        model.render_dev(*db, n, rgb, depth, acc)
+    model.set_profiling(True)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = model.launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        model.render_dev(*db, n, rgb, depth, acc)
+    e1.record(stream)
+    model.synchronize()
+    sync_all()
+    prof = model.read_profile()
+    launches = model.launch_count() - l0
+    tt = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item()) / args.steps
+    w0 = time.perf_counter()
+    out = model.render(*hb)
+    w1 = time.perf_counter()
+    te = torch.tensor([(w1 - w0) * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        hbm_peak, tc_peak, peak_src = peaks()
+        work, n_params = algorithmic_work(n, N_SAMPLES)
+        fwd_ms = prof.get("mlp_fwd_gemm", (0, 0))[0] / args.steps
+        ach = work["mlp_fwd_gemm"][1] / 1e12 / (fwd_ms / 1e3) if fwd_ms else None
+        print(json.dumps({
+            "metric": "render rays/sec (forward only)", "value": total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "configs[3]: full-image 800x800 render (640000 rays, 128+128 samples), forward only, rays split "
+                                   f"across {world} GPU(s)", "rays_per_gpu": n, "chunk_rays": chunk, "precision": args.precision},
+            "e2e": {"value": total / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n * 5 * 4},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "mlp_fwd_gemm", "bound": "tensor", "achieved": None if ach is None else round(ach, 2), "peak": tc_peak,
+                         "unit": "TFLOP/s", "frac": None if ach is None else round(ach / tc_peak, 4), "traffic": None, "peak_source": peak_src},
+            "kernels": {k: {"ms_per_step": round(v[0] / args.steps, 4), "launches_per_step": v[1] / args.steps} for k, v in prof.items()},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("NERF_BENCH_PRECISION", "fp32"), choices=["fp32", "fp32_tc", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("NERF_BENCH_PRECISION", "fp32_tc"), choices=["fp32", "fp32_tc", "bf16"],
+                    help="fp32_tc (default): fp32-accurate bf16x3 split on tcgen05; fp32: CUDA-core FFMA; bf16: configs[2] mode")
+    ap.add_argument("--mode", default="train", choices=["train", "render"], help="render: configs[3], forward only")
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         reference_arm(args)
+    elif args.mode == "render":
+        render_arm(args)
     else:
         ours_arm(args)
 

@@ -23,6 +23,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 #include "gemm_tc.cuh"
 #include "sm100.cuh"
@@ -743,7 +744,49 @@ EncodeTiledFn get_encode() {
 
 }  // namespace
 
+namespace {
+// Encoding a tensor map costs microseconds of host time and a step issues ~270 of them over a fixed set of buffers:
+// memoise by (base, rows, cols, pitch, box) so steady-state steps only pay a hash lookup.
+struct TmapKey {
+  const void* base; uint64_t rows, cols, pitch; uint32_t box_rows;
+  bool operator==(const TmapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 1315423911ull + (h << 6) + (h >> 2));
+    h ^= (k.pitch * 2654435761ull + (h << 6) + (h >> 2));
+    h ^= ((uint64_t)k.box_rows * 40503ull + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+}  // namespace
+
+void tc_tmap_cache_clear() {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  g_tmap_cache.clear();
+}
+
 int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
+  const TmapKey key{base, rows, cols, pitch_elems, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
+  }
+  const int rc = tc_encode_tmap(out, base, rows, cols, pitch_elems, box_rows);
+  if (rc == 0) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+  }
+  return rc;
+}
+
+int tc_encode_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return 100002; }
   const cuuint64_t gdim[2] = {cols, rows};

@@ -56,7 +56,9 @@ struct alignas(64) TcParams {
   int head_n;           // 0..3
 };
 
-int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);
+int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);  // memoised
+int tc_encode_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);
+void tc_tmap_cache_clear();
 int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st);
 int tc_smem_bytes(int BN, int n_stages, bool mn_major);
 int tc_pick_stages(int BN, int n_kblocks, bool mn_major);

@@ -314,7 +314,7 @@ class TcMlp : public MlpEngine {
   static void wgrad_split(int N, int K, long M, int* splits, long* split_len) {
     const int BN = K > 256 ? 256 : round_up(K, 64);
     const long tiles = cdiv(N, 128) * cdiv(K, BN);
-    long s = cdiv(2 * 148, tiles);
+    long s = cdiv(148, tiles);  // one CTA per SM, one wave
     const long maxs = cdiv(M, 256);
     if (s > maxs) s = maxs;
     if (s < 1) s = 1;
