@@ -405,6 +405,68 @@ def render_arm(args):
         dist.destroy_process_group()
 
 
+def sweep_arm(args):
+    """configs[4]: MLP (depth x width) x batch sweep on one GPU — tensor-pipe throughput of the GEMM families and HBM GB/s of
+    compositing fwd/bwd against the roofline.  One JSON line per cell (not the driver's headline line)."""
+    import torch
+
+    import nerf_or_nothing_b200 as nb
+    from nerf_or_nothing_b200.scene import synthetic_rays
+
+    torch.cuda.set_device(0)
+    hbm_peak, tc_peak, peak_src = peaks()
+    cells = [(d, w, r) for (d, w) in ((4, 128), (8, 256), (8, 512)) for r in (4096, 16384, 65536)]
+    for depth, width, R in cells:
+        kw = dict(n_samples=N_SAMPLES, net_depth=depth, net_width=width, net_depth_condition=1, net_width_condition=width // 2,
+                  skip_layer=4, deg_point=16, deg_view=4)
+        try:
+            cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[args.precision], **kw)
+            model = nb.AcceleratedMipNeRF(cfg)
+            opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes())
+            rays, pix = synthetic_rays(R, width=800, height=800, seed=1)
+            hb = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"], pix)
+            db = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb)
+            for _ in range(3):
+                model.train_step_dev(opt, *db, R, 1e-4)
+            model.set_profiling(True)
+            stream = torch.cuda.ExternalStream(model.stream())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 3
+            e0.record(stream)
+            for _ in range(steps):
+                model.train_step_dev(opt, *db, R, 1e-4)
+            e1.record(stream)
+            model.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            prof = model.read_profile()
+            P, Dd, Wc = 96, 27, width // 2
+            lay = [(width, P, 0)] + [(width, width, P if (i % 4 == 0) else 0) for i in range(1, depth)] + [(Wc, width, Dd)]
+            M = R * N_SAMPLES * 2
+            fwd = 2 * M * sum(o * (a + b) for o, a, b in lay)
+            dgr = 2 * M * sum(o * a for i, (o, a, b) in enumerate(lay) if i > 0)
+
+            def tf(name, flops):
+                t = prof.get(name, (0, 0))[0] / steps
+                return round(flops / 1e12 / (t / 1e3), 1) if t > 0 else None
+
+            def gb(name, nbytes):
+                t = prof.get(name, (0, 0))[0] / steps
+                return round(nbytes / 1e9 / (t / 1e3), 1) if t > 0 else None
+
+            cf, cb = gb("composite_fwd", M * 24 + 2 * R * 32), gb("composite_bwd", M * 36 + 2 * R * 24)
+            print(json.dumps({"sweep": f"{depth}x{width}", "rays": R, "precision": args.precision, "ms_per_step": round(ms, 3),
+                              "train_rays_per_s": round(R / (ms / 1e3)), "chunk_launches_composite": prof.get("composite_fwd", (0, 0))[1] / steps,
+                              "fwd_tflops": tf("mlp_fwd_gemm", fwd), "dgrad_tflops": tf("mlp_dgrad_gemm", dgr), "wgrad_tflops": tf("mlp_wgrad_gemm", fwd),
+                              "tensor_peak_tflops": tc_peak, "composite_fwd_gbs": cf, "composite_bwd_gbs": cb, "hbm_peak_gbs": hbm_peak,
+                              "composite_fwd_frac": None if cf is None else round(cf / hbm_peak, 3),
+                              "composite_bwd_frac": None if cb is None else round(cb / hbm_peak, 3), "peak_source": peak_src}), flush=True)
+            model.close(); opt.close()
+            del db
+            torch.cuda.empty_cache()
+        except Exception as e:  # a cell that does not fit is reported, not fatal
+            print(json.dumps({"sweep": f"{depth}x{width}", "rays": R, "error": str(e)[:200]}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -413,7 +475,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("NERF_BENCH_PRECISION", "fp32_tc"), choices=["fp32", "fp32_tc", "bf16"],
                     help="fp32_tc (default): fp32-accurate bf16x3 split on tcgen05; fp32: CUDA-core FFMA; bf16: configs[2] mode")
-    ap.add_argument("--mode", default="train", choices=["train", "render"], help="render: configs[3], forward only")
+    ap.add_argument("--mode", default="train", choices=["train", "render", "sweep"], help="render: configs[3], forward only; sweep: configs[4]")
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -422,6 +484,8 @@ def main():
         reference_arm(args)
     elif args.mode == "render":
         render_arm(args)
+    elif args.mode == "sweep":
+        sweep_arm(args)
     else:
         ours_arm(args)
 

@@ -17,6 +17,16 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
+// These kernels must stay HBM-bound: with libm expf/log1pf/IEEE division the ~7 transcendentals per sample cost more
+// issue slots than the 24-36 bytes per sample cost memory time.  ex2.approx / lg2.approx / rcp.approx keep every
+// quantity within ~4e-7 relative (1e-7 absolute near 0) — far inside the 1e-4 + 1e-6 parity tolerance.
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  const float e = __expf(-fabsf(x));
+  const float r = __fdividef(1.f, 1.f + e);
+  return x >= 0.f ? r : e * r;
+}
+__device__ __forceinline__ float fast_softplus(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
+
 template <int V> struct VecLoad;
 template <> struct VecLoad<1> {
   static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
@@ -73,10 +83,10 @@ struct LaneSamples {
       tm[q] = (tv[q] + tv[q + 1]) / 2;
       if (RAW) {
         rs[q] = dv[q] + act.density_bias;
-        sig[q] = softplusf_(rs[q]);
+        sig[q] = fast_softplus(rs[q]);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          rc[q][a] = sigmoidf_(cv[q * 3 + a]);  // keep s = sigmoid(raw) for s(1-s)
+          rc[q][a] = fast_sigmoid(cv[q * 3 + a]);  // keep s = sigmoid(raw) for s(1-s)
           c[q][a] = rc[q][a] * (1.f + 2.f * act.rgb_padding) - act.rgb_padding;
         }
       } else {
@@ -92,7 +102,9 @@ struct LaneSamples {
     float om[V], p = 1.f;
 #pragma unroll
     for (int q = 0; q < V; q++) {
-      alpha[q] = 1.f - expf(-sig[q] * delta[q] * dl);
+      // alpha = 1 - exp(-s) (.cu:330); for small s the 3-term series keeps alpha's RELATIVE accuracy (no cancellation)
+      const float s = sig[q] * delta[q] * dl;
+      alpha[q] = s < 1e-2f ? s * (1.f - 0.5f * s * (1.f - s * (1.f / 3.f))) : 1.f - __expf(-s);
       om[q] = 1.f - alpha[q];
       p *= om[q];
     }
@@ -194,7 +206,7 @@ k_composite_bwd(const float* __restrict__ g, const float* __restrict__ rgb, cons
     suffix += dLdw[q] * ls.w[q];
     float cx = gx * wq, cy = gy * wq, cz = gz * wq;  // .cu:388
     if (RAW) {  // SN/MipNerfModel.cs:184-189
-      dsig *= sigmoidf_(ls.rs[q]);
+      dsig *= fast_sigmoid(ls.rs[q]);
       const float k = 1.f + 2.f * act.rgb_padding;
       cx *= ls.rc[q][0] * (1.f - ls.rc[q][0]) * k;
       cy *= ls.rc[q][1] * (1.f - ls.rc[q][1]) * k;

@@ -3,15 +3,10 @@
 // Replaces the inner loops of get_neuron_output* (.cu:36-90, one dot product per thread from global memory) and
 // backpropagate_neuron* (.cu:91-182, two global float atomics per multiply).
 //
-// One CTA computes one 128 x BN output tile:
-//   warp 4 (one elected lane)  TMA producer: cp.async.bulk.tensor boxes of 64 bf16 x rows, 128-byte swizzle,
-//                              into an n_stages-deep shared-memory ring guarded by full/empty mbarriers
-//   warp 5 (one elected lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16), 4 per stage,
-//                              accumulating in TMEM (BN fp32 columns); tcgen05.commit frees the stage / signals done
-//   warps 0-3                  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias + activation / ReLU mask
-//                              + rank-1 term / raw fp32 partial, bf16 hi(+lo) plane stores
-// 192 threads, <= 100 KB shared memory and 256 TMEM columns per CTA so that two CTAs share an SM: one CTA's
-// epilogue overlaps the other's main loop without a persistent scheduler.
+// Two kernels share the TMA / mbarrier / tcgen05 machinery of sm100.cuh:
+//   k_tc_gemm_persist  forward and dgrad (K-major operands): persistent, warp-specialised, accumulator double-buffered
+//                      in TMEM, per-warp TMA-store epilogue with bias/ReLU/bit-mask/head or rank-1/mask fused
+//   k_tc_wgrad         dW = dZ^T X (MN-major operands) split over the samples, bias gradient via a ones tile
 //
 // Operand layouts (sm100.cuh): K-major tiles for forward/dgrad (activations [M,K] and weights [N,K] are both
 // reduction-contiguous), MN-major tiles for wgrad (dW = dZ^T X: both operands are read "transposed" straight from
@@ -42,9 +37,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <bool MN_MAJOR>
-__global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __grid_constant__ TcParams p) {
-  constexpr int kTmemCols = MN_MAJOR ? 512 : 256;  // wgrad keeps 16 extra columns for the bias gradient
+// MN-major kernel (wgrad): one CTA = one 128 x BN tile of dW over a slice of the samples.
+//   warp 4 lane 0  TMA producer   boxes {64 cols, 64 rows} of the dZ / X planes, 128B-swizzled, n_stages-deep ring
+//   warp 5 lane 0  MMA issuer     tcgen05.mma M=128, N=BN, K=16, both operands MN-major (a_major = b_major = 1);
+//                                 + an N=16 MMA of the same dZ tile against a constant tile of ones: TMEM columns
+//                                 256..271 accumulate colsum(dZ) = the bias gradient for free
+//   warps 0-3      epilogue       tcgen05.ld -> fp32 partial tile [split][row][col] (+ bias column)
+// One CTA per SM (192 KB ring, 512 TMEM columns); the kernel runs at the HBM roofline of reading dZ and X once.
+__global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], done_bar;
   __shared__ uint32_t tmem_base_smem;
@@ -53,37 +53,29 @@ __global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __
   const int BN = p.BN;
   const int stage_bytes = kABytes + BN * 128;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ones = smem + (size_t)p.n_stages * stage_bytes;  // MN-major only: 8 KB of bf16 1.0
+  uint8_t* ones = smem + (size_t)p.n_stages * stage_bytes;  // 8 KB of bf16 1.0
 
-  const long row0 = (long)blockIdx.x * 128;  // first output row
-  const int col0 = blockIdx.y * BN;          // first output column
-  int n_kb;                                  // pipeline iterations
-  long red0 = 0;
-  if (!MN_MAJOR) {
-    n_kb = p.n_kb;
-  } else {
-    red0 = (long)blockIdx.z * p.split_len;
-    long red1 = red0 + p.split_len;
-    if (red1 > p.red_len) red1 = p.red_len;
-    const long nblk = red1 > red0 ? (red1 - red0 + 63) / 64 : 0;
-    n_kb = (int)nblk * p.n_pass;
-  }
-  const bool want_bias = MN_MAJOR && p.bias_out != nullptr && blockIdx.y == 0;
+  const long row0 = (long)blockIdx.x * 128;  // first output row (= column of the dZ planes)
+  const int col0 = blockIdx.y * BN;          // first output column (= column of the X planes)
+  const long red0 = (long)blockIdx.z * p.split_len;
+  long red1 = red0 + p.split_len;
+  if (red1 > p.red_len) red1 = p.red_len;
+  const long nblk = red1 > red0 ? (red1 - red0 + 63) / 64 : 0;
+  const int n_kb = (int)nblk * p.n_pass;
+  const bool want_bias = p.bias_out != nullptr && blockIdx.y == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
-  if (MN_MAJOR) {
-    for (int i = threadIdx.x; i < 2048; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
-    fence_proxy_async();
-  }
+  for (int i = threadIdx.x; i < 2048; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  fence_proxy_async();
   if (warp == 4) {
-    tmem_alloc<kTmemCols>(&tmem_base_smem);
+    tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) prefetch_tmap(&p.maps[i]);
+      for (int i = 0; i < 6; i++) prefetch_tmap(&p.maps[i]);
     }
   }
   tc_fence_before_sync();
@@ -92,8 +84,7 @@ __global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0) {  // ---------------------------------------------------------------- TMA producer
       for (int i = 0; i < n_kb; i++) {
         const int s = i % p.n_stages;
         const uint32_t ph = (i / p.n_stages) & 1;
@@ -101,25 +92,18 @@ __global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + kABytes;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-        if (!MN_MAJOR) {
-          const TcParams::KB kb = p.kb[i];
-          tma_load_2d(a_dst, &p.maps[kb.a], kb.a_col, (int)row0, &full_bar[s]);  // box {64, 128}
-          tma_load_2d(b_dst, &p.maps[kb.b], kb.b_col, col0, &full_bar[s]);       // box {64, BN}
-        } else {
-          const int blk = i / p.n_pass, ps = i % p.n_pass;
-          const int r = (int)(red0 + (long)blk * 64);
-          const CUtensorMap* ma = &p.maps[p.pass_a[ps]];
-          const CUtensorMap* mb = &p.maps[p.pass_b[ps]];
-          tma_load_2d(a_dst, ma, p.a_col0 + (int)row0, r, &full_bar[s]);  // boxes {64 cols, 64 rows} = 8 KB each
-          tma_load_2d(a_dst + 8192, ma, p.a_col0 + (int)row0 + 64, r, &full_bar[s]);
-          for (int c = 0; c < BN; c += 64) tma_load_2d(b_dst + (c >> 6) * 8192, mb, col0 + c, r, &full_bar[s]);
-        }
+        const int blk = i / p.n_pass, ps = i % p.n_pass;
+        const int r = (int)(red0 + (long)blk * 64);
+        const CUtensorMap* ma = &p.maps[p.pass_a[ps]];
+        const CUtensorMap* mb = &p.maps[p.pass_b[ps]];
+        tma_load_2d(a_dst, ma, p.a_col0 + (int)row0, r, &full_bar[s]);
+        tma_load_2d(a_dst + 8192, ma, p.a_col0 + (int)row0 + 64, r, &full_bar[s]);
+        for (int c = 0; c < BN; c += 64) tma_load_2d(b_dst + (c >> 6) * 8192, mb, col0 + c, r, &full_bar[s]);
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BN, MN_MAJOR, MN_MAJOR);
+    if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc = make_idesc_bf16(128, BN, true, true);
       const uint32_t idesc_bias = make_idesc_bf16(128, 16, true, true);
       const uint32_t ones_base = smem_u32(ones);
       bool bias_started = false;
@@ -131,188 +115,61 @@ __global__ void __launch_bounds__(kThreads, MN_MAJOR ? 1 : 2) k_tc_gemm(const __
         const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t b_base = a_base + kABytes;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {  // 4 x (K = 16) per 64-wide k-block
-          uint64_t da, db;
-          if (!MN_MAJOR) {
-            da = make_smem_desc(a_base + k * 32, 16, 1024);
-            db = make_smem_desc(b_base + k * 32, 16, 1024);
-          } else {
-            da = make_smem_desc(a_base + k * 2048, 8192, 1024);
-            db = make_smem_desc(b_base + k * 2048, 8192, 1024);
-          }
-          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        }
-        if (MN_MAJOR && want_bias && p.pass_b[i % p.n_pass] == 4) {
-          // db[n] += sum_m dZ[m, n]: the same A tile against a constant tile of ones (N = 16), TMEM columns 256..271
+        for (int k = 0; k < 4; k++)  // 16 reduction rows per MMA = 2 KB of each 64-column box
+          umma_bf16(tmem_base, make_smem_desc(a_base + k * 2048, 8192, 1024), make_smem_desc(b_base + k * 2048, 8192, 1024),
+                    idesc, (i > 0 || k > 0) ? 1u : 0u);
+        if (want_bias && p.pass_b[i % p.n_pass] == 4) {  // passes whose B plane is `hi`: (hi,hi) and (lo,hi) -> sum(hi + lo)
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint64_t da = make_smem_desc(a_base + k * 2048, 8192, 1024);
-            const uint64_t d1 = make_smem_desc(ones_base + k * 2048, 8192, 1024);
-            umma_bf16(tmem_base + 256, da, d1, idesc_bias, (bias_started || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + 256, make_smem_desc(a_base + k * 2048, 8192, 1024),
+                      make_smem_desc(ones_base + k * 2048, 8192, 1024), idesc_bias, (bias_started || k > 0) ? 1u : 0u);
           bias_started = true;
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        umma_commit(&empty_bar[s]);
       }
-      umma_commit(&done_bar);  // accumulator complete
+      umma_commit(&done_bar);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3: TMEM lanes 32w..32w+31)
-    const int tr = threadIdx.x;  // row inside the tile
-    const long row = row0 + tr;
+    const long row = row0 + threadIdx.x;
     if (n_kb > 0) {
       mbar_wait(&done_bar, 0);
       tc_fence_after_sync();
     }
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    if (MN_MAJOR) {
-      // raw fp32 partial: out[split][row][col] (+ the bias column)
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        if (n_kb > 0) { tmem_ld_32x32(t_lane + c0, r); tmem_ld_wait(); }
-        else {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (n_kb > 0) { tmem_ld_32x32(t_lane + c0, r); tmem_ld_wait(); }
+      else {
 #pragma unroll
-          for (int j = 0; j < 32; j++) r[j] = 0u;
-        }
-        const int col = col0 + c0;
-        if (row < p.rows_valid) {
-          float* dst = p.out_f32 + (long)blockIdx.z * p.split_stride + row * p.ld_f32 + col;
+        for (int j = 0; j < 32; j++) r[j] = 0u;
+      }
+      const int col = col0 + c0;
+      if (row < p.rows_valid) {
+        float* dst = p.out_f32 + (long)blockIdx.z * p.split_stride + row * p.ld_f32 + col;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col + j + 3 < p.n_valid) {
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            } else {
-              for (int q = 0; q < 4; q++)
-                if (col + j + q < p.n_valid) dst[j + q] = __uint_as_float(r[j + q]);
-            }
+        for (int j = 0; j < 32; j += 4) {
+          if (col + j + 3 < p.n_valid) {
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+            for (int q = 0; q < 4; q++)
+              if (col + j + q < p.n_valid) dst[j + q] = __uint_as_float(r[j + q]);
           }
         }
       }
-      if (want_bias) {
-        uint32_t r[32];
-        if (n_kb > 0) { tmem_ld_32x32(t_lane + 256, r); tmem_ld_wait(); }
-        else r[0] = 0u;
-        if (row < p.rows_valid) p.bias_out[(long)blockIdx.z * p.bias_split_stride + row] = __uint_as_float(r[0]);
-      }
-    } else {
-      // planes out through shared memory + TMA stores: 6 slots of 16 KB (64 columns x 128 rows, 128B-swizzled) in
-      // the now idle stage ring; one bulk group per 64 output columns (hi box [+ lo box])
-      uint8_t* stg = smem;
-      const bool row_ok = row < p.M;
-      const float ri = (p.epi == 1 && p.r1 && row_ok) ? __ldg(p.r1 + row) : 0.f;
-      const int n_groups = BN / 64;
-      float head_acc[3] = {0.f, 0.f, 0.f};
-      for (int g = 0; g < n_groups; g++) {
-        const int slot = (g % 3) * 2;
-        if (g >= 3) {
-          if (threadIdx.x == 0) tma_store_wait_read<2>();
-          named_barrier_sync(1, 128);
-        }
-        uint8_t* row_hi = stg + (size_t)slot * 16384 + tr * 128;
-        uint8_t* row_lo = row_hi + 16384;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-          const int c0 = g * 64 + half * 32;
-          const int col = col0 + c0;
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + c0, r);
-          tmem_ld_wait();
-          float v[32];
-          if (p.epi == 0) {  // Z = acc + b (.cu:45), Y = act(Z)
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const float z = __uint_as_float(r[j]) + ((p.bias && col + j < p.n_valid) ? __ldg(p.bias + col + j) : 0.f);
-              v[j] = p.act == ACT_RELU ? fmaxf(z, 0.f) : z;
-            }
-            if (p.bits_out) {
-              uint32_t bits = 0u;
-#pragma unroll
-              for (int j = 0; j < 32; j++) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-              if (row_ok && col < p.n_valid) p.bits_out[row * p.ld_bits + (col >> 5)] = bits;
-            }
-            if (p.head_n > 0 && col < p.n_valid) {
-#pragma unroll
-              for (int n = 0; n < 3; n++) {
-                if (n < p.head_n) {
-                  const float* hw = p.head_w + (long)n * p.n_valid + col;
-                  float a = head_acc[n];
-#pragma unroll
-                  for (int j = 0; j < 32; j++) a = fmaf(v[j], __ldg(hw + j), a);
-                  head_acc[n] = a;
-                }
-              }
-            }
-          } else {  // dgrad: (+ r1[m] v1[k]) then the ReLU mask of the layer below (.cu:99)
-            uint32_t mk[16];
-            const bool use_bits = p.mask_bits != nullptr;
-            const uint32_t mbits = (use_bits && row_ok && col < p.n_valid) ? __ldg(p.mask_bits + row * p.ld_bits + (col >> 5)) : 0u;
-            const bool use_mask = p.mask != nullptr && !use_bits;
-            if (use_mask && row_ok && col < p.n_valid) {
-              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + row * p.ld_mask + col);
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const uint4 t = __ldg(mp + q);
-                mk[q * 4] = t.x; mk[q * 4 + 1] = t.y; mk[q * 4 + 2] = t.z; mk[q * 4 + 3] = t.w;
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 16; q++) mk[q] = 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              float x = __uint_as_float(r[j]);
-              if (p.r1 && col + j < p.n_valid) x = fmaf(ri, __ldg(p.v1 + col + j), x);
-              if (use_bits) x = ((mbits >> j) & 1u) ? x : 0.f;
-              if (use_mask) {
-                const uint32_t w = mk[j >> 1];
-                const uint32_t h = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                x = ((h & 0x8000u) == 0 && (h & 0x7FFFu) != 0) ? x : 0.f;
-              }
-              v[j] = x;
-            }
-          }
-          // bf16 split planes: hi = bf16(v), lo = bf16(v - hi); 16-byte chunk c of row r lives at chunk c ^ (r & 7)
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int chunk = (half * 4 + q) ^ (tr & 7);
-            *reinterpret_cast<uint4*>(row_hi + (chunk << 4)) =
-                make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                           pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-          }
-          if (p.out_lo) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const int chunk = (half * 4 + q) ^ (tr & 7);
-              *reinterpret_cast<uint4*>(row_lo + (chunk << 4)) =
-                  make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-            }
-          }
-        }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
-        named_barrier_sync(1, 128);
-        if (threadIdx.x == 0) {
-          tma_store_2d(&p.maps[6], stg + (size_t)slot * 16384, col0 + g * 64, (int)row0);
-          if (p.out_lo) tma_store_2d(&p.maps[7], stg + (size_t)(slot + 1) * 16384, col0 + g * 64, (int)row0);
-          tma_store_commit();
-        }
-      }
-      if (p.epi == 0 && p.head_n > 0 && row_ok) {
-#pragma unroll
-        for (int n = 0; n < 3; n++)
-          if (n < p.head_n) p.head_out[row * p.head_n + n] = head_acc[n] + (p.head_b ? __ldg(p.head_b + n) : 0.f);
-      }
-      if (threadIdx.x == 0) tma_store_wait_read<0>();  // shared memory must outlive the bulk reads
+    }
+    if (want_bias) {
+      uint32_t r[32];
+      if (n_kb > 0) { tmem_ld_32x32(t_lane + 256, r); tmem_ld_wait(); }
+      else r[0] = 0u;
+      if (row < p.rows_valid) p.bias_out[(long)blockIdx.z * p.bias_split_stride + row] = __uint_as_float(r[0]);
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 4) tmem_dealloc<512>(tmem_base);
 }
 
 // Persistent K-major variant (forward / dgrad): one CTA per SM walks row tiles tile = blockIdx.x + i * gridDim.x.
@@ -824,20 +681,11 @@ static int persist_stages(int BN) {
   int s = budget / (kABytes + BN * 128);
   return s > kMaxStages ? kMaxStages : (s < 1 ? 1 : s);
 }
-static bool use_persistent() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("NERF_TC_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-
 int tc_launch(const TcParams& p_in, bool mn_major, dim3 grid, cudaStream_t st) {
   TcParams p = p_in;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_tc_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_tc_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  });
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
   if (p.BN % 16 || p.BN < 16 || p.BN > 256 || p.n_stages < 1 || p.n_stages > kMaxStages) { set_error("tc_launch: bad BN=%d stages=%d", p.BN, p.n_stages); return 100001; }
   if (mn_major && p.BN % 64) { set_error("tc_launch: MN-major needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
@@ -862,8 +710,7 @@ int tc_launch(const TcParams& p_in, bool mn_major, dim3 grid, cudaStream_t st) {
     return 0;
   }
   const size_t smem = (size_t)tc_smem_bytes(p.BN, p.n_stages, mn_major);
-  if (mn_major) k_tc_gemm<true><<<grid, kThreads, smem, st>>>(p);
-  else k_tc_gemm<false><<<grid, kThreads, smem, st>>>(p);
+  k_tc_wgrad<<<grid, kThreads, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
 }
@@ -911,15 +758,18 @@ long thin_wgrad_chunk(long M) {  // ~4 blocks per SM, at least 256 rows each
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
                              long M, int N, int K, float* workspace, cudaStream_t st) {
   if (N > 4) { set_error("thin_wgrad_planes: N=%d", N); return 100001; }
-  if (N > 3 || K > 256 || K % 8) { set_error("thin_wgrad_planes: N=%d K=%d unsupported", N, K); return 100001; }
+  if (N > 3 || K % 8) { set_error("thin_wgrad_planes: N=%d K=%d unsupported", N, K); return 100001; }
   const long chunk = thin_wgrad_chunk(M);
   const int chunks = (int)cdiv(M, chunk);
   float* part = workspace;
-  float* partb = workspace + (size_t)chunks * N * K;
-  k_thin_wgrad_planes_partial<<<chunks, 256, 0, st>>>(xh, xl, ldx, dZ, M, N, K, chunk, part, partb);
-  NERF_CHECK_LAUNCH();
-  NERF_TRY(launch_reduce_partials(part, chunks, (long)N * K, N, K, K, dW, K, 0, st));
-  if (db) NERF_TRY(launch_reduce_partials(partb, chunks, N, 1, N, N, db, N, 0, st));
+  float* partb = workspace + (size_t)chunks * N * 256;
+  for (int k0 = 0; k0 < K; k0 += 256) {  // the kernel covers 256 columns (8 per lane) per pass
+    const int kp = K - k0 < 256 ? K - k0 : 256;
+    k_thin_wgrad_planes_partial<<<chunks, 256, 0, st>>>(xh + k0, xl ? xl + k0 : nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    NERF_CHECK_LAUNCH();
+    NERF_TRY(launch_reduce_partials(part, chunks, (long)N * kp, N, kp, kp, dW, K, k0, st));
+    if (db && k0 == 0) NERF_TRY(launch_reduce_partials(partb, chunks, N, 1, N, N, db, N, 0, st));
+  }
   return 0;
 }
 

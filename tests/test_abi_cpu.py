@@ -75,3 +75,30 @@ def test_lr_schedule_matches_oracle():
 
     for step in (0, 1, 100, 2500, 50000, 1000000):
         assert abs(nb.learning_rate_decay(step) - orc.learning_rate_decay(step)) <= 1e-6 * orc.learning_rate_decay(step) + 1e-12
+
+
+def _build_cpp_example(tmp_path):
+    import subprocess
+
+    exe = tmp_path / "train_loop"
+    libdir = ROOT / "nerf_or_nothing_b200"
+    cmd = ["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17", "-O1", f"-I{ROOT / 'include'}",
+           str(ROOT / "examples" / "train_loop.cpp"), f"-L{libdir}", "-lnerfb200", f"-Wl,-rpath,{libdir}", "-o", str(exe)]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/nerfb200.hpp (the five reference class names in C++) links against the C ABI; with no GPU the native
+    host exits with the library's 'no CPU path' error instead of computing anything."""
+    import subprocess
+
+    nb.lib()
+    exe = _build_cpp_example(tmp_path)
+    n = ctypes.c_int()
+    nb.lib().nerf_device_count(ctypes.byref(n))
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    if n.value == 0:
+        assert r.returncode == 2 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+    else:
+        assert r.returncode == 0 and "Step 3/3, Loss:" in r.stdout, (r.returncode, r.stdout, r.stderr)

@@ -1,0 +1,39 @@
+"""-m gpu: BASELINE.json's training criterion — the loss curve of the tensor-core modes stays within 1 % of the fp32
+CUDA-core path over 1000 Adam steps on identical batches, uniforms and initial weights (8x256 net, 64+64 samples)."""
+import numpy as np
+import pytest
+
+import nerf_or_nothing_b200 as nb
+from nerf_or_nothing_b200.scene import synthetic_rays
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_loss_curve_within_one_percent_over_1k_steps():
+    R, S, steps, pool = 256, 64, 1000, 64
+    kw = dict(n_rays=R, n_samples=S)
+    models = {p: nb.AcceleratedMipNeRF(nb.default_config(precision=p, **kw)) for p in ("fp32", "fp32_tc", "bf16")}
+    opts = {p: nb.AcceleratedAdamOptimizer(m.GetLayerSizes()) for p, m in models.items()}
+    p0 = models["fp32"].get_params()
+    for m in models.values():
+        m.set_params(p0)
+    batches = [synthetic_rays(R, width=100, height=100, seed=1000 + b) for b in range(pool)]
+    curves = {p: [] for p in models}
+    for step in range(1, steps + 1):
+        rays, pix = batches[step % pool]
+        lr = 5e-4
+        for p, m in models.items():
+            m.set_step(step)  # same Philox counters -> same sampling uniforms in every model
+            curves[p].append(m.train_step(opts[p], rays["origins"], rays["directions"], rays["radii"], rays["nears"],
+                                          rays["fars"], rays["loss_mults"], pix, lr))
+    c = {p: np.asarray(v, np.float64) for p, v in curves.items()}
+    assert c["fp32"][-50:].mean() < 0.7 * c["fp32"][:50].mean(), "training did not reduce the loss"
+    win = 50
+    ref = c["fp32"].reshape(-1, win).mean(1)
+    for p in ("fp32_tc", "bf16"):
+        w = c[p].reshape(-1, win).mean(1)
+        rel = np.abs(w - ref) / ref
+        print(f"{p}: max windowed ({win}-step) loss deviation {rel.max():.3%}; per-step max {np.abs(c[p] - c['fp32']).max() / c['fp32'].mean():.3%}; "
+              f"loss {c[p][:win].mean():.4f} -> {c[p][-win:].mean():.4f}")
+        assert rel.max() <= 0.01, (p, rel.max())
