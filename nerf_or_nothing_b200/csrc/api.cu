@@ -194,7 +194,7 @@ int validate(const nerf_config& c) {
 }
 
 // forward of all levels for rays [c0, c0+rc) of the current batch
-int forward_chunk(nerf_mipnerf* h, int c0, int rc) {
+int forward_chunk(nerf_mipnerf* h, int c0, int rc, bool for_training = true) {
   const nerf_config& c = h->cfg;
   const int S = h->S;
   for (int l = 0; l < h->NL; l++) {
@@ -208,7 +208,8 @@ int forward_chunk(nerf_mipnerf* h, int c0, int rc) {
     { ProfScope ps(PC_ENCODE, h->st);
     NERF_TRY(launch_cast_encode_fused(L.t, h->origins + (size_t)c0 * 3, h->dirs + (size_t)c0 * 3, h->radii + c0, rc, S,
                                       c.deg_point, c.deg_view, h->mlp->encode_targets(l), h->st)); }
-    NERF_TRY(h->mlp->forward(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
+    if (for_training) NERF_TRY(h->mlp->forward(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
+    else NERF_TRY(h->mlp->forward_only(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
     L.last_rows = (long)rc * S;
     { ProfScope ps(PC_COMPOSITE_FWD, h->st);
     NERF_TRY(launch_composite_fwd(L.raw_rgb, L.raw_density, L.t, h->dirs + (size_t)c0 * 3, rc, S, c.white_bkgd,
@@ -553,7 +554,7 @@ int nerf_mipnerf_render_dev(nerf_mipnerf* h, const float* o, const float* d, con
     set_batch_dev(h, o + b0 * 3, d + b0 * 3, radii + b0, nears + b0, fars + b0, nullptr, nullptr);
     const uint32_t keep = h->ray_offset;
     h->ray_offset = keep + (uint32_t)b0;
-    const int s = forward_chunk(h, 0, rc);
+    const int s = forward_chunk(h, 0, rc, false);
     h->ray_offset = keep;
     NERF_TRY(s);
     auto& L = h->lv[last];
@@ -576,7 +577,7 @@ int nerf_mipnerf_render(nerf_mipnerf* h, const float* o, const float* d, const f
     NERF_TRY(upload_batch(h, o + b0 * 3, d + b0 * 3, radii + b0, nears + b0, fars + b0, nullptr, nullptr, rc));
     const uint32_t keep = h->ray_offset;
     h->ray_offset = keep + (uint32_t)b0;
-    const int s = forward_chunk(h, 0, rc);
+    const int s = forward_chunk(h, 0, rc, false);
     h->ray_offset = keep;
     NERF_TRY(s);
     auto& L = h->lv[last];

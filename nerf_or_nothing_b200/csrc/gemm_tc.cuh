@@ -63,6 +63,12 @@ int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st);
 int tc_smem_bytes(int BN, int n_stages, bool mn_major);
 int tc_pick_stages(int BN, int n_kblocks, bool mn_major);
 
+// whole-MLP forward with TMEM-resident activations (mlp_fused.cu); bf16 planes only
+int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv_bfloat16* dir, int dir_pitch,
+                             const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
+                             const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
+                             float* raw_density, float* raw_rgb, cudaStream_t st);
+
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]
 int launch_f32_to_planes(const float* src, int src_pitch, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,

@@ -50,6 +50,10 @@ class MlpEngine {
   virtual int prepare(const float* params, cudaStream_t st) = 0;
   // raw (pre-activation) heads: raw_density [M], raw_rgb [M,3]; caches activations of `level`
   virtual int forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) = 0;
+  // same heads, but no backward pass will follow: an engine may skip the activation caches (rendering)
+  virtual int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) {
+    return forward(level, M, params, raw_density, raw_rgb, st);
+  }
   // accumulates dL/dparams into grads from dL/d raw heads
   virtual int backward(int level, long M, const float* params, float* grads, const float* d_raw_density,
                        const float* d_raw_rgb, cudaStream_t st) = 0;

@@ -10,6 +10,7 @@
 //             splits the sample dimension over CTAs and reduces the fp32 partials in a fixed order.
 // The N=1 / N=3 heads stay on CUDA cores (too thin for a UMMA tile) but read the same planes.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm_tc.cuh"
@@ -96,6 +97,7 @@ class TcMlp : public MlpEngine {
   // refresh the bf16 weight planes (and their transposes for dgrad) from the fp32 master parameters
   int prepare(const float* params, cudaStream_t st) override {
     ProfScope ps(PC_CAST, st);
+    fconsts_dirty_ = true;
     for (int l = 0; l < s_.L; l++) {
       const LayerInfo& L = s_.layers[l];
       if (L.out <= 4) continue;
@@ -148,6 +150,49 @@ class TcMlp : public MlpEngine {
       NERF_TRY(launch_thin_fwd_planes(c->hi, c->lo, c->pitch, params + L.w_off, params + L.b_off, raw_rgb, M, 3, s_.Wc, st));
     }
     return 0;
+  }
+
+  // Rendering: no backward follows, so in bf16 mode the whole net runs as one kernel with the activations kept in
+  // tensor memory (mlp_fused.cu) instead of one GEMM launch per layer with the activations written to HBM.
+  bool can_fuse_forward() const {
+    return !split_ && s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 20 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
+           getenv("NERF_NO_FUSED_FORWARD") == nullptr;
+  }
+
+  int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
+    if (!can_fuse_forward()) return forward(level, M, params, raw_density, raw_rgb, st);
+    Level& lv = levels_[level];
+    const int D = s_.D;
+    std::vector<int> bias_off(D + 1), kpad(D + 1), in_b(D + 1);
+    std::vector<const __nv_bfloat16*> wpl(D + 1);
+    for (int s = 0; s <= D; s++) {
+      const int l = s < D ? s : D + 1;
+      bias_off[s] = s * 256;
+      kpad[s] = wp_[l].pitch; in_b[s] = s_.layers[l].in_b; wpl[s] = wp_[l].hi;
+    }
+    const int head_d_off = D * 256 + 128, head_rgb_off = head_d_off + 260, n_consts = head_rgb_off + 3 * 128 + 4;
+    if (!fconsts_) {
+      NERF_CUDA(cudaMalloc(&fconsts_, n_consts * sizeof(float)));
+      owned_.push_back(fconsts_);
+      NERF_CUDA(cudaMemsetAsync(fconsts_, 0, n_consts * sizeof(float), st));
+    }
+    if (fconsts_dirty_) {  // gather biases and head weights once per parameter version
+      ProfScope ps(PC_CAST, st);
+      for (int s = 0; s <= D; s++) {
+        const LayerInfo& L = s_.layers[s < D ? s : D + 1];
+        NERF_CUDA(cudaMemcpyAsync(fconsts_ + bias_off[s], params + L.b_off, L.out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+      const LayerInfo& Ld = s_.layers[D];
+      const LayerInfo& Lr = s_.layers[D + 2];
+      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off, params + Ld.w_off, 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off + 256, params + Ld.b_off, sizeof(float), cudaMemcpyDeviceToDevice, st));
+      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off, params + Lr.w_off, 3 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off + 384, params + Lr.b_off, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      fconsts_dirty_ = false;
+    }
+    ProfScope ps(PC_MLP_FWD, st);
+    return launch_mlp_fused_forward(lv.enc_pos.hi, pos_pitch_, lv.enc_dir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
+                                    s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb, st);
   }
 
   int backward(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
@@ -365,6 +410,8 @@ class TcMlp : public MlpEngine {
   Plane dz_[2];
   std::vector<Plane> wp_, wtp_;
   float* ws_ = nullptr;
+  float* fconsts_ = nullptr;  // fused forward: biases + head weights, gathered per parameter version
+  bool fconsts_dirty_ = true;
   size_t bytes_ = 0;
   std::vector<void*> owned_;
 };

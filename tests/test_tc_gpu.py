@@ -140,3 +140,31 @@ def test_tc_whole_step_and_training(precision):
             losses.append(mod.train_step(opt, rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"],
                                          rays["loss_mults"], pix, 1e-3))
         assert abs(losses[0] - losses[1]) <= 1e-2 * losses[1], (step, losses)
+
+
+@pytest.mark.parametrize("R", [200, 1], ids=["R200-chunked", "R1"])
+def test_fused_forward_render_bf16(R, monkeypatch):
+    """Rendering in bf16 mode runs the whole MLP as ONE kernel with TMEM-resident activations (mlp_fused.cu).  It must
+    agree with the fp64 oracle within the bf16 tolerance and with the layer-by-layer bf16 chain (same operands, same
+    roundings between layers) far tighter; ragged last tile (R*S not a multiple of 128 rows) and tile loop included."""
+    m, ncfg, ocfg = _model(64, "bf16", **NET)
+    S = ncfg.n_samples
+    rays, pix, _ = batch(R, S)
+    params = _params_with_biases(ocfg)
+    m.set_params(params)
+    u = np.stack([orc.sampling_uniforms(7, 0, lv, 0, R, S + 1) for lv in range(2)])
+    args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    monkeypatch.delenv("NERF_NO_FUSED_FORWARD", raising=False)
+    rgb, depth, acc = m.render(*args)
+    monkeypatch.setenv("NERF_NO_FUSED_FORWARD", "1")
+    rgb2, depth2, acc2 = m.render(*args)
+    monkeypatch.delenv("NERF_NO_FUSED_FORWARD")
+    o = orc.train_gradient(ocfg, params, rays, pix, u, with_backward=False, prec="f64")
+    print(f"fused vs layered: rgb {np.abs(rgb - rgb2).max():.2e}  fused vs f64: rgb {np.abs(rgb - o['comp_rgb'][1]).max():.2e} "
+          f"acc {np.abs(acc - o['acc'][1]).max():.2e}")
+    assert np.isfinite(rgb).all()
+    np.testing.assert_allclose(rgb, o["comp_rgb"][1], atol=TOL["bf16"])
+    np.testing.assert_allclose(acc, o["acc"][1], atol=TOL["bf16"])
+    np.testing.assert_allclose(depth, o["depth"][1], atol=TOL["bf16"] * float(rays["fars"].max()))
+    np.testing.assert_allclose(rgb, rgb2, atol=2e-3)
+    np.testing.assert_allclose(acc, acc2, atol=2e-3)
