@@ -102,32 +102,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {  // ---------------------------------------------------------------- MMA issuer
+    {  // ---------------------------------------------------------------- MMA issuer (uniform warp, one elected lane issues)
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, BN, true, true);
       const uint32_t idesc_bias = make_idesc_bf16(128, 16, true, true);
-      const uint32_t ones_base = smem_u32(ones);
+      const uint64_t desc0 = make_smem_desc(0, 8192, 1024);  // + (shared address >> 4)
+      const uint32_t ones_base = smem_u32(ones), smem_base = smem_u32(smem);
       bool bias_started = false;
       for (int i = 0; i < n_kb; i++) {
         const int s = i % p.n_stages;
         const uint32_t ph = (i / p.n_stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after_sync();
-        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_base = a_base + kABytes;
+        const uint32_t a_base = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
+        const uint64_t da = desc0 + (a_base >> 4), db = desc0 + ((a_base + kABytes) >> 4);
+        const bool bias_pass = want_bias && p.pass_b[i % p.n_pass] == 4;  // passes whose B plane is `hi`: (hi,hi) and (lo,hi) -> sum(hi + lo)
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)  // 16 reduction rows per MMA = 2 KB of each 64-column box
-          umma_bf16(tmem_base, make_smem_desc(a_base + k * 2048, 8192, 1024), make_smem_desc(b_base + k * 2048, 8192, 1024),
-                    idesc, (i > 0 || k > 0) ? 1u : 0u);
-        if (want_bias && p.pass_b[i % p.n_pass] == 4) {  // passes whose B plane is `hi`: (hi,hi) and (lo,hi) -> sum(hi + lo)
+          for (int k = 0; k < 4; k++)  // 16 reduction rows per MMA = 2 KB of each 64-column box
+            umma_bf16(tmem_base, da + k * 128, db + k * 128, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (bias_pass) {
+            const uint64_t d1 = desc0 + (ones_base >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_bf16(tmem_base + 256, make_smem_desc(a_base + k * 2048, 8192, 1024),
-                      make_smem_desc(ones_base + k * 2048, 8192, 1024), idesc_bias, (bias_started || k > 0) ? 1u : 0u);
-          bias_started = true;
+            for (int k = 0; k < 4; k++) umma_bf16(tmem_base + 256, da + k * 128, d1 + k * 128, idesc_bias, (bias_started || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        if (bias_pass) bias_started = true;
       }
-      umma_commit(&done_bar);
+      if (leader) umma_commit(&done_bar);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3: TMEM lanes 32w..32w+31)
@@ -260,9 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm_persist(const __grid_co
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (uniform warp, one elected lane issues)
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024);  // + (shared address >> 4)
+      const uint32_t smem_base = smem_u32(smem);
       uint32_t it = 0, t = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t++) {
         const uint32_t b = t & 1;
@@ -274,16 +281,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm_persist(const __grid_co
           const uint32_t ph = (it / p.n_stages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
-          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_base = a_base + kABytes;
+          const uint32_t a_base = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
+          const uint64_t da = desc0 + (a_base >> 4), db = desc0 + ((a_base + kABytes) >> 4);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_bf16(acc, make_smem_desc(a_base + k * 32, 16, 1024), make_smem_desc(b_base + k * 32, 16, 1024), idesc,
-                      (i > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+            for (int k = 0; k < 4; k++) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+          }
         }
-        umma_commit(&tfull_bar[b]);
+        if (leader) umma_commit(&tfull_bar[b]);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue: warp w owns rows 32w..32w+31

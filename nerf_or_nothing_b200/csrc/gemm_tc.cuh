@@ -67,7 +67,8 @@ int tc_pick_stages(int BN, int n_kblocks, bool mn_major);
 int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv_bfloat16* dir, int dir_pitch,
                              const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
-                             float* raw_density, float* raw_rgb, cudaStream_t st);
+                             float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
+                             cudaStream_t st);  // act_out != nullptr: also write every layer's activations + ReLU bit planes
 
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]

@@ -26,19 +26,13 @@ namespace {
 
 using namespace sm100;
 
-constexpr int kThreadsF = 192;
-constexpr int kWStages = 6;
+constexpr int kThreadsF = 320;
+constexpr int kWStages = 6;                       // render; training gives one stage to the activation staging
 constexpr int kWStageBytes = 128 * 128;           // [128 rows (N half) x 64 bf16]
-constexpr int kEncBytes = 2 * 16384 + 16384;      // pos: 2 boxes of [128 x 64]; dir: 1 box
-constexpr int kMaxSteps = 20;
+constexpr int kEncBytes = 2 * 16384 + 16384;      // per tile: position encoding 2 boxes of [128 x 64], direction 1 box
+constexpr int kMaxSteps = 12;
+constexpr int kStageSlot = 4096;                  // per epilogue warp: one [32 rows x 64 bf16] store box
 
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -77,198 +71,314 @@ struct alignas(64) FusedParams {
   int head_d_off, head_rgb_off;
   float* raw_density;   // [M]
   float* raw_rgb;       // [M, 3]
+  // training only: every step's activations [M, N] bf16 (box {64, 32}, one store per epilogue warp) and ReLU bit planes
+  CUtensorMap map_act[kMaxSteps];
+  uint32_t* bits[kMaxSteps];
 };
 
 namespace {
 
+// One 32-column chunk of the accumulator: + bias, ReLU, bf16 pairs out (two per 32-bit TMEM column of the next A
+// operand).  HEAD = 0: ReLU on the packed pair (one HMNMX2 per two values).  HEAD = 1 / 3: the density / rgb head
+// rides along as FMAs on the fp32 activations.  BITS: also the ReLU mask of the 32 columns (bit j = column j passed),
+// gathered from the sign bits with one funnel shift per value (four independent chains of eight).
+template <int HEAD, bool BITS>
+__device__ __forceinline__ uint32_t epi_chunk(const uint32_t (&r)[32], const float* bias, const float* head_w, float (&head)[3],
+                                              uint32_t* packed16) {
+  const float4* bv = reinterpret_cast<const float4*>(bias);
+  float x[32];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 bb = bv[q];
+    x[4 * q] = __uint_as_float(r[4 * q]) + bb.x; x[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+    x[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z; x[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+  }
+  uint32_t mask = 0u;
+  if (BITS) {
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int e = 7; e >= 0; e--) m[c] = __funnelshift_l(__float_as_uint(x[8 * c + e]), m[c], 1);  // m = m << 1 | sign
+    mask = ~__byte_perm(__byte_perm(m[0], m[1], 0x0040), __byte_perm(m[2], m[3], 0x0040), 0x5410);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    float x0 = x[4 * q], x1 = x[4 * q + 1], x2 = x[4 * q + 2], x3 = x[4 * q + 3];
+    if (HEAD == 0) {
+      const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+      __nv_bfloat162 a = __hmax2(__floats2bfloat162_rn(x0, x1), z), b = __hmax2(__floats2bfloat162_rn(x2, x3), z);
+      packed16[2 * q] = *reinterpret_cast<uint32_t*>(&a);
+      packed16[2 * q + 1] = *reinterpret_cast<uint32_t*>(&b);
+    } else {
+      x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+#pragma unroll
+      for (int n = 0; n < HEAD; n++) {
+        const float4 w = reinterpret_cast<const float4*>(head_w + n * 128)[q];
+        head[n] = fmaf(x0, w.x, head[n]); head[n] = fmaf(x1, w.y, head[n]);
+        head[n] = fmaf(x2, w.z, head[n]); head[n] = fmaf(x3, w.w, head[n]);
+      }
+      packed16[2 * q] = pack2(x0, x1);
+      packed16[2 * q + 1] = pack2(x2, x3);
+    }
+  }
+  return mask;
+}
+template <bool BITS>
+__device__ __forceinline__ uint32_t epi_chunk_any(int head_kind, const uint32_t (&r)[32], const float* bias, const float* head_w,
+                                                  float (&head)[3], uint32_t* packed16) {
+  if (head_kind == 0) return epi_chunk<0, BITS>(r, bias, head_w, head, packed16);
+  if (head_kind == 1) return epi_chunk<1, BITS>(r, bias, head_w, head, packed16);
+  return epi_chunk<3, BITS>(r, bias, head_w, head, packed16);
+}
+// 16 packed words = 32 bf16 columns = half of this thread's 128-byte row of the warp's store box (128-byte swizzle)
+__device__ __forceinline__ void stage_half_row(uint8_t* row_ptr, int half, int swz, const uint32_t* pk) {
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    *reinterpret_cast<uint4*>(row_ptr + (((half * 4 + q) ^ swz) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// One CTA walks PAIRS of 128-row tiles.  Tensor memory (512 columns): per tile t, ACT[t] = 128 columns holding the
+// 256 bf16 activations of the current layer (updated IN PLACE once the layer's MMAs are complete) and ACC[t] = 128
+// fp32 accumulator columns (one N-half of the layer).  Both tiles consume every weight stage, so a [128 x 64] weight
+// tile is fetched from L2 once per 256 rows.  Warps 0-3 are the epilogue of tile 0, warps 4-7 of tile 1 (warp % 4 =
+// the TMEM lane quarter it may access), warp 8 the TMA producer, warp 9 the MMA issuer.
+// TRAIN: every layer's activations and ReLU bit planes are also written out for the backward pass (each epilogue warp
+// restages its 32 rows in shared memory and issues its own TMA store).
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_constant__ FusedParams p) {
+  constexpr int NS = TRAIN ? kWStages - 1 : kWStages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[kWStages], w_empty[kWStages], enc_full[2], enc_empty[2], acc_full[2], acc_empty[2], act_ready[2];
+  __shared__ uint64_t w_full[kWStages], w_empty[kWStages], pos_full, pos_empty, dir_full, dir_empty, acc_full, acc_empty, act_ready;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_ring = smem;                                   // kWStages x 16 KB
-  uint8_t* enc_buf = smem + kWStages * kWStageBytes;        // 2 x 48 KB
-  float* s_const = reinterpret_cast<float*>(enc_buf + 2 * kEncBytes);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  uint8_t* w_ring = smem;                                   // NS x 16 KB
+  uint8_t* pos_buf = smem + NS * kWStageBytes;              // tile t: 2 boxes of [128 x 64] at t * 32 KB
+  uint8_t* dir_buf = pos_buf + 2 * 32768;                   // tile t: 1 box at t * 16 KB
+  uint8_t* stage_buf = dir_buf + 2 * 16384;                 // TRAIN: 8 epilogue warps x 4 KB
+  float* s_const = reinterpret_cast<float*>(stage_buf + (TRAIN ? 8 * kStageSlot : 0));
 
   const int n_tiles = (int)((p.M + 127) / 128);
+  const int n_pairs = (n_tiles + 1) / 2;
+  int last_pos_step = 0;
+  for (int s = 0; s < p.n_steps; s++) if (p.steps[s].enc_kind == 1) last_pos_step = s;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWStages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int b = 0; b < 2; b++) {
-      mbar_init(&enc_full[b], 1); mbar_init(&enc_empty[b], 1);
-      mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4);
-      mbar_init(&act_ready[b], 4);
-    }
+    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(&pos_full, 1); mbar_init(&pos_empty, 1); mbar_init(&dir_full, 1); mbar_init(&dir_empty, 1);
+    mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8); mbar_init(&act_ready, 8);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.n_consts; i += kThreadsF) s_const[i] = __ldg(p.consts + i);
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
       prefetch_tmap(&p.map_pos); prefetch_tmap(&p.map_dir);
-      for (int s = 0; s < p.n_steps; s++) prefetch_tmap(&p.map_w[s]);
+      for (int s = 0; s < p.n_steps; s++) { prefetch_tmap(&p.map_w[s]); if (TRAIN) prefetch_tmap(&p.map_act[s]); }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t ACC0 = tmem_base, ACT0 = tmem_base + 256;  // ACC[h] = ACC0 + 128 h; ACT[b] = ACT0 + 128 b
+  const uint32_t tmem_base = tmem_base_smem;  // tile t: ACT at +256 t, ACC at +256 t + 128
 
-  if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer: encodings per tile + weight ring
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer: encodings per pair + weight ring
     if (lane == 0) {
-      uint32_t wit = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
-        const int row0 = tile * 128;
-        const uint32_t eb = tl & 1;
-        mbar_wait(&enc_empty[eb], ((tl >> 1) & 1) ^ 1);
-        uint8_t* e = enc_buf + (size_t)eb * kEncBytes;
-        mbar_arrive_expect_tx(&enc_full[eb], kEncBytes);
-        tma_load_2d(e, &p.map_pos, 0, row0, &enc_full[eb]);
-        tma_load_2d(e + 16384, &p.map_pos, 64, row0, &enc_full[eb]);
-        tma_load_2d(e + 32768, &p.map_dir, 0, row0, &enc_full[eb]);
+      uint32_t wit = 0, pl = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
+        const int row0 = pair * 256;
+        mbar_wait(&pos_empty, (pl & 1) ^ 1);
+        mbar_arrive_expect_tx(&pos_full, 2 * 32768);
+        for (int t = 0; t < 2; t++) {
+          tma_load_2d(pos_buf + t * 32768, &p.map_pos, 0, row0 + t * 128, &pos_full);
+          tma_load_2d(pos_buf + t * 32768 + 16384, &p.map_pos, 64, row0 + t * 128, &pos_full);
+        }
         for (int s = 0; s < p.n_steps; s++) {
           const FusedParams::Step st = p.steps[s];
           const int n_kb = st.n_act_kb + st.n_enc_kb;
+          if (st.enc_kind == 2) {  // direction encodings: needed by the condition layer only, so loaded just ahead of it
+            mbar_wait(&dir_empty, (pl & 1) ^ 1);
+            mbar_arrive_expect_tx(&dir_full, 2 * 16384);
+            for (int t = 0; t < 2; t++) tma_load_2d(dir_buf + t * 16384, &p.map_dir, 0, row0 + t * 128, &dir_full);
+          }
           for (int h = 0; h < st.n_halves; h++)
             for (int kb = 0; kb < n_kb; kb++, wit++) {
-              const int ws = wit % kWStages;
-              mbar_wait(&w_empty[ws], ((wit / kWStages) & 1) ^ 1);
+              const int ws = wit % NS;
+              mbar_wait(&w_empty[ws], ((wit / NS) & 1) ^ 1);
               mbar_arrive_expect_tx(&w_full[ws], kWStageBytes);
               tma_load_2d(w_ring + (size_t)ws * kWStageBytes, &p.map_w[s], kb * 64, h * 128, &w_full[ws]);
             }
         }
       }
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
-      uint32_t wit = 0, tl = 0, acc_uses[2] = {0, 0}, act_waits[2] = {0, 0};
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
-        const uint32_t eb = tl & 1;
-        const uint32_t e_base = smem_u32(enc_buf + (size_t)eb * kEncBytes);
-        bool enc_waited = false;
-        for (int s = 0; s < p.n_steps; s++) {
-          const FusedParams::Step st = p.steps[s];
-          const uint32_t act_cur = ACT0 + 128 * (s & 1);  // written by the epilogue of step s-1
-          bool act_ok[2] = {false, false};
-          for (int h = 0; h < st.n_halves; h++) {
-            mbar_wait(&acc_empty[h], (acc_uses[h] & 1) ^ 1);  // epilogue drained this accumulator half
-            acc_uses[h]++;
-            tc_fence_after_sync();
-            const uint32_t acc = ACC0 + 128 * h;
-            const int n_kb = st.n_act_kb + st.n_enc_kb;
-            for (int kb = 0; kb < n_kb; kb++, wit++) {
-              const bool from_act = kb < st.n_act_kb;
-              if (from_act) {
-                const int hh = kb >> 1;  // k-blocks 0,1 read the half-0 output of the previous step; 2,3 half 1
-                if (!act_ok[hh]) {
-                  mbar_wait(&act_ready[hh], act_waits[hh] & 1);
-                  act_waits[hh]++;
-                  act_ok[hh] = true;
-                  tc_fence_after_sync();
-                }
-              } else if (!enc_waited) {
-                mbar_wait(&enc_full[eb], (tl >> 1) & 1);
-                enc_waited = true;
-                tc_fence_after_sync();
-              }
-              const int ws = wit % kWStages;
-              mbar_wait(&w_full[ws], (wit / kWStages) & 1);
-              tc_fence_after_sync();
-              const uint32_t b_base = smem_u32(w_ring + (size_t)ws * kWStageBytes);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024);
-                const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                if (from_act) {
-                  umma_bf16_ts(acc, act_cur + kb * 32 + k * 8, db, idesc, accum);
-                } else {
-                  const int ekb = kb - st.n_act_kb;
-                  const uint32_t a_base = e_base + (st.enc_kind == 2 ? 32768u : (uint32_t)ekb * 16384u);
-                  umma_bf16(acc, make_smem_desc(a_base + k * 32, 16, 1024), db, idesc, accum);
-                }
-              }
-              umma_commit(&w_empty[ws]);
-            }
-            umma_commit(&acc_full[h]);
-          }
-        }
-        umma_commit(&enc_empty[eb]);  // every MMA that read this tile's encodings has completed
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue: warp w owns rows 32w..32w+31
-    uint32_t full_uses[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long row = (long)tile * 128 + threadIdx.x;
-      const bool row_ok = row < p.M;
-      const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-      float head[3] = {0.f, 0.f, 0.f};
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer.  The whole warp walks the schedule in
+    // uniform control flow (so addresses and descriptors live in uniform registers); one elected lane issues.
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+    const uint64_t desc0 = make_smem_desc(0, 16, 1024);  // + (smem address >> 4)
+    const uint32_t pos_base = smem_u32(pos_buf), dir_base = smem_u32(dir_buf), ring_base = smem_u32(w_ring);
+    uint32_t wit = 0, pl = 0, n_acc = 0, n_act = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
       for (int s = 0; s < p.n_steps; s++) {
         const FusedParams::Step st = p.steps[s];
-        const uint32_t act_next = ACT0 + 128 * ((s + 1) & 1);
         for (int h = 0; h < st.n_halves; h++) {
-          mbar_wait(&acc_full[h], full_uses[h] & 1);
-          full_uses[h]++;
+          mbar_wait(&acc_empty, (n_acc & 1) ^ 1);  // both tiles' accumulators drained by the epilogue warps
+          n_acc++;
+          if (h == 0) {
+            if (st.n_act_kb > 0) { mbar_wait(&act_ready, n_act & 1); n_act++; }  // ACT of both tiles rewritten in place
+            if (s == 0) mbar_wait(&pos_full, pl & 1);
+            if (st.enc_kind == 2) mbar_wait(&dir_full, pl & 1);
+          }
           tc_fence_after_sync();
-          const uint32_t acc = ACC0 + 128 * h + lane_off;
+          for (int kb = 0; kb < st.n_act_kb; kb++, wit++) {  // A = activations resident in tensor memory
+            const uint32_t ws = wit % NS;
+            mbar_wait(&w_full[ws], (wit / NS) & 1);
+            tc_fence_after_sync();
+            const uint64_t db = desc0 + ((ring_base + ws * kWStageBytes) >> 4);
+            if (leader) {
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            uint32_t r[32];
-            tmem_ld_32x32(acc + c * 32, r);
+              for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  umma_bf16_ts(tmem_base + 256 * t + 128, tmem_base + 256 * t + kb * 32 + k * 8, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              umma_commit(&w_empty[ws]);
+            }
+          }
+          for (int kb = 0; kb < st.n_enc_kb; kb++, wit++) {  // A = this pair's encodings in shared memory
+            const uint32_t ws = wit % NS;
+            mbar_wait(&w_full[ws], (wit / NS) & 1);
+            tc_fence_after_sync();
+            const uint64_t db = desc0 + ((ring_base + ws * kWStageBytes) >> 4);
+            const uint32_t a0 = st.enc_kind == 2 ? dir_base : pos_base + kb * 16384;
+            const uint32_t a_tile = st.enc_kind == 2 ? 16384 : 32768;
+            if (leader) {
+#pragma unroll
+              for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  umma_bf16(tmem_base + 256 * t + 128, desc0 + ((a0 + t * a_tile) >> 4) + 2 * k, db + 2 * k, idesc,
+                            (st.n_act_kb | kb | k) ? 1u : 0u);
+              umma_commit(&w_empty[ws]);
+            }
+          }
+          if (leader) umma_commit(&acc_full);
+        }
+        if (s == last_pos_step && leader) umma_commit(&pos_empty);  // the next pair's position encodings may land
+      }
+      if (leader) umma_commit(&dir_empty);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: tile t = warp / 4, rows 32 (warp % 4) ..
+    const int t = warp >> 2;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t act = tmem_base + 256 * t + lane_off, acc = act + 128;
+    uint8_t* slot = stage_buf + warp * kStageSlot;  // TRAIN: this warp's [32 x 64] bf16 store box
+    uint8_t* slot_row = slot + lane * 128;
+    const int swz = lane & 7;
+    uint32_t n_full = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int row_w = pair * 256 + t * 128 + (warp & 3) * 32;  // first row of this warp
+      const long row = (long)row_w + lane;
+      const bool row_ok = row < p.M;
+      float head[3] = {0.f, 0.f, 0.f};
+      uint32_t held[64];  // first half's outputs wait in registers until the second half's MMAs have read ACT
+      for (int s = 0; s < p.n_steps; s++) {
+        const FusedParams::Step st = p.steps[s];
+        const float* head_w = s_const + (st.head == 3 ? p.head_rgb_off : p.head_d_off);
+        // TRAIN: 32 packed columns of this thread's row go to the warp's store box; every second call ships the box
+        auto ship = [&](int col0, int half, const uint32_t* pk) {
+          if (!TRAIN) return;
+          if (half == 0) {
+            if (lane == 0) tma_store_wait_read<0>();  // the previous box of this warp has been read out
+            __syncwarp();
+          }
+          stage_half_row(slot_row, half, swz, pk);
+          if (half == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.map_act[s], slot, col0, row_w);
+              tma_store_commit();
+            }
+          }
+        };
+        for (int h = 0; h < st.n_halves; h++) {
+          const bool last_half = h == st.n_halves - 1;
+          const float* bias = s_const + st.bias_off + h * 128;
+          uint32_t m0, m1, m2, m3;
+          mbar_wait(&acc_full, n_full & 1);
+          n_full++;
+          tc_fence_after_sync();
+          if (!last_half) {
+            // first half: pull the whole accumulator into registers at once so the second half's MMAs can start
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            tmem_ld_32x32(acc, r0); tmem_ld_32x32(acc + 32, r1); tmem_ld_32x32(acc + 64, r2); tmem_ld_32x32(acc + 96, r3);
             tmem_ld_wait();
-            const int col = h * 128 + c * 32;
-            const float4* bv = reinterpret_cast<const float4*>(s_const + st.bias_off + col);
-            float v[32];
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty);
+            m0 = epi_chunk_any<TRAIN>(st.head, r0, bias, head_w + h * 128, head, held);
+            ship(h * 128, 0, held);
+            m1 = epi_chunk_any<TRAIN>(st.head, r1, bias + 32, head_w + h * 128 + 32, head, held + 16);
+            ship(h * 128, 1, held + 16);
+            m2 = epi_chunk_any<TRAIN>(st.head, r2, bias + 64, head_w + h * 128 + 64, head, held + 32);
+            ship(h * 128 + 64, 0, held + 32);
+            m3 = epi_chunk_any<TRAIN>(st.head, r3, bias + 96, head_w + h * 128 + 96, head, held + 48);
+            ship(h * 128 + 64, 1, held + 48);
+          } else {
+            // every MMA of the layer is complete: ACT may be overwritten in place
+            if (st.n_halves == 2 && st.produces) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const float4 bb = bv[q];
-              v[4 * q] = fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f);
-              v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
-              v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f);
-              v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
+              for (int c = 0; c < 4; c++) tmem_st_16(act + c * 16, held + 16 * c);
             }
-            if (st.head == 1) {  // density head: raw = y . w + b (N = 1)
-              const float4* hv = reinterpret_cast<const float4*>(s_const + p.head_d_off + col);
-#pragma unroll
-              for (int q = 0; q < 8; q++) {
-                const float4 w = hv[q];
-                head[0] = fmaf(v[4 * q], w.x, head[0]); head[0] = fmaf(v[4 * q + 1], w.y, head[0]);
-                head[0] = fmaf(v[4 * q + 2], w.z, head[0]); head[0] = fmaf(v[4 * q + 3], w.w, head[0]);
-              }
-            } else if (st.head == 3) {  // rgb head (N = 3) over the 128 condition features
-#pragma unroll
-              for (int n = 0; n < 3; n++) {
-                const float4* hv = reinterpret_cast<const float4*>(s_const + p.head_rgb_off + n * 128 + col);
-                float a = head[n];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                  const float4 w = hv[q];
-                  a = fmaf(v[4 * q], w.x, a); a = fmaf(v[4 * q + 1], w.y, a);
-                  a = fmaf(v[4 * q + 2], w.z, a); a = fmaf(v[4 * q + 3], w.w, a);
-                }
-                head[n] = a;
-              }
+            const uint32_t out = act + h * 64;
+            const float* hw = head_w + (st.head == 3 ? 0 : h * 128);
+            uint32_t ra[32], rb[32], pk[16];
+            tmem_ld_32x32(acc, ra);
+            tmem_ld_wait();
+            tmem_ld_32x32(acc + 32, rb);
+            m0 = epi_chunk_any<TRAIN>(st.head, ra, bias, hw, head, pk);
+            if (st.produces) tmem_st_16(out, pk);
+            ship(h * 128, 0, pk);
+            tmem_ld_wait();
+            tmem_ld_32x32(acc + 64, ra);
+            m1 = epi_chunk_any<TRAIN>(st.head, rb, bias + 32, hw + 32, head, pk);
+            if (st.produces) tmem_st_16(out + 16, pk);
+            ship(h * 128, 1, pk);
+            tmem_ld_wait();
+            tmem_ld_32x32(acc + 96, rb);
+            m2 = epi_chunk_any<TRAIN>(st.head, ra, bias + 64, hw + 64, head, pk);
+            if (st.produces) tmem_st_16(out + 32, pk);
+            ship(h * 128 + 64, 0, pk);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty);
+            m3 = epi_chunk_any<TRAIN>(st.head, rb, bias + 96, hw + 96, head, pk);
+            if (st.produces) {
+              tmem_st_16(out + 48, pk);
+              tmem_st_wait();
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&act_ready);
             }
-            if (st.produces) {  // next layer's A operand: bf16 pairs, two per 32-bit TMEM column
-              uint32_t w16[16];
-#pragma unroll
-              for (int q = 0; q < 16; q++) w16[q] = pack2(v[2 * q], v[2 * q + 1]);
-              tmem_st_32x16(act_next + lane_off + (uint32_t)(col >> 1), w16);
-            }
+            ship(h * 128 + 64, 1, pk);
           }
-          if (st.produces) tmem_st_wait();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&acc_empty[h]);
-            if (st.produces) mbar_arrive(&act_ready[h]);
-          }
+          if (TRAIN && row_ok)
+            *reinterpret_cast<uint4*>(p.bits[s] + row * (st.n_halves * 4) + h * 4) = make_uint4(m0, m1, m2, m3);
         }
         if (st.head == 1) {
           if (row_ok) p.raw_density[row] = head[0] + s_const[p.head_d_off + 256];
@@ -282,11 +392,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
         }
       }
     }
+    if (TRAIN && lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tmem_base);
+  if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace
@@ -298,17 +409,21 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
 int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv_bfloat16* dir, int dir_pitch,
                              const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
-                             float* raw_density, float* raw_rgb, cudaStream_t st) {
+                             float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
+                             cudaStream_t st) {
   if (W != 256 || Wc != 128 || D + 1 > kMaxSteps || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
     return 100001;
   }
+  const bool train = act_out != nullptr;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   static int sms = 148;
-  const size_t smem = (size_t)kWStages * kWStageBytes + 2 * kEncBytes + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
+  const size_t smem = (size_t)(train ? kWStages - 1 : kWStages) * kWStageBytes + 2 * kEncBytes + (train ? 8 * kStageSlot : 0) +
+                      (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -322,6 +437,10 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   for (int s = 0; s <= D; s++) {
     const int N = s < D ? W : Wc;
     NERF_TRY(tc_make_tmap(&p.map_w[s], wplanes[s], N, kpad[s], kpad[s], 128));
+    if (train) {
+      NERF_TRY(tc_make_tmap(&p.map_act[s], act_out[s], M, N, N, 32));
+      p.bits[s] = bits_out[s];
+    }
     FusedParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
     else if (s < D) { stp.n_act_kb = 4; stp.enc_kind = in_b[s] ? 1 : 0; stp.n_enc_kb = in_b[s] ? 2 : 0; }
@@ -334,8 +453,10 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  const int tiles = (int)cdiv(M, 128);
-  k_mlp_fused_fwd<<<tiles < sms ? tiles : sms, kThreadsF, smem, st>>>(p);
+  const int pairs = (int)cdiv(M, 256);
+  const int grid = pairs < sms ? pairs : sms;
+  if (train) k_mlp_fused_fwd<true><<<grid, kThreadsF, smem, st>>>(p);
+  else k_mlp_fused_fwd<false><<<grid, kThreadsF, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
 }

@@ -110,6 +110,8 @@ class TcMlp : public MlpEngine {
   }
 
   int forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
+    if (can_fuse_forward() && getenv("NERF_NO_FUSED_TRAIN_FORWARD") == nullptr)
+      return fused_forward(level, M, params, raw_density, raw_rgb, true, st);
     Level& lv = levels_[level];
     const int D = s_.D, C = s_.C;
     const Plane* h = &lv.enc_pos;
@@ -161,6 +163,10 @@ class TcMlp : public MlpEngine {
 
   int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
     if (!can_fuse_forward()) return forward(level, M, params, raw_density, raw_rgb, st);
+    return fused_forward(level, M, params, raw_density, raw_rgb, false, st);
+  }
+
+  int fused_forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, bool train, cudaStream_t st) {
     Level& lv = levels_[level];
     const int D = s_.D;
     std::vector<int> bias_off(D + 1), kpad(D + 1), in_b(D + 1);
@@ -190,9 +196,12 @@ class TcMlp : public MlpEngine {
       NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off + 384, params + Lr.b_off, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
       fconsts_dirty_ = false;
     }
+    std::vector<__nv_bfloat16*> act_out(D + 1);
+    for (int s = 0; s <= D; s++) act_out[s] = lv.acts[s].hi;
     ProfScope ps(PC_MLP_FWD, st);
     return launch_mlp_fused_forward(lv.enc_pos.hi, pos_pitch_, lv.enc_dir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
-                                    s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb, st);
+                                    s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
+                                    train ? act_out.data() : nullptr, train ? lv.bits.data() : nullptr, st);
   }
 
   int backward(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
