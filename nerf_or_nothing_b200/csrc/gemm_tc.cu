@@ -636,13 +636,19 @@ void tc_tmap_cache_clear() {
 }
 
 int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
-  const TmapKey key{base, rows, cols, pitch_elems, box_rows};
+  return tc_make_tmap_box(out, base, rows, cols, pitch_elems, 64, box_rows);
+}
+
+// box_cols = 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B); box_rows packed with box_cols in the key
+int tc_make_tmap_box(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
+                     uint32_t box_rows) {
+  const TmapKey key{base, rows, cols, pitch_elems, box_rows | (box_cols << 16)};
   {
     std::lock_guard<std::mutex> lk(g_tmap_mu);
     auto it = g_tmap_cache.find(key);
     if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
   }
-  const int rc = tc_encode_tmap(out, base, rows, cols, pitch_elems, box_rows);
+  const int rc = tc_encode_tmap_box(out, base, rows, cols, pitch_elems, box_cols, box_rows);
   if (rc == 0) {
     std::lock_guard<std::mutex> lk(g_tmap_mu);
     if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
@@ -652,14 +658,21 @@ int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 }
 
 int tc_encode_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
+  return tc_encode_tmap_box(out, base, rows, cols, pitch_elems, 64, box_rows);
+}
+
+int tc_encode_tmap_box(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
+                       uint32_t box_rows) {
+  if (box_cols != 64 && box_cols != 32) { set_error("tensor map: box of %u columns unsupported", box_cols); return 100001; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return 100002; }
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {pitch_elems * 2};
-  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r, base,

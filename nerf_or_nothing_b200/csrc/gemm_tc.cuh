@@ -58,6 +58,10 @@ struct alignas(64) TcParams {
 
 int tc_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);  // memoised
 int tc_encode_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);
+int tc_make_tmap_box(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
+                     uint32_t box_rows);  // memoised; box_cols 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+int tc_encode_tmap_box(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_cols,
+                       uint32_t box_rows);
 void tc_tmap_cache_clear();
 int tc_launch(const TcParams& p, bool mn_major, dim3 grid, cudaStream_t st);
 int tc_smem_bytes(int BN, int n_stages, bool mn_major);
@@ -69,6 +73,14 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                              float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
                              cudaStream_t st);  // act_out != nullptr: also write every layer's activations + ReLU bit planes
+
+// the same for the fp32-accurate split mode (hi/lo planes, three-term products; mlp_fused_split.cu)
+int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloat16* pos_lo, int pos_pitch, const __nv_bfloat16* dir_hi,
+                                   const __nv_bfloat16* dir_lo, int dir_pitch, const __nv_bfloat16* const* w_hi,
+                                   const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
+                                   const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
+                                   float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
+                                   uint32_t* const* bits_out, cudaStream_t st);
 
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]

@@ -1,0 +1,430 @@
+// mlp_fused_split.cu — the MipNeRF MLP forward as ONE persistent tcgen05 kernel in the fp32-accurate
+// tensor-core mode (NERF_PRECISION_FP32_TC): every tensor is a pair of bf16 planes x = hi + lo and every product is the
+// three-term split hi*hi + lo*hi + hi*lo accumulated in fp32.
+//
+// Replaces the per-layer launch chain of AcceleratedMLP::get_output (ANU/AcceleratedMLP.cpp:214-255).  In this mode the
+// layer-by-layer GEMMs are HBM-bound (each layer reads the previous activations' two planes and writes its own);
+// here the activations never come back from HBM: per 128-row tile, tensor memory (512 columns) holds
+//   ACT_hi [0,128)  ACT_lo [128,256)   the current layer's input as the A operand of ".ts" MMAs (256 bf16 per row, each)
+//   ACC    [256,512)                   the layer's fp32 accumulator: two N-halves of 128 columns
+// and the only global traffic per layer is the (training-only) write of the layer's activation planes + ReLU bits.
+// A layer is two N-halves; per half and 64-wide k-block one 32 KB ring stage brings W_hi|W_lo [128 x 64] and feeds the
+// MMAs A_hi*W_hi, A_lo*W_hi, A_hi*W_lo (128x128x16 each).  The eight epilogue warps (two per TMEM lane quarter) apply
+// bias + ReLU, split into hi/lo, write both planes back into ACT in place once the layer's MMAs are complete, and
+// (training) ship them through 64-byte-swizzled [32 x 32] boxes with their own TMA stores.  The encodings of layer 0,
+// the skip layer and the condition layer stream through the same ring as shared-memory A operands.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "gemm_tc.cuh"
+#include "sm100.cuh"
+
+namespace nerf {
+namespace {
+
+using namespace sm100;
+
+constexpr int kThreadsS = 320;            // 8 epilogue warps + TMA producer + MMA issuer
+constexpr int kEpiWarps = 8;
+constexpr int kNSInfer = 6, kNSTrain = 5;  // operand ring: 32 KB stages (a weight plane tile [<=256 x 64], or an encoding k-block's hi|lo tiles)
+constexpr int kStageB = 256 * 128;        // 32 KB
+constexpr int kSlotB = 2 * 2048;          // per epilogue warp: one [32 x 32] hi box + one lo box
+constexpr int kMaxStepsS = 12;
+
+__device__ __forceinline__ uint32_t pack2s(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace
+
+struct alignas(64) SplitParams {
+  CUtensorMap map_pos[2], map_dir[2];         // [hi, lo] encodings [M, 128] / [M, 64], box {64, 128}
+  CUtensorMap map_w[kMaxStepsS][2];           // [hi, lo] weight planes [N, Kpad], box {64, 128}
+  CUtensorMap map_act[kMaxStepsS][2];         // training: [hi, lo] activation planes [M, N], box {32, 32} (SWIZZLE_64B)
+  uint32_t* bits[kMaxStepsS];                 // training: ReLU bit planes [M, N/32]
+  struct Step {
+    int16_t n_act_kb, enc_kind, n_enc_kb, n_halves;  // n_halves = N / 128
+    int16_t produces, head;
+    int32_t bias_off;
+  } steps[kMaxStepsS];
+  int n_steps;
+  long M;
+  const float* consts;
+  int n_consts, head_d_off, head_rgb_off;
+  float* raw_density;
+  float* raw_rgb;
+  long long* dbg;  // NERF_FUSED_DBG=1: clock64 stamps of CTA 0's first steps (development aid, normally null)
+};
+
+namespace {
+
+// bias + ReLU + hi/lo split of one 32-column chunk; optional ReLU mask (bit j = column j passed) and head FMAs
+template <bool BITS>
+__device__ __forceinline__ uint32_t split_chunk(const uint32_t (&r)[32], const float* bias, int head_n, const float* head_w, float (&head)[3],
+                                                uint32_t* hw, uint32_t* lw) {
+  float x[32];
+  const float4* bv = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 bb = bv[q];
+    x[4 * q] = __uint_as_float(r[4 * q]) + bb.x; x[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+    x[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z; x[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+  }
+  uint32_t mask = 0u;
+  if (BITS) {  // from the sign bits: four chains of eight funnel shifts (m = m << 1 | sign)
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int e = 7; e >= 0; e--) m[g] = __funnelshift_l(__float_as_uint(x[8 * g + e]), m[g], 1);
+    mask = ~__byte_perm(__byte_perm(m[0], m[1], 0x0040), __byte_perm(m[2], m[3], 0x0040), 0x5410);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
+  if (head_n) {  // 1: density head; 3: rgb head
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+      if (n < head_n) {
+        const float4* hv = reinterpret_cast<const float4*>(head_w + n * 128);
+        float a = head[n];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float4 w = hv[q];
+          a = fmaf(x[4 * q], w.x, a); a = fmaf(x[4 * q + 1], w.y, a);
+          a = fmaf(x[4 * q + 2], w.z, a); a = fmaf(x[4 * q + 3], w.w, a);
+        }
+        head[n] = a;
+      }
+  }
+  // x = hi + lo: hi = bf16(x) in pairs, lo = bf16(x - hi) with hi rebuilt from the packed bits
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    hw[q] = pack2s(x[2 * q], x[2 * q + 1]);
+    lw[q] = pack2s(x[2 * q] - __uint_as_float(hw[q] << 16), x[2 * q + 1] - __uint_as_float(hw[q] & 0xFFFF0000u));
+  }
+  return mask;
+}
+
+// One CTA walks 128-row tiles.  A layer is two N-halves with their own accumulator columns: while the MMAs of the second
+// half run, the eight epilogue warps (TMEM lane quarter = warp % 4, 64 of the half's 128 columns each) finish the first
+// half into registers; its hi/lo words are written into ACT — in place — only after the second half's MMAs have read
+// ACT, together with the second half's.
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
+  constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float head_part[128][4];  // partial head dot products of the upper-column warps
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* w_ring = smem;                         // NS x 32 KB
+  uint8_t* stage_buf = smem + NS * kStageB;       // TRAIN: 8 x 4 KB
+  float* s_const = reinterpret_cast<float*>(stage_buf + (TRAIN ? kEpiWarps * kSlotB : 0));
+
+  const int n_tiles = (int)((p.M + 127) / 128);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int h = 0; h < 2; h++) { mbar_init(&acc_full[h], 1); mbar_init(&acc_empty[h], kEpiWarps); }
+    mbar_init(&act_ready, kEpiWarps);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.n_consts; i += kThreadsS) s_const[i] = __ldg(p.consts + i);
+  if (warp == kEpiWarps) {
+    tmem_alloc<512>(&tmem_base_smem);
+    if (lane == 0) {
+      for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_pos[q]); prefetch_tmap(&p.map_dir[q]); }
+      for (int s = 0; s < p.n_steps; s++)
+        for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_w[s][q]); if (TRAIN) prefetch_tmap(&p.map_act[s][q]); }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t ACT_HI = tmem_base, ACT_LO = tmem_base + 128, ACC = tmem_base + 256;  // ACC half h at + 128 h
+
+  if (warp == kEpiWarps) {
+    // ------------------------------------------------------------------ TMA producer: everything goes through ONE ring of
+    // 32 KB stages — the hi|lo tiles [128 x 64] of a weight half-layer k-block, or of an encoding k-block (A operand)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * 128;
+        for (int s = 0; s < p.n_steps; s++) {
+          const SplitParams::Step st = p.steps[s];
+          const int n_kb = st.n_act_kb + st.n_enc_kb;
+          for (int h = 0; h < st.n_halves; h++)
+            for (int kb = 0; kb < n_kb; kb++) {
+              if (kb >= st.n_act_kb) {  // encoding k-block: A_hi | A_lo
+                const int ws = it % NS;
+                mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);
+                mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
+                const CUtensorMap* me = st.enc_kind == 2 ? p.map_dir : p.map_pos;
+                const int ecol = (kb - st.n_act_kb) * 64;
+                tma_load_2d(w_ring + (size_t)ws * kStageB, &me[0], ecol, row0, &w_full[ws]);
+                tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &me[1], ecol, row0, &w_full[ws]);
+                it++;
+              }
+              const int ws = it % NS;  // W_hi | W_lo rows [128 h, 128 h + 128) of this k-block
+              mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);
+              mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
+              tma_load_2d(w_ring + (size_t)ws * kStageB, &p.map_w[s][0], kb * 64, h * 128, &w_full[ws]);
+              tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &p.map_w[s][1], kb * 64, h * 128, &w_full[ws]);
+              it++;
+            }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ------------------------------------------------------------------ MMA issuer (uniform warp, one elected lane issues)
+    const bool leader = elect_one();
+    const uint64_t desc0 = make_smem_desc(0, 16, 1024);
+    const uint32_t ring_base = smem_u32(w_ring);
+    const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+    uint32_t it = 0, n_acc[2] = {0, 0}, n_act = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < p.n_steps; s++) {
+        const SplitParams::Step st = p.steps[s];
+        const int n_kb = st.n_act_kb + st.n_enc_kb;
+        for (int h = 0; h < st.n_halves; h++) {
+          mbar_wait(&acc_empty[h], (n_acc[h] & 1) ^ 1);
+          n_acc[h]++;
+          if (h == 0 && st.n_act_kb > 0) { mbar_wait(&act_ready, n_act & 1); n_act++; }
+          tc_fence_after_sync();
+          const uint32_t acc = ACC + 128 * h;
+          const bool stamp = p.dbg && blockIdx.x == 0 && leader && n_acc[0] <= 16;
+          if (stamp) p.dbg[((n_acc[0] - 1) * 2 + h) * 8 + 0] = clock64();
+          for (int kb = 0; kb < n_kb; kb++) {
+            const bool from_act = kb < st.n_act_kb;
+            uint32_t a_stage = 0, a_hi = 0;
+            if (!from_act) {  // the encoding tiles of this k-block arrive in their own stage
+              a_stage = it % NS;
+              mbar_wait(&w_full[a_stage], (it / NS) & 1);
+              a_hi = ring_base + a_stage * kStageB;
+              it++;
+            }
+            const uint32_t ws = it % NS;
+            mbar_wait(&w_full[ws], (it / NS) & 1);
+            tc_fence_after_sync();
+            const uint64_t dbh = desc0 + ((ring_base + ws * kStageB) >> 4), dbl = dbh + (16384 >> 4);
+            if (leader) {
+              if (from_act) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {  // hi*hi + lo*hi + hi*lo
+                  umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                  umma_bf16_ts(acc, ACT_LO + kb * 32 + k * 8, dbh + 2 * k, idesc, 1u);
+                  umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbl + 2 * k, idesc, 1u);
+                }
+              } else {
+                const uint64_t dah = desc0 + (a_hi >> 4), dal = dah + (16384 >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  umma_bf16(acc, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                  umma_bf16(acc, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+                  umma_bf16(acc, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+                }
+                umma_commit(&w_empty[a_stage]);
+              }
+              umma_commit(&w_empty[ws]);
+            }
+            it++;
+          }
+          if (leader) umma_commit(&acc_full[h]);
+          if (stamp) p.dbg[((n_acc[0] - 1) * 2 + h) * 8 + 1] = clock64();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: lane quarter warp % 4, column half warp / 4
+    const int qtr = warp & 3, ch = warp >> 2;
+    const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
+    uint8_t* slot = stage_buf + warp * kSlotB;   // TRAIN: [32 x 32] hi box + lo box
+    uint8_t* slot_row = slot + lane * 64;
+    const int swz = (lane >> 1) & 3;             // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
+    uint32_t n_full[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row_w = tile * 128 + qtr * 32;
+      const int row_t = qtr * 32 + lane;         // row within the tile
+      const long row = (long)row_w + lane;
+      const bool row_ok = row < p.M;
+      uint32_t held_h[32], held_l[32];           // first half's words wait here until the second half's MMAs have read ACT
+      for (int s = 0; s < p.n_steps; s++) {
+        const SplitParams::Step st = p.steps[s];
+        float head[3] = {0.f, 0.f, 0.f};
+        // TRAIN: ship one 32-column chunk (both planes) of this warp's 32 rows
+        auto ship = [&](int col, const uint32_t* hw, const uint32_t* lw) {
+          if (!TRAIN) return;
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous pair of boxes has been read out
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+            *reinterpret_cast<uint4*>(slot_row + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.map_act[s][0], slot, col, row_w);
+            tma_store_2d(&p.map_act[s][1], slot + 2048, col, row_w);
+            tma_store_commit();
+          }
+        };
+        for (int h = 0; h < st.n_halves; h++) {
+          const bool last_half = h == st.n_halves - 1;
+          const int col_t = h * 128 + ch * 64;   // first column of this thread in this half
+          const float* bias = s_const + st.bias_off + col_t;
+          const float* head_w = s_const + (st.head == 3 ? p.head_rgb_off : p.head_d_off) + col_t;
+          const uint32_t acc = ACC + 128 * h + lane_off + ch * 64;
+          uint32_t m0, m1;
+          mbar_wait(&acc_full[h], n_full[h] & 1);
+          n_full[h]++;
+          tc_fence_after_sync();
+          const bool stamp = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && n_full[0] <= 16;
+          if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 2] = clock64();
+          if (last_half && st.n_halves == 2 && st.produces) {  // every MMA of the layer is complete: ACT is rewritten in place
+            tmem_st_16(ACT_HI + lane_off + ch * 32, held_h); tmem_st_16(ACT_HI + lane_off + ch * 32 + 16, held_h + 16);
+            tmem_st_16(ACT_LO + lane_off + ch * 32, held_l); tmem_st_16(ACT_LO + lane_off + ch * 32 + 16, held_l + 16);
+          }
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(acc, r0);
+          tmem_ld_32x32(acc + 32, r1);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[h]);  // accumulator half in registers: its next MMAs may start
+          if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 3] = clock64();
+          if (!last_half) {
+            m0 = split_chunk<TRAIN>(r0, bias, st.head, head_w, head, held_h, held_l);
+            ship(col_t, held_h, held_l);
+            m1 = split_chunk<TRAIN>(r1, bias + 32, st.head, head_w + 32, head, held_h + 16, held_l + 16);
+            ship(col_t + 32, held_h + 16, held_l + 16);
+          } else {
+            uint32_t hw[16], lw[16];
+            const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
+            m0 = split_chunk<TRAIN>(r0, bias, st.head, head_w, head, hw, lw);
+            if (st.produces) { tmem_st_16(ACT_HI + out, hw); tmem_st_16(ACT_LO + out, lw); }
+            ship(col_t, hw, lw);
+            m1 = split_chunk<TRAIN>(r1, bias + 32, st.head, head_w + 32, head, hw, lw);
+            if (st.produces) {
+              tmem_st_16(ACT_HI + out + 16, hw); tmem_st_16(ACT_LO + out + 16, lw);
+              tmem_st_wait();
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&act_ready);
+            }
+            ship(col_t + 32, hw, lw);
+          }
+          if (TRAIN && row_ok) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5)) = make_uint2(m0, m1);
+          if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 4] = clock64();
+        }
+        if (st.head) {  // the column halves of a row meet in shared memory
+          if (ch == 1) { head_part[row_t][0] = head[0]; head_part[row_t][1] = head[1]; head_part[row_t][2] = head[2]; }
+          named_barrier_sync(1 + qtr, 64);
+          if (ch == 0 && row_ok) {
+            if (st.head == 1) {
+              p.raw_density[row] = head[0] + head_part[row_t][0] + s_const[p.head_d_off + 256];
+            } else {
+#pragma unroll
+              for (int n = 0; n < 3; n++) p.raw_rgb[row * 3 + n] = head[n] + head_part[row_t][n] + s_const[p.head_rgb_off + 3 * 128 + n];
+            }
+          }
+          named_barrier_sync(1 + qtr, 64);  // head_part may be rewritten
+        }
+      }
+    }
+    if (TRAIN && lane == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+// Host side.  wplanes_hi/lo[s]: weight planes of dense layer s (trunk 0..D-1, then the condition layer), [N, kpad[s]].
+// consts layout as in mlp_fused.cu.  act_hi == nullptr -> inference (nothing but the raw heads is written).
+int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloat16* pos_lo, int pos_pitch, const __nv_bfloat16* dir_hi,
+                                   const __nv_bfloat16* dir_lo, int dir_pitch, const __nv_bfloat16* const* w_hi,
+                                   const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
+                                   const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
+                                   float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
+                                   uint32_t* const* bits_out, cudaStream_t st) {
+  if (W != 256 || Wc != 128 || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
+    set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
+    return 100001;
+  }
+  const bool train = act_hi != nullptr;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  static int sms = 148;
+  const size_t smem = (size_t)(train ? kNSTrain : kNSInfer) * kStageB + (train ? kEpiWarps * kSlotB : 0) + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(k_mlp_fused_split<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_split<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
+  if (smem > 218 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
+  SplitParams p;
+  memset(&p, 0, sizeof(p));
+  NERF_TRY(tc_make_tmap(&p.map_pos[0], pos_hi, M, 128, pos_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_pos[1], pos_lo, M, 128, pos_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_dir[0], dir_hi, M, 64, dir_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_dir[1], dir_lo, M, 64, dir_pitch, 128));
+  for (int s = 0; s <= D; s++) {
+    const int N = s < D ? W : Wc;
+    NERF_TRY(tc_make_tmap(&p.map_w[s][0], w_hi[s], N, kpad[s], kpad[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_w[s][1], w_lo[s], N, kpad[s], kpad[s], 128));
+    if (train) {
+      NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], act_hi[s], M, N, N, 32, 32));
+      NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], act_lo[s], M, N, N, 32, 32));
+      p.bits[s] = bits_out[s];
+    }
+    SplitParams::Step& stp = p.steps[s];
+    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
+    else if (s < D) { stp.n_act_kb = 4; stp.enc_kind = in_b[s] ? 1 : 0; stp.n_enc_kb = in_b[s] ? 2 : 0; }
+    else { stp.n_act_kb = 4; stp.enc_kind = 2; stp.n_enc_kb = 1; }
+    stp.n_halves = (int16_t)(N / 128);
+    stp.produces = s < D ? 1 : 0;
+    stp.head = s == D - 1 ? 1 : (s == D ? 3 : 0);
+    stp.bias_off = bias_off[s];
+  }
+  p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
+  p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
+  p.raw_density = raw_density; p.raw_rgb = raw_rgb;
+  static long long* dbg_dev = nullptr;
+  if (getenv("NERF_FUSED_DBG")) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 32 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 32 * 8 * sizeof(long long), st);
+    p.dbg = dbg_dev;
+  }
+  const int tiles = (int)cdiv(M, 128);
+  const int grid = tiles < sms ? tiles : sms;
+  if (train) k_mlp_fused_split<true><<<grid, kThreadsS, smem, st>>>(p);
+  else k_mlp_fused_split<false><<<grid, kThreadsS, smem, st>>>(p);
+  NERF_CHECK_LAUNCH();
+  if (p.dbg) {
+    long long h[32 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[0];
+    fprintf(stderr, "[fused-split] M=%ld train=%d  (step,half): mma_start mma_issued | epi_start ld_done epi_done   (cycles)\n", M, (int)train);
+    for (int i = 0; i < 24; i++)
+      fprintf(stderr, "  (%d,%d): %7lld %7lld | %7lld %7lld %7lld\n", i / 2, i % 2, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0,
+              h[i * 8 + 3] - t0, h[i * 8 + 4] - t0);
+  }
+  return 0;
+}
+
+}  // namespace nerf

@@ -157,7 +157,7 @@ class TcMlp : public MlpEngine {
   // Rendering: no backward follows, so in bf16 mode the whole net runs as one kernel with the activations kept in
   // tensor memory (mlp_fused.cu) instead of one GEMM launch per layer with the activations written to HBM.
   bool can_fuse_forward() const {
-    return !split_ && s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 20 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
+    return s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 20 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
            getenv("NERF_NO_FUSED_FORWARD") == nullptr;
   }
 
@@ -199,6 +199,15 @@ class TcMlp : public MlpEngine {
     std::vector<__nv_bfloat16*> act_out(D + 1);
     for (int s = 0; s <= D; s++) act_out[s] = lv.acts[s].hi;
     ProfScope ps(PC_MLP_FWD, st);
+    if (split_) {
+      std::vector<const __nv_bfloat16*> wlo(D + 1);
+      std::vector<__nv_bfloat16*> act_lo(D + 1);
+      for (int s = 0; s <= D; s++) { wlo[s] = wp_[s < D ? s : D + 1].lo; act_lo[s] = lv.acts[s].lo; }
+      return launch_mlp_fused_forward_split(lv.enc_pos.hi, lv.enc_pos.lo, pos_pitch_, lv.enc_dir.hi, lv.enc_dir.lo, dir_pitch_, wpl.data(),
+                                            wlo.data(), kpad.data(), in_b.data(), D, s_.W, s_.Wc, M, fconsts_, n_consts, head_d_off,
+                                            head_rgb_off, bias_off.data(), raw_density, raw_rgb, train ? act_out.data() : nullptr,
+                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, st);
+    }
     return launch_mlp_fused_forward(lv.enc_pos.hi, pos_pitch_, lv.enc_dir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
                                     train ? act_out.data() : nullptr, train ? lv.bits.data() : nullptr, st);
