@@ -233,6 +233,39 @@ int nerf_adam_optimizer_step(float* variables, const float* gradients, float* m,
                              float beta1, float beta2, float inv_1_minus_beta1_pow,
                              float inv_1_minus_beta2_pow, long size, int eps_mode);
 
+
+/* ---- resident dataset, image metrics, schedule, checkpoints ----------------------- */
+#define NERF_RECORD_BYTES 64 /* SN/BinDataset.cs:35-49: o(3) d(3) viewdir(3) radius near far lossmult rgb(3) */
+typedef struct nerf_dataset nerf_dataset;
+/* Replaces BinDataset (SN/BinDataset.cs:10-52): the records live in device memory once. n_records < 2^32. */
+int nerf_dataset_create(const void* records, long n_records, int device, nerf_dataset** out);
+int nerf_dataset_load(const char* path, int device, nerf_dataset** out); /* train_data.bin, SN/Program.cs:23 */
+int nerf_dataset_size(const nerf_dataset* ds, long* n);                  /* SN/BinDataset.cs:15 */
+int nerf_dataset_destroy(nerf_dataset* ds);
+/* BinDataset.Next (SN/BinDataset.cs:21-25): batch indices drawn with replacement — here from Philox4x32-10 with
+ * counter (first_slot + i, 0, step, 0x0DA7A5E7), key = seed, index = floor(word0 * n / 2^32) — instead of
+ * System.Random; this call exports them for parity checks. */
+int nerf_dataset_draw_indices(nerf_dataset* ds, uint64_t seed, uint32_t step, uint32_t first_slot,
+                              int n_rays, int64_t* idx_host);
+/* LoadBatch (SN/BinDataset.cs:27-51) on the device: idx_host == NULL uses the draw above. */
+int nerf_dataset_gather(nerf_dataset* ds, const int64_t* idx_host, uint64_t seed, uint32_t step,
+                        uint32_t first_slot, int n_rays, float* origins3_dev, float* directions3_dev,
+                        float* radii_dev, float* nears_dev, float* fars_dev, float* loss_mults_dev,
+                        float* pixels3_dev);
+/* One iteration of Train() (SN/Program.cs:28-45) with the batch drawn and assembled on the device. */
+int nerf_mipnerf_train_step_dataset(nerf_mipnerf* h, nerf_adam* a, nerf_dataset* ds, int n_rays,
+                                    uint64_t sampler_seed, float lr, float* loss_out);
+/* mse and MseToPsnr (SN/MipHelpers.cs:672) of two float arrays (host pointers unless on_device). */
+int nerf_image_error(const float* a, const float* b, long n_floats, int on_device, double* mse,
+                     double* psnr);
+/* LearningRateDecay (SN/MipHelpers.cs:758-773). */
+float nerf_learning_rate_decay(int step, float lr_init, float lr_final, int max_steps,
+                               int lr_delay_steps, float lr_delay_mult);
+/* Parameters + Adam m/v/iteration + sampling step counter in one file (Config.SaveEvery, SN/TrainState.cs:62;
+ * the reference never implemented the save). `a` may be NULL (parameters only). */
+int nerf_checkpoint_save(nerf_mipnerf* h, nerf_adam* a, const char* path);
+int nerf_checkpoint_load(nerf_mipnerf* h, nerf_adam* a, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

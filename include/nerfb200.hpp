@@ -142,6 +142,44 @@ class AcceleratedGradientCalculator {
   nerf_gradcalc* g_ = nullptr;
 };
 
+// ScratchNerf/ScratchNerf/BinDataset.cs:10-52 with the 64-byte records resident in device memory: Next() + the upload
+// in AcceleratedMipNeRF::GetGradient become one on-device draw-and-gather inside TrainStep.
+class BinDataset {
+ public:
+  static constexpr int BatchSize = 1024;  // BinDataset.cs:12
+  explicit BinDataset(const std::string& file, int device = 0) { check(nerf_dataset_load(file.c_str(), device, &d_)); }
+  BinDataset(const void* records, long n_records, int device = 0) { check(nerf_dataset_create(records, n_records, device, &d_)); }
+  ~BinDataset() { nerf_dataset_destroy(d_); }
+  BinDataset(const BinDataset&) = delete;
+  long NumSamples() const {  // BinDataset.cs:15
+    long n = 0;
+    check(nerf_dataset_size(d_, &n));
+    return n;
+  }
+  // one iteration of Train() (Program.cs:28-45): draw the batch, forward, backward, Adam; returns the total loss
+  float TrainStep(AcceleratedMipNeRF& model, AcceleratedAdamOptimizer& optimizer, int batch_size, uint64_t sampler_seed, float lr) {
+    float loss = 0.f;
+    check(nerf_mipnerf_train_step_dataset(model.handle(), optimizer.handle(), d_, batch_size, sampler_seed, lr, &loss));
+    return loss;
+  }
+  nerf_dataset* handle() const { return d_; }
+
+ private:
+  nerf_dataset* d_ = nullptr;
+};
+
+// MipHelpers.LearningRateDecay (ScratchNerf/ScratchNerf/MipHelpers.cs:758-773) with Config's defaults (TrainState.cs:54-60)
+inline float LearningRateDecay(int step, float lr_init = 5e-4f, float lr_final = 5e-6f, int max_steps = 1000000, int lr_delay_steps = 2500,
+                               float lr_delay_mult = 0.01f) {
+  return nerf_learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult);
+}
+inline void SaveCheckpoint(AcceleratedMipNeRF& model, AcceleratedAdamOptimizer* optimizer, const std::string& path) {
+  check(nerf_checkpoint_save(model.handle(), optimizer ? optimizer->handle() : nullptr, path.c_str()));
+}
+inline void LoadCheckpoint(AcceleratedMipNeRF& model, AcceleratedAdamOptimizer* optimizer, const std::string& path) {
+  check(nerf_checkpoint_load(model.handle(), optimizer ? optimizer->handle() : nullptr, path.c_str()));
+}
+
 // ANU/OutputRetriever.h:7-11
 struct OutputRetriever {
   static std::vector<Vector3> RetrieveOutput(uint64_t dev_output, int size) {  // .cpp:6-14

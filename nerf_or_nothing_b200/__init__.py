@@ -109,6 +109,17 @@ _SIGNATURES = {
     "nerf_get_output_gradient": [_VP, _VP, _VP, _VP, _F, _F, _I],
     "nerf_volumetric_rendering_gradient": [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I],
     "nerf_adam_optimizer_step": [_VP, _VP, _VP, _VP, _F, _F, _F, _F, _F, _L, _I],
+    "nerf_dataset_create": [_VP, _L, _I, C.POINTER(_VP)],
+    "nerf_dataset_load": [C.c_char_p, _I, C.POINTER(_VP)],
+    "nerf_dataset_size": [_VP, C.POINTER(_L)],
+    "nerf_dataset_destroy": [_VP],
+    "nerf_dataset_draw_indices": [_VP, C.c_uint64, C.c_uint32, C.c_uint32, _I, _VP],
+    "nerf_dataset_gather": [_VP, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP],
+    "nerf_mipnerf_train_step_dataset": [_VP, _VP, _VP, _I, C.c_uint64, _F, C.POINTER(_F)],
+    "nerf_image_error": [_VP, _VP, _L, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "nerf_learning_rate_decay": [_I, _F, _F, _I, _I, _F],
+    "nerf_checkpoint_save": [_VP, _VP, C.c_char_p],
+    "nerf_checkpoint_load": [_VP, _VP, C.c_char_p],
     "nerf_version": [],
     "nerf_last_error": [],
 }
@@ -127,6 +138,7 @@ def lib() -> C.CDLL:
             fn.argtypes = args
             fn.restype = C.c_int
         l.nerf_last_error.restype = C.c_char_p
+        l.nerf_learning_rate_decay.restype = C.c_float
         l.nerf_default_config.restype = None
         _lib = l
     return _lib
@@ -359,6 +371,21 @@ class AcceleratedMipNeRF:
                                                 C.byref(loss) if want_loss else None))
         return loss.value if want_loss else None
 
+    def train_step_dataset(self, optimizer, dataset, n_rays, sampler_seed, lr, want_loss=True):
+        """One iteration of Train() (SN/Program.cs:28-45) with the batch drawn and gathered on the device from a resident
+        BinDataset: no per-step host->device traffic."""
+        loss = C.c_float()
+        check(lib().nerf_mipnerf_train_step_dataset(self._h, optimizer._h, dataset._h, n_rays, sampler_seed, lr,
+                                                    C.byref(loss) if want_loss else None))
+        return loss.value if want_loss else None
+
+    # ---- checkpoints (SURVEY §8(f) row 4)
+    def save_checkpoint(self, path, optimizer=None):
+        check(lib().nerf_checkpoint_save(self._h, optimizer._h if optimizer is not None else None, str(path).encode()))
+
+    def load_checkpoint(self, path, optimizer=None):
+        check(lib().nerf_checkpoint_load(self._h, optimizer._h if optimizer is not None else None, str(path).encode()))
+
     # ---- multi-GPU (SURVEY §8e)
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
@@ -366,6 +393,58 @@ class AcceleratedMipNeRF:
 
     def allreduce_gradients(self):
         check(lib().nerf_mipnerf_allreduce_gradients(self._h))
+
+
+class BinDataset:
+    """SN/BinDataset.cs:10-52 with the records resident in device memory (64-byte records, `scene.pack_records`)."""
+
+    def __init__(self, records_or_path, device=0):
+        self._h = C.c_void_p()
+        if isinstance(records_or_path, (str, bytes)) or hasattr(records_or_path, "__fspath__"):
+            check(lib().nerf_dataset_load(str(records_or_path).encode(), device, C.byref(self._h)))
+        else:
+            rec = np.ascontiguousarray(records_or_path, np.float32).reshape(-1, 16)
+            check(lib().nerf_dataset_create(_hp(rec), rec.shape[0], device, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.nerf_dataset_destroy(self._h)
+            self._h = None
+
+    def __len__(self):
+        n = C.c_long()
+        check(lib().nerf_dataset_size(self._h, C.byref(n)))
+        return n.value
+
+    def draw_indices(self, seed, step, n_rays, first_slot=0):
+        idx = np.empty(n_rays, np.int64)
+        check(lib().nerf_dataset_draw_indices(self._h, seed, step, first_slot, n_rays, _hp(idx)))
+        return idx
+
+    def gather(self, n_rays, indices=None, seed=0, step=0, first_slot=0):
+        """LoadBatch on the device; returns host copies of the SoA batch (parity hook)."""
+        import torch
+        bufs = {k: torch.empty((n_rays, w), dtype=torch.float32, device="cuda")
+                for k, w in (("origins", 3), ("directions", 3), ("radii", 1), ("nears", 1), ("fars", 1), ("loss_mults", 1), ("pixels", 3))}
+        idx = None if indices is None else np.ascontiguousarray(indices, np.int64)
+        check(lib().nerf_dataset_gather(self._h, _hp(idx) if idx is not None else None, seed, step, first_slot, n_rays,
+                                        *[C.c_void_p(bufs[k].data_ptr()) for k in ("origins", "directions", "radii", "nears", "fars",
+                                                                                   "loss_mults", "pixels")]))
+        out = {k: v.cpu().numpy() for k, v in bufs.items()}
+        for k in ("radii", "nears", "fars", "loss_mults"):
+            out[k] = out[k][:, 0]
+        return out
+
+
+def image_error(a, b):
+    """(mse, psnr) of two images; psnr = MseToPsnr (SN/MipHelpers.cs:672).  Computed on the device."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    if a.shape != b.shape:
+        raise ValueError("image_error: shape mismatch")
+    mse, psnr = C.c_double(), C.c_double()
+    check(lib().nerf_image_error(_hp(a), _hp(b), a.size, 0, C.byref(mse), C.byref(psnr)))
+    return mse.value, psnr.value
 
 
 def comm_unique_id() -> bytes:
@@ -448,7 +527,12 @@ class OutputRetriever:
 
 
 def learning_rate_decay(step, lr_init=5e-4, lr_final=5e-6, max_steps=1000000, lr_delay_steps=2500, lr_delay_mult=0.01):
-    """SN/MipHelpers.cs:758-773 with the defaults of SN/TrainState.cs:54-60 (host-side, float32 arithmetic)."""
+    """SN/MipHelpers.cs:758-773 with the defaults of SN/TrainState.cs:54-60 — the library's C entry point."""
+    return float(lib().nerf_learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult))
+
+
+def _learning_rate_decay_numpy(step, lr_init=5e-4, lr_final=5e-6, max_steps=1000000, lr_delay_steps=2500, lr_delay_mult=0.01):
+    """numpy float32 restatement of the same schedule (kept for cross-checks)."""
     f = np.float32
     delay = f(1.0)
     if lr_delay_steps > 0:

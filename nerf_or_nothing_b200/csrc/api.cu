@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -815,6 +816,236 @@ int nerf_mipnerf_train_step_dev(nerf_mipnerf* h, nerf_adam* a, const float* o, c
   set_batch_dev(h, o, d, radii, nears, fars, lm, pixels);
   NERF_TRY(gradient_core(h, n_rays, nullptr, nullptr));
   return finish_step(h, a, lr, loss_out);
+}
+
+// ---- resident dataset + on-device batch assembly (replaces SN/BinDataset.cs:27-52) -----------
+struct nerf_dataset {
+  int device = 0;
+  long n = 0;
+  float* rec = nullptr;  // [n, 16] floats in HBM
+  long* idx = nullptr;   // scratch for explicit / exported indices
+  long idx_cap = 0;
+};
+
+static int dataset_scratch(nerf_dataset* ds, long n) {
+  if (n <= ds->idx_cap) return 0;
+  if (ds->idx) cudaFree(ds->idx);
+  ds->idx = nullptr; ds->idx_cap = 0;
+  NERF_CUDA(cudaMalloc(&ds->idx, (size_t)n * sizeof(long)));
+  ds->idx_cap = n;
+  return 0;
+}
+
+int nerf_dataset_create(const void* records, long n_records, int device, nerf_dataset** out) {
+  if (!records || n_records <= 0 || n_records > 0xFFFFFFFFL || !out) { set_error("dataset_create: bad arguments"); return NERF_ERR_INVALID; }
+  *out = nullptr;
+  NERF_TRY(check_device(device));
+  nerf_dataset* ds = new nerf_dataset();
+  ds->device = device; ds->n = n_records;
+  if (cudaMalloc(&ds->rec, (size_t)n_records * NERF_RECORD_BYTES) != cudaSuccess) {
+    set_error("dataset_create: cudaMalloc of %ld records failed", n_records); delete ds; return NERF_ERR_NO_DEVICE;
+  }
+  if (cudaMemcpy(ds->rec, records, (size_t)n_records * NERF_RECORD_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("dataset_create: upload failed"); cudaFree(ds->rec); delete ds; return NERF_ERR_NO_DEVICE;
+  }
+  *out = ds;
+  return 0;
+}
+
+int nerf_dataset_load(const char* path, int device, nerf_dataset** out) {  // train_data.bin of SN/Program.cs:23
+  if (!path || !out) { set_error("dataset_load: null argument"); return NERF_ERR_INVALID; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("dataset_load: cannot open %s", path); return NERF_ERR_INVALID; }
+  fseek(f, 0, SEEK_END);
+  const long bytes = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  const long n = bytes / NERF_RECORD_BYTES;  // SN/BinDataset.cs:15
+  if (n <= 0) { fclose(f); set_error("dataset_load: %s holds no 64-byte record", path); return NERF_ERR_INVALID; }
+  std::vector<char> buf((size_t)n * NERF_RECORD_BYTES);
+  const size_t got = fread(buf.data(), NERF_RECORD_BYTES, (size_t)n, f);
+  fclose(f);
+  if ((long)got != n) { set_error("dataset_load: short read from %s", path); return NERF_ERR_INVALID; }  // SN/BinDataset.cs:38-39
+  return nerf_dataset_create(buf.data(), n, device, out);
+}
+
+int nerf_dataset_size(const nerf_dataset* ds, long* n) {
+  if (!ds || !n) { set_error("null argument"); return NERF_ERR_INVALID; }
+  *n = ds->n;
+  return 0;
+}
+
+int nerf_dataset_destroy(nerf_dataset* ds) {
+  if (!ds) return 0;
+  cudaSetDevice(ds->device);
+  cudaFree(ds->rec); cudaFree(ds->idx);
+  delete ds;
+  return 0;
+}
+
+// the record indices a step with (seed, step, first_slot) draws — what nerf_mipnerf_train_step_dataset uses
+int nerf_dataset_draw_indices(nerf_dataset* ds, uint64_t seed, uint32_t step, uint32_t first_slot, int n_rays, int64_t* idx_host) {
+  if (!ds || !idx_host || n_rays <= 0) { set_error("draw_indices: bad arguments"); return NERF_ERR_INVALID; }
+  NERF_CUDA(cudaSetDevice(ds->device));
+  NERF_TRY(dataset_scratch(ds, n_rays));
+  NERF_TRY(launch_draw_indices(seed, first_slot, step, ds->n, n_rays, ds->idx, nullptr));
+  NERF_CUDA(cudaMemcpy(idx_host, ds->idx, (size_t)n_rays * sizeof(long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// gather records idx_host[0..n) (or, if NULL, the Philox draw of (seed, step, first_slot)) into caller device arrays
+int nerf_dataset_gather(nerf_dataset* ds, const int64_t* idx_host, uint64_t seed, uint32_t step, uint32_t first_slot, int n_rays,
+                        float* origins3_dev, float* directions3_dev, float* radii_dev, float* nears_dev, float* fars_dev,
+                        float* loss_mults_dev, float* pixels3_dev) {
+  if (!ds || n_rays <= 0 || !origins3_dev || !directions3_dev || !radii_dev || !nears_dev || !fars_dev || !loss_mults_dev || !pixels3_dev) {
+    set_error("dataset_gather: bad arguments"); return NERF_ERR_INVALID;
+  }
+  NERF_CUDA(cudaSetDevice(ds->device));
+  const long* idx = nullptr;
+  if (idx_host) {
+    NERF_TRY(dataset_scratch(ds, n_rays));
+    NERF_CUDA(cudaMemcpy(ds->idx, idx_host, (size_t)n_rays * sizeof(long), cudaMemcpyHostToDevice));
+    idx = ds->idx;
+  }
+  NERF_TRY(launch_gather_batch(ds->rec, ds->n, idx, seed, first_slot, step, n_rays, origins3_dev, directions3_dev, radii_dev, nears_dev,
+                               fars_dev, loss_mults_dev, pixels3_dev, nullptr));
+  NERF_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+// one training step with the batch drawn and assembled on the device: no host->device traffic
+int nerf_mipnerf_train_step_dataset(nerf_mipnerf* h, nerf_adam* a, nerf_dataset* ds, int n_rays, uint64_t sampler_seed, float lr,
+                                    float* loss_out) {
+  if (!h || !a || !ds) { set_error("train_step_dataset: null argument"); return NERF_ERR_INVALID; }
+  if (ds->device != h->cfg.device) { set_error("train_step_dataset: dataset on device %d, model on %d", ds->device, h->cfg.device); return NERF_ERR_INVALID; }
+  if (n_rays <= 0 || n_rays > h->Rmax) { set_error("n_rays=%d outside (0, %d]", n_rays, h->Rmax); return NERF_ERR_INVALID; }
+  NERF_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t R = (size_t)h->Rmax;
+  float* b = h->rays_dev;
+  {
+    ProfActivate pa(h);
+    ProfScope ps(PC_MISC, h->st);
+    NERF_TRY(launch_gather_batch(ds->rec, ds->n, nullptr, sampler_seed, h->ray_offset, h->step, n_rays, b, b + 3 * R, b + 6 * R, b + 7 * R,
+                                 b + 8 * R, b + 9 * R, b + 10 * R, h->st));
+  }
+  set_batch_dev(h, b, b + 3 * R, b + 6 * R, b + 7 * R, b + 8 * R, b + 9 * R, b + 10 * R);
+  NERF_TRY(gradient_core(h, n_rays, nullptr, nullptr));
+  return finish_step(h, a, lr, loss_out);
+}
+
+// ---- image metrics ----------------------------------------------------------------------------
+// mse over n floats and psnr = -10/ln(10) * ln(mse) (SN/MipHelpers.cs:672); on_device: a/b are device pointers
+int nerf_image_error(const float* a, const float* b, long n, int on_device, double* mse, double* psnr) {
+  if (!a || !b || n <= 0) { set_error("image_error: bad arguments"); return NERF_ERR_INVALID; }
+  struct DevBuf {  // freed on every exit path
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+  } da, db, dout;
+  NERF_CUDA(cudaMalloc(&dout.p, sizeof(double)));
+  if (!on_device) {
+    NERF_CUDA(cudaMalloc(&da.p, (size_t)n * 4));
+    NERF_CUDA(cudaMalloc(&db.p, (size_t)n * 4));
+    NERF_CUDA(cudaMemcpy(da.p, a, (size_t)n * 4, cudaMemcpyHostToDevice));
+    NERF_CUDA(cudaMemcpy(db.p, b, (size_t)n * 4, cudaMemcpyHostToDevice));
+  }
+  NERF_TRY(launch_sq_err(on_device ? a : (const float*)da.p, on_device ? b : (const float*)db.p, n, (double*)dout.p, nullptr));
+  double sq = 0.0;
+  NERF_CUDA(cudaMemcpy(&sq, dout.p, sizeof(double), cudaMemcpyDeviceToHost));
+  const double m = sq / (double)n;
+  if (mse) *mse = m;
+  if (psnr) *psnr = -10.0 / log(10.0) * log(m);
+  return 0;
+}
+
+// ---- learning-rate schedule and checkpoints ---------------------------------------------------
+// SN/MipHelpers.cs:758-773, float32 arithmetic like the original
+float nerf_learning_rate_decay(int step, float lr_init, float lr_final, int max_steps, int lr_delay_steps, float lr_delay_mult) {
+  float delay_rate = 1.0f;
+  if (lr_delay_steps > 0) {
+    float p = (float)step / (float)lr_delay_steps;
+    p = p < 0.f ? 0.f : (p > 1.f ? 1.f : p);
+    delay_rate = lr_delay_mult + (1.0f - lr_delay_mult) * sinf(0.5f * 3.14159274f * p);
+  }
+  float t = (float)step / (float)max_steps;
+  t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+  return delay_rate * expf(logf(lr_init) * (1.0f - t) + logf(lr_final) * t);
+}
+
+namespace {
+struct CkptHeader {
+  char magic[8];        // "NERFB200"
+  uint32_t version;     // 1
+  uint32_t n_tensors;
+  int64_t n_params;
+  int32_t adam_iteration;  // -1: no optimizer state stored
+  uint32_t step;           // Philox step counter of the model
+  int32_t shape[7];        // depth, width, depth_cond, width_cond, skip, deg_point, deg_view
+};
+}  // namespace
+
+// parameters (flat W0..W10,b0..b10), Adam m/v/iteration and the sampling step counter -> one file
+int nerf_checkpoint_save(nerf_mipnerf* h, nerf_adam* a, const char* path) {
+  if (!h || !path) { set_error("checkpoint_save: null argument"); return NERF_ERR_INVALID; }
+  if (a && a->n != h->shape.n_params) { set_error("checkpoint_save: optimizer size %ld != model parameters %ld", a->n, h->shape.n_params); return NERF_ERR_INVALID; }
+  NERF_CUDA(cudaSetDevice(h->cfg.device));
+  NERF_CUDA(cudaStreamSynchronize(h->st));
+  const long n = h->shape.n_params;
+  std::vector<float> buf((size_t)n * (a ? 3 : 1));
+  NERF_CUDA(cudaMemcpy(buf.data(), h->params, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (a) {
+    NERF_CUDA(cudaMemcpy(buf.data() + n, a->m, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    NERF_CUDA(cudaMemcpy(buf.data() + 2 * n, a->v, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  CkptHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, "NERFB200", 8);
+  hd.version = 1; hd.n_tensors = (uint32_t)h->sizes.size(); hd.n_params = n;
+  hd.adam_iteration = a ? a->iteration : -1; hd.step = h->step;
+  const nerf_config& c = h->cfg;
+  const int32_t shp[7] = {c.net_depth, c.net_width, c.net_depth_condition, c.net_width_condition, c.skip_layer, c.deg_point, c.deg_view};
+  memcpy(hd.shape, shp, sizeof(shp));
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("checkpoint_save: cannot open %s", path); return NERF_ERR_INVALID; }
+  bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+  ok = ok && fwrite(h->sizes.data(), sizeof(int), h->sizes.size(), f) == h->sizes.size();
+  ok = ok && fwrite(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { set_error("checkpoint_save: write to %s failed", path); return NERF_ERR_INVALID; }
+  return 0;
+}
+
+int nerf_checkpoint_load(nerf_mipnerf* h, nerf_adam* a, const char* path) {
+  if (!h || !path) { set_error("checkpoint_load: null argument"); return NERF_ERR_INVALID; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("checkpoint_load: cannot open %s", path); return NERF_ERR_INVALID; }
+  CkptHeader hd;
+  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "NERFB200", 8) != 0 || hd.version != 1) {
+    fclose(f); set_error("checkpoint_load: %s is not a version-1 checkpoint", path); return NERF_ERR_INVALID;
+  }
+  const nerf_config& c = h->cfg;
+  const int32_t shp[7] = {c.net_depth, c.net_width, c.net_depth_condition, c.net_width_condition, c.skip_layer, c.deg_point, c.deg_view};
+  std::vector<int> sizes(hd.n_tensors);
+  if (hd.n_params != h->shape.n_params || hd.n_tensors != h->sizes.size() || memcmp(hd.shape, shp, sizeof(shp)) != 0 ||
+      fread(sizes.data(), sizeof(int), sizes.size(), f) != sizes.size() || sizes != h->sizes) {
+    fclose(f); set_error("checkpoint_load: %s was written for a different network shape", path); return NERF_ERR_INVALID;
+  }
+  const long n = h->shape.n_params;
+  const bool has_opt = hd.adam_iteration >= 0;
+  if (a && !has_opt) { fclose(f); set_error("checkpoint_load: %s holds no optimizer state", path); return NERF_ERR_INVALID; }
+  if (a && a->n != n) { fclose(f); set_error("checkpoint_load: optimizer size %ld != %ld", a->n, n); return NERF_ERR_INVALID; }
+  std::vector<float> buf((size_t)n * (has_opt ? 3 : 1));
+  const size_t got = fread(buf.data(), sizeof(float), buf.size(), f);
+  fclose(f);
+  if (got != buf.size()) { set_error("checkpoint_load: %s is truncated", path); return NERF_ERR_INVALID; }
+  NERF_CUDA(cudaSetDevice(h->cfg.device));
+  NERF_CUDA(cudaStreamSynchronize(h->st));
+  NERF_CUDA(cudaMemcpy(h->params, buf.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  h->step = hd.step;
+  if (a) {
+    NERF_CUDA(cudaMemcpy(a->m, buf.data() + n, (size_t)n * 4, cudaMemcpyHostToDevice));
+    NERF_CUDA(cudaMemcpy(a->v, buf.data() + 2 * n, (size_t)n * 4, cudaMemcpyHostToDevice));
+    a->iteration = hd.adam_iteration;
+  }
+  return 0;
 }
 
 // ---- multi-GPU -------------------------------------------------------------------------------------

@@ -1,0 +1,85 @@
+// dataset.cu — device-resident ray dataset and on-device batch assembly, image metrics (row 3).
+//
+// Replaces SN/BinDataset.cs:27-52 (LoadBatch: BatchSize random 64-byte records read one by one from train_data.bin with a
+// file seek each, then six small host->device copies per step in ANU/AcceleratedMipNeRF.cpp:66-79).  Here the records
+// live in HBM once; a step draws its record indices on the device from the counter-based Philox stream and gathers them
+// straight into the structure-of-arrays batch the kernels read — no per-step host traffic at all.
+// Record (16 floats, SN/BinDataset.cs:40-49): origin(3) direction(3) viewdir(3) radius near far lossmult rgb(3).
+#include "kernels.cuh"
+
+namespace nerf {
+namespace {
+
+// Philox stream of the batch sampler: counter = (global ray slot, 0, step, 0xDA7A5E7), key = seed; index = floor(x * n / 2^32)
+__device__ __forceinline__ long draw_index(uint64_t seed, uint32_t slot, uint32_t step, long n) {
+  const uint32_t x = philox4x32_10_w0(slot, 0u, step, 0x0DA7A5E7u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (long)(((unsigned long long)x * (unsigned long long)n) >> 32);
+}
+
+__global__ void k_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, int R, long* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) idx[i] = draw_index(seed, slot0 + (uint32_t)i, step, n);
+}
+
+// one thread per ray: 64-byte record in (4 x 16-byte loads), SoA out
+__global__ void k_gather_batch(const float4* __restrict__ rec, long n, const long* __restrict__ idx, uint64_t seed, uint32_t slot0,
+                               uint32_t step, int R, float* __restrict__ o, float* __restrict__ d, float* __restrict__ radii,
+                               float* __restrict__ nears, float* __restrict__ fars, float* __restrict__ lm, float* __restrict__ pix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  long j = idx ? idx[i] : draw_index(seed, slot0 + (uint32_t)i, step, n);
+  j = j < 0 ? 0 : (j >= n ? n - 1 : j);
+  const float4 a = __ldg(rec + j * 4), b = __ldg(rec + j * 4 + 1), c = __ldg(rec + j * 4 + 2), e = __ldg(rec + j * 4 + 3);
+  o[i * 3] = a.x; o[i * 3 + 1] = a.y; o[i * 3 + 2] = a.z;
+  d[i * 3] = a.w; d[i * 3 + 1] = b.x; d[i * 3 + 2] = b.y;
+  // b.z b.w c.x = viewdir: the kernels normalise `direction` themselves (SURVEY A-D7), kept in the record for layout parity
+  radii[i] = c.y; nears[i] = c.z; fars[i] = c.w; lm[i] = e.x;
+  pix[i * 3] = e.y; pix[i * 3 + 1] = e.z; pix[i * 3 + 2] = e.w;
+}
+
+// sum of squared differences over n floats -> out[0] (fp64 accumulation; one launch, atomics on a zeroed double)
+__global__ void k_sq_err(const float* __restrict__ a, const float* __restrict__ b, long n, double* __restrict__ out) {
+  double s = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double d = (double)a[i] - (double)b[i];
+    s += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += ws[w];
+    atomicAdd(out, t);
+  }
+}
+
+}  // namespace
+
+int launch_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, int R, long* idx, cudaStream_t st) {
+  k_draw_indices<<<(unsigned)cdiv(R, 256), 256, 0, st>>>(seed, slot0, step, n, R, idx);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_gather_batch(const float* records, long n, const long* idx, uint64_t seed, uint32_t slot0, uint32_t step, int R, float* o,
+                        float* d, float* radii, float* nears, float* fars, float* lm, float* pix, cudaStream_t st) {
+  k_gather_batch<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(reinterpret_cast<const float4*>(records), n, idx, seed, slot0, step, R, o, d, radii,
+                                                         nears, fars, lm, pix);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_sq_err(const float* a, const float* b, long n, double* out, cudaStream_t st) {
+  NERF_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+  long blocks = cdiv(n, 256 * 8);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  k_sq_err<<<(unsigned)blocks, 256, 0, st>>>(a, b, n, out);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace nerf

@@ -57,6 +57,12 @@ int launch_output_gradient(const float* comp_rgb, const float* pixels, const flo
                            cudaStream_t st);
 int launch_sum(const float* x, int n, float* out, cudaStream_t st);  // deterministic single-block sum
 
+// dataset.cu — resident dataset (64-byte records, SN/BinDataset.cs:40-49), on-device batch draw + gather, image error
+int launch_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, int R, long* idx, cudaStream_t st);
+int launch_gather_batch(const float* records, long n, const long* idx, uint64_t seed, uint32_t slot0, uint32_t step, int R, float* o,
+                        float* d, float* radii, float* nears, float* fars, float* lm, float* pix, cudaStream_t st);
+int launch_sq_err(const float* a, const float* b, long n, double* out, cudaStream_t st);
+
 // ---- adam.cu (B.6) ------------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float inv1,
                 float inv2, int eps_mode, float grad_scale, cudaStream_t st);
