@@ -14,18 +14,6 @@
 
 using namespace AcceleratedNeRFUtils;
 
-// SN/MipHelpers.cs:758-773 with SN/TrainState.cs:54-60
-static float LearningRateDecay(int step, float lrInit = 5e-4f, float lrFinal = 5e-6f, int maxSteps = 1000000, int delaySteps = 2500,
-                               float delayMult = 0.01f) {
-  float delayRate = 1.f;
-  if (delaySteps > 0) {
-    const float p = std::fmin(std::fmax((float)step / delaySteps, 0.f), 1.f);
-    delayRate = delayMult + (1.f - delayMult) * std::sin(0.5f * 3.14159265358979f * p);
-  }
-  const float t = std::fmin(std::fmax((float)step / maxSteps, 0.f), 1.f);
-  return delayRate * std::exp(std::log(lrInit) * (1 - t) + std::log(lrFinal) * t);
-}
-
 int main(int argc, char** argv) {
   const int batch = 1024, steps = argc > 2 ? std::atoi(argv[2]) : 3;  // SN/BinDataset.cs:12
   std::vector<Vector3> origins(batch), dirs(batch), pixels(batch);
@@ -49,7 +37,7 @@ int main(int argc, char** argv) {
         }
       }
       uint64_t output = 0;
-      const float lr = LearningRateDecay(step);
+      const float lr = LearningRateDecay(step);                                       // MipHelpers.cs:758-773 via the library
       auto grad = model.GetGradient(origins, dirs, radii, nears, fars, lossMults,     // Program.cs:51-58
                                     [&](uint64_t inputptr, int level, float lossMultSum, uint64_t lm) {
                                       output = inputptr;
