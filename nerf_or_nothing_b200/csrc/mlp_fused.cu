@@ -62,6 +62,8 @@ struct alignas(64) FusedParams {
   // training only: every step's activations [M, N] bf16 (box {64, 32}, one store per epilogue warp) and ReLU bit planes
   CUtensorMap map_act[kMaxSteps];
   uint32_t* bits[kMaxSteps];
+  // dgrad chain only: bits[s] is READ (ReLU mask of the step's output); step 0 adds the rank-1 term r1[row] * v1[col]
+  const float* r1;      // [M] dL/d raw_density
 };
 
 namespace {
@@ -126,6 +128,18 @@ __device__ __forceinline__ void stage_half_row(uint8_t* row_ptr, int half, int s
     *reinterpret_cast<uint4*>(row_ptr + (((half * 4 + q) ^ swz) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
+// dgrad chain: one 32-column chunk of dX = dZ W (+ r1 v1^T), masked by the ReLU bits of the layer below, bf16 pairs out
+__device__ __forceinline__ void dgrad_chunk(const uint32_t (&r)[32], uint32_t mask, float r1, const float* v1, uint32_t* packed16) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    float x0 = __uint_as_float(r[2 * q]), x1 = __uint_as_float(r[2 * q + 1]);
+    if (v1) { x0 = fmaf(r1, v1[2 * q], x0); x1 = fmaf(r1, v1[2 * q + 1], x1); }
+    x0 = ((mask >> (2 * q)) & 1u) ? x0 : 0.f;
+    x1 = ((mask >> (2 * q + 1)) & 1u) ? x1 : 0.f;
+    packed16[q] = pack2(x0, x1);
+  }
+}
+
 // One CTA walks PAIRS of 128-row tiles.  Tensor memory (512 columns): per tile t, ACT[t] = 128 columns holding the
 // 256 bf16 activations of the current layer (updated IN PLACE once the layer's MMAs are complete) and ACC[t] = 128
 // fp32 accumulator columns (one N-half of the layer).  Both tiles consume every weight stage, so a [128 x 64] weight
@@ -133,8 +147,12 @@ __device__ __forceinline__ void stage_half_row(uint8_t* row_ptr, int half, int s
 // the TMEM lane quarter it may access), warp 8 the TMA producer, warp 9 the MMA issuer.
 // TRAIN: every layer's activations and ReLU bit planes are also written out for the backward pass (each epilogue warp
 // restages its 32 rows in shared memory and issues its own TMA store).
-template <bool TRAIN>
+// MODE 0: inference forward; 1: training forward; 2: backward dgrad chain (A of step 0 = dZ of the condition layer from
+// shared memory, epilogue = rank-1 density-head term + ReLU mask of the layer below, every step's dZ written out for wgrad).
+template <int MODE>
 __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_constant__ FusedParams p) {
+  constexpr bool TRAIN = MODE != 0;   // activations / gradients are written out
+  constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kWStages - 1 : kWStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[kWStages], w_empty[kWStages], pos_full, pos_empty, dir_full, dir_empty, acc_full, acc_empty, act_ready;
@@ -163,7 +181,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
   if (warp == 8) {
     tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
-      prefetch_tmap(&p.map_pos); prefetch_tmap(&p.map_dir);
+      prefetch_tmap(&p.map_pos);
+      if (!DGRAD) prefetch_tmap(&p.map_dir);
       for (int s = 0; s < p.n_steps; s++) { prefetch_tmap(&p.map_w[s]); if (TRAIN) prefetch_tmap(&p.map_act[s]); }
     }
   }
@@ -274,6 +293,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
       const long row = (long)row_w + lane;
       const bool row_ok = row < p.M;
       float head[3] = {0.f, 0.f, 0.f};
+      const float r1v = (DGRAD && row_ok) ? __ldg(p.r1 + row) : 0.f;
       uint32_t held[64];  // first half's outputs wait in registers until the second half's MMAs have read ACT
       for (int s = 0; s < p.n_steps; s++) {
         const FusedParams::Step st = p.steps[s];
@@ -299,6 +319,18 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
           const bool last_half = h == st.n_halves - 1;
           const float* bias = s_const + st.bias_off + h * 128;
           uint32_t m0, m1, m2, m3;
+          uint4 mk = make_uint4(0u, 0u, 0u, 0u);  // DGRAD: ReLU mask words of this thread's 128 columns (requested before the wait)
+          if (DGRAD && row_ok) mk = __ldg(reinterpret_cast<const uint4*>(p.bits[s] + row * (st.n_halves * 4) + h * 4));
+          const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + h * 128 : nullptr;
+          // one 32-column chunk c of this half: forward = bias + ReLU (+ heads, + mask out); dgrad = (+ r1 v1^T) * mask in
+          auto chunk = [&](const uint32_t (&r)[32], int c, const float* hw, uint32_t* out16) -> uint32_t {
+            if (DGRAD) {
+              const uint32_t m = c == 0 ? mk.x : (c == 1 ? mk.y : (c == 2 ? mk.z : mk.w));
+              dgrad_chunk(r, m, r1v, v1 ? v1 + c * 32 : nullptr, out16);
+              return 0u;
+            }
+            return epi_chunk_any<MODE == 1>(st.head, r, bias + c * 32, hw + c * 32, head, out16);
+          };
           mbar_wait(&acc_full, n_full & 1);
           n_full++;
           tc_fence_after_sync();
@@ -310,13 +342,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty);
-            m0 = epi_chunk_any<TRAIN>(st.head, r0, bias, head_w + h * 128, head, held);
+            m0 = chunk(r0, 0, head_w + h * 128, held);
             ship(h * 128, 0, held);
-            m1 = epi_chunk_any<TRAIN>(st.head, r1, bias + 32, head_w + h * 128 + 32, head, held + 16);
+            m1 = chunk(r1, 1, head_w + h * 128, held + 16);
             ship(h * 128, 1, held + 16);
-            m2 = epi_chunk_any<TRAIN>(st.head, r2, bias + 64, head_w + h * 128 + 64, head, held + 32);
+            m2 = chunk(r2, 2, head_w + h * 128, held + 32);
             ship(h * 128 + 64, 0, held + 32);
-            m3 = epi_chunk_any<TRAIN>(st.head, r3, bias + 96, head_w + h * 128 + 96, head, held + 48);
+            m3 = chunk(r3, 3, head_w + h * 128, held + 48);
             ship(h * 128 + 64, 1, held + 48);
           } else {
             // every MMA of the layer is complete: ACT may be overwritten in place
@@ -330,24 +362,24 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
             tmem_ld_32x32(acc, ra);
             tmem_ld_wait();
             tmem_ld_32x32(acc + 32, rb);
-            m0 = epi_chunk_any<TRAIN>(st.head, ra, bias, hw, head, pk);
+            m0 = chunk(ra, 0, hw, pk);
             if (st.produces) tmem_st_16(out, pk);
             ship(h * 128, 0, pk);
             tmem_ld_wait();
             tmem_ld_32x32(acc + 64, ra);
-            m1 = epi_chunk_any<TRAIN>(st.head, rb, bias + 32, hw + 32, head, pk);
+            m1 = chunk(rb, 1, hw, pk);
             if (st.produces) tmem_st_16(out + 16, pk);
             ship(h * 128, 1, pk);
             tmem_ld_wait();
             tmem_ld_32x32(acc + 96, rb);
-            m2 = epi_chunk_any<TRAIN>(st.head, ra, bias + 64, hw + 64, head, pk);
+            m2 = chunk(ra, 2, hw, pk);
             if (st.produces) tmem_st_16(out + 32, pk);
             ship(h * 128 + 64, 0, pk);
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty);
-            m3 = epi_chunk_any<TRAIN>(st.head, rb, bias + 96, hw + 96, head, pk);
+            m3 = chunk(rb, 3, hw, pk);
             if (st.produces) {
               tmem_st_16(out + 48, pk);
               tmem_st_wait();
@@ -357,9 +389,10 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
             }
             ship(h * 128 + 64, 1, pk);
           }
-          if (TRAIN && row_ok)
+          if (MODE == 1 && row_ok)
             *reinterpret_cast<uint4*>(p.bits[s] + row * (st.n_halves * 4) + h * 4) = make_uint4(m0, m1, m2, m3);
         }
+        if (DGRAD) continue;
         if (st.head == 1) {
           if (row_ok) p.raw_density[row] = head[0] + s_const[p.head_d_off + 256];
           head[0] = 0.f;
@@ -402,8 +435,9 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   const size_t smem = (size_t)(train ? kWStages - 1 : kWStages) * kWStageBytes + 2 * kEncBytes + (train ? 8 * kStageSlot : 0) +
                       (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -435,8 +469,51 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
   const int pairs = (int)cdiv(M, 256);
   const int grid = pairs < sms ? pairs : sms;
-  if (train) k_mlp_fused_fwd<true><<<grid, kThreadsF, smem, st>>>(p);
-  else k_mlp_fused_fwd<false><<<grid, kThreadsF, smem, st>>>(p);
+  if (train) k_mlp_fused_fwd<1><<<grid, kThreadsF, smem, st>>>(p);
+  else k_mlp_fused_fwd<0><<<grid, kThreadsF, smem, st>>>(p);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+
+// The backward dgrad chain of the trunk as one kernel (bf16 mode): step 0 takes dZ of the condition layer [M, Wc] and
+// W_cond^T, adds the density head's rank-1 term d_raw_density w_d^T and masks with the ReLU bits of the last trunk layer;
+// steps 1..D-1 walk the trunk downwards.  dz_out[i] receives dZ of trunk layer D-1-i (what the wgrad of that layer reads);
+// mask_bits[i] is the bit plane of that layer's activations.  wt[0] = W_cond^T [W, Wc]; wt[i] = W_{D-i}^T [W, W].
+int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, const __nv_bfloat16* const* wt, const int* wt_pitch, int D, int W,
+                           int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
+                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, cudaStream_t st) {
+  if (W != 256 || Wc != 128 || D > kMaxSteps || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  static int sms = 148;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
+  const size_t smem = (size_t)(kWStages - 1) * kWStageBytes + 2 * kEncBytes + 8 * kStageSlot + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
+  if (smem > 226 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  NERF_TRY(tc_make_tmap(&p.map_pos, dz_cond, M, 128, dz_cond_pitch, 128));  // A of step 0, loaded like the position encoding
+  for (int s = 0; s < D; s++) {
+    NERF_TRY(tc_make_tmap(&p.map_w[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_act[s], dz_out[s], M, W, W, 32));
+    p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
+    FusedParams::Step& stp = p.steps[s];
+    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
+    else { stp.n_act_kb = 4; stp.enc_kind = 0; stp.n_enc_kb = 0; }
+    stp.n_halves = 2;
+    stp.produces = s < D - 1 ? 1 : 0;
+    stp.head = 0; stp.bias_off = 0;
+  }
+  p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
+  p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
+  const int pairs = (int)cdiv(M, 256);
+  k_mlp_fused_fwd<2><<<pairs < sms ? pairs : sms, kThreadsF, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
 }

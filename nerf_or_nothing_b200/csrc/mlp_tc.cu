@@ -166,6 +166,32 @@ class TcMlp : public MlpEngine {
     return fused_forward(level, M, params, raw_density, raw_rgb, false, st);
   }
 
+  // biases of the D trunk layers and the condition layer, then the density head (w[256], b) and the rgb head (w[3][128], b[3]):
+  // the constants the fused kernels stage in shared memory, gathered once per parameter version
+  int ensure_fconsts(const float* params, cudaStream_t st) {
+    const int D = s_.D;
+    const int head_d_off = D * 256 + 128, head_rgb_off = head_d_off + 260, n_consts = head_rgb_off + 3 * 128 + 4;
+    if (!fconsts_) {
+      NERF_CUDA(cudaMalloc(&fconsts_, n_consts * sizeof(float)));
+      owned_.push_back(fconsts_);
+      NERF_CUDA(cudaMemsetAsync(fconsts_, 0, n_consts * sizeof(float), st));
+    }
+    if (!fconsts_dirty_) return 0;
+    ProfScope ps(PC_CAST, st);
+    for (int s = 0; s <= D; s++) {
+      const LayerInfo& L = s_.layers[s < D ? s : D + 1];
+      NERF_CUDA(cudaMemcpyAsync(fconsts_ + s * 256, params + L.b_off, L.out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    const LayerInfo& Ld = s_.layers[D];
+    const LayerInfo& Lr = s_.layers[D + 2];
+    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off, params + Ld.w_off, 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off + 256, params + Ld.b_off, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off, params + Lr.w_off, 3 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off + 384, params + Lr.b_off, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    fconsts_dirty_ = false;
+    return 0;
+  }
+
   int fused_forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, bool train, cudaStream_t st) {
     Level& lv = levels_[level];
     const int D = s_.D;
@@ -177,25 +203,7 @@ class TcMlp : public MlpEngine {
       kpad[s] = wp_[l].pitch; in_b[s] = s_.layers[l].in_b; wpl[s] = wp_[l].hi;
     }
     const int head_d_off = D * 256 + 128, head_rgb_off = head_d_off + 260, n_consts = head_rgb_off + 3 * 128 + 4;
-    if (!fconsts_) {
-      NERF_CUDA(cudaMalloc(&fconsts_, n_consts * sizeof(float)));
-      owned_.push_back(fconsts_);
-      NERF_CUDA(cudaMemsetAsync(fconsts_, 0, n_consts * sizeof(float), st));
-    }
-    if (fconsts_dirty_) {  // gather biases and head weights once per parameter version
-      ProfScope ps(PC_CAST, st);
-      for (int s = 0; s <= D; s++) {
-        const LayerInfo& L = s_.layers[s < D ? s : D + 1];
-        NERF_CUDA(cudaMemcpyAsync(fconsts_ + bias_off[s], params + L.b_off, L.out * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      }
-      const LayerInfo& Ld = s_.layers[D];
-      const LayerInfo& Lr = s_.layers[D + 2];
-      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off, params + Ld.w_off, 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off + 256, params + Ld.b_off, sizeof(float), cudaMemcpyDeviceToDevice, st));
-      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off, params + Lr.w_off, 3 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off + 384, params + Lr.b_off, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      fconsts_dirty_ = false;
-    }
+    NERF_TRY(ensure_fconsts(params, st));
     std::vector<__nv_bfloat16*> act_out(D + 1);
     for (int s = 0; s <= D; s++) act_out[s] = lv.acts[s].hi;
     ProfScope ps(PC_MLP_FWD, st);
@@ -226,6 +234,8 @@ class TcMlp : public MlpEngine {
       NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st));
       NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st));
     }
+    if (!split_ && can_fuse_forward() && getenv("NERF_NO_FUSED_DGRAD") == nullptr)
+      return backward_fused_chain(level, M, params, grads, d_raw_density, *cur, st);
     for (int i = C - 1; i >= 0; i--) {
       const int l = D + 1 + i;
       const LayerInfo& L = s_.layers[l];
@@ -261,6 +271,52 @@ class TcMlp : public MlpEngine {
         NERF_TRY(gemm_dgrad(*cur, wtp_[i], *nxt, M, L.out, L.in_a, nullptr, nullptr, lv.bits[i - 1], st));
         Plane* t = cur; cur = nxt; nxt = t;
       }
+    }
+    return 0;
+  }
+
+  // bf16 mode: the whole dgrad chain (condition layer -> trunk layers D-1..1) is ONE kernel that keeps dZ in tensor
+  // memory between layers and writes every layer's dZ once; the wgrad GEMMs then read those planes.
+  int backward_fused_chain(int level, long M, const float* params, float* grads, const float* d_raw_density, const Plane& dz_cond,
+                           cudaStream_t st) {
+    auto& lv = levels_[level];
+    const int D = s_.D, W = s_.W;
+    if (dzs_.empty()) {  // first training step through this path
+      dzs_.resize(D);
+      for (int j = 0; j < D; j++) NERF_TRY(alloc_plane(&dzs_[j], max_rows_, W));
+    }
+    NERF_TRY(ensure_fconsts(params, st));
+    const int head_d_off = D * 256 + 128, n_consts = head_d_off + 260 + 3 * 128 + 4;
+    std::vector<const __nv_bfloat16*> wt(D);
+    std::vector<int> wt_pitch(D);
+    std::vector<__nv_bfloat16*> dz_out(D);
+    std::vector<const uint32_t*> masks(D);
+    for (int j = 0; j < D; j++) {
+      const int l = j == 0 ? D + 1 : D - j;  // the layer whose dgrad step j performs; it produces dZ of trunk layer D-1-j
+      wt[j] = wtp_[l].hi; wt_pitch[j] = wtp_[l].pitch;
+      dz_out[j] = dzs_[j].hi; masks[j] = lv.bits[D - 1 - j];
+    }
+    {
+      ProfScope ps(PC_MLP_DGRAD, st);
+      NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
+                                      d_raw_density, dz_out.data(), masks.data(), st));
+    }
+    {  // condition layer
+      const LayerInfo& L = s_.layers[D + 1];
+      ProfScope ps(PC_MLP_WGRAD, st);
+      NERF_TRY(gemm_wgrad(dz_cond, lv.acts[D - 1], L.in_a, &lv.enc_dir, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
+    }
+    {  // density head
+      const LayerInfo& L = s_.layers[D];
+      const Plane& x = lv.acts[D - 1];
+      ProfScope ps(PC_MLP_HEADS_BWD, st);
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_density, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 1, W, ws_, st));
+    }
+    for (int i = D - 1; i >= 0; i--) {
+      const LayerInfo& L = s_.layers[i];
+      const Plane& in = i == 0 ? lv.enc_pos : lv.acts[i - 1];
+      ProfScope ps(PC_MLP_WGRAD, st);
+      NERF_TRY(gemm_wgrad(dzs_[D - 1 - i], in, L.in_a, L.in_b ? &lv.enc_pos : nullptr, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
     }
     return 0;
   }
@@ -426,6 +482,7 @@ class TcMlp : public MlpEngine {
   int pos_pitch_ = 0, dir_pitch_ = 0;
   std::vector<Level> levels_;
   Plane dz_[2];
+  std::vector<Plane> dzs_;  // bf16 fused dgrad chain: dZ of trunk layer D-1-j, kept for the wgrad GEMMs
   std::vector<Plane> wp_, wtp_;
   float* ws_ = nullptr;
   float* fconsts_ = nullptr;  // fused forward: biases + head weights, gathered per parameter version
