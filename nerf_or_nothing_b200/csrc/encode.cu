@@ -55,12 +55,21 @@ __device__ __forceinline__ HalfTurns to_half_turns(float mean) {
   v.lo = __fmaf_rn(mean, kInvPiHi, -v.hi) + mean * kInvPiLo;
   return v;
 }
-__device__ __forceinline__ void ipe_pair(HalfTurns v, float var, float scale, float& s, float& c) {
+// `fast`: the output is rounded to a single bf16 plane (2^-9 relative), so after the same exact reduction to [-1, 1]
+// half-turns the SFU sin/cos (absolute error < 5e-7 on [-pi, pi]) replace sincospif's polynomials.
+__device__ __forceinline__ void ipe_pair(HalfTurns v, float var, float scale, float& s, float& c, bool fast = false) {
   const float x = __fmul_rn(0.5f, __fmul_rn(__fmul_rn(var, scale), scale));  // .5*var*4^f, the reference's rounding
   if (x > 87.f) { s = 0.f; c = 0.f; return; }                               // exp(-x) < 1.2e-38: below fp32 normals
   const float e = exp2f(-1.4426950216293335f * x);
   float s0, c0;
-  sincospif(v.hi * scale, &s0, &c0);  // exact scaling; sin/cos(pi * a)
+  if (fast) {
+    float a = v.hi * scale;            // exact
+    a = a - 2.f * rintf(0.5f * a);     // exact: a mod 2 in [-1, 1]
+    s0 = __sinf(3.1415927410125732f * a);
+    c0 = __cosf(3.1415927410125732f * a);
+  } else {
+    sincospif(v.hi * scale, &s0, &c0);  // exact scaling; sin/cos(pi * a)
+  }
   const float d = 3.1415927410125732f * (v.lo * scale);
   const float q = fmaf(-0.5f * d, d, 1.0f);
   s = e * fmaf(d, c0, s0 * q);
@@ -107,12 +116,13 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
       g.cx = in1[m * 3]; g.cy = in1[m * 3 + 1]; g.cz = in1[m * 3 + 2];
     }
     const HalfTurns hx = to_half_turns(g.mx), hy = to_half_turns(g.my), hz = to_half_turns(g.mz);
+    const bool fast = enc_f32 == nullptr && lo == nullptr;  // single bf16 plane out
     for (int f = fl; f < deg; f += kFreqLanes) {
       const float scale = (float)(1u << f);  // .cu:196
       float* e = tile + ls * P + f * 6;
-      ipe_pair(hx, g.cx, scale, e[0], e[3]);
-      ipe_pair(hy, g.cy, scale, e[1], e[4]);
-      ipe_pair(hz, g.cz, scale, e[2], e[5]);
+      ipe_pair(hx, g.cx, scale, e[0], e[3], fast);
+      ipe_pair(hy, g.cy, scale, e[1], e[4], fast);
+      ipe_pair(hz, g.cz, scale, e[2], e[5], fast);
     }
   }
   __syncthreads();
@@ -127,23 +137,21 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
       for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = tile[i];
     }
   }
-  if (hi) {  // bf16 split planes: x ~= hi + lo  (lo optional)
-    for (int i = threadIdx.x * 2; i < n; i += blockDim.x * 2) {
-      const int row = i / P, col = i % P;  // P even, so (col, col+1) stay in one row
-      const float a = tile[i], b = tile[i + 1];
-      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-      const long off = (m0 + row) * pitch_h + col;
-      *reinterpret_cast<__nv_bfloat162*>(hi + off) = __nv_bfloat162(ah, bh);
-      if (lo)
-        *reinterpret_cast<__nv_bfloat162*>(lo + off) =
-            __nv_bfloat162(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
-    }
-    // zero the K padding columns [P, pitch_h) once per row so padded K-blocks contribute nothing
-    const int padc = pitch_h - P;
-    for (int i = threadIdx.x; i < rows * padc; i += blockDim.x) {
-      const long off = (m0 + i / padc) * pitch_h + P + i % padc;
-      hi[off] = __float2bfloat16_rn(0.f);
-      if (lo) lo[off] = __float2bfloat16_rn(0.f);
+  if (hi) {  // bf16 split planes: x ~= hi + lo  (lo optional).  One warp per row: conflict-free float2 reads, 128-byte stores,
+             // the zero K padding [P, pitch_h) in the same sweep, no integer division
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int row = warp; row < rows; row += n_warps) {
+      const float* trow = tile + row * P;
+      const long off0 = (m0 + row) * pitch_h;
+      for (int col = lane * 2; col < pitch_h; col += 64) {
+        float a = 0.f, b = 0.f;
+        if (col < P) { const float2 v = *reinterpret_cast<const float2*>(trow + col); a = v.x; b = v.y; }  // P even
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        *reinterpret_cast<__nv_bfloat162*>(hi + off0 + col) = __nv_bfloat162(ah, bh);
+        if (lo)
+          *reinterpret_cast<__nv_bfloat162*>(lo + off0 + col) =
+              __nv_bfloat162(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+      }
     }
   }
 }
