@@ -249,30 +249,37 @@ def ours_arm(args):
 
     for i in range(args.warmup):
         dev_step(i)
-    model.set_profiling(True)
-    sync_all()
+
+    def timed_region(profile):
+        """EXACTLY args.steps steps between barriers; device time from CUDA events on the library's stream, max over ranks."""
+        model.set_profiling(profile)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launch_count()
+        t0 = time.time()
+        e0.record(stream)
+        for i in range(args.steps):
+            dev_step(i)
+        e1.record(stream)
+        model.synchronize()
+        t1 = time.time()
+        sync_all()
+        tt = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / args.steps, model.launch_count() - l0, t0, t1
+
     clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = model.launch_count()
-    t0 = time.time()
-    e0.record(stream)
-    for i in range(args.steps):
-        dev_step(i)
-    e1.record(stream)
-    model.synchronize()
-    t1 = time.time()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
-    launches = model.launch_count() - l0
+    # region 1: the headline `value` — nothing but the step's own kernels on the stream
+    ms_step, launches, t0, t1 = timed_region(False)
+    # region 2: the same K steps again with the in-stream CUDA events of the per-kernel profile (two event records per
+    # kernel family instance perturb the stream a little, so they stay out of the headline region)
+    ms_step_prof, _, _, t1 = timed_region(True)
     clk = clocks.stop(t0, t1)
     prof = model.read_profile()
     model.set_profiling(False)
-    tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_step = float(tt.item()) / args.steps
     value = world * R / (ms_step / 1e3)
 
     # e2e: host arrays in, loss out, every step
@@ -343,7 +350,7 @@ def ours_arm(args):
                 "peak": tc_peak if tk["unit"] == "TFLOP/s" else hbm_peak, "unit": tk["unit"], "frac": tk["frac"],
                 "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(tk["ms_per_step"] / max(1.0, tk["launches_per_step"]), 5),
-                "share_of_step": round(tk["ms_per_step"] / ms_step, 4)}
+                "share_of_step": round(tk["ms_per_step"] / ms_step_prof, 4)}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -362,6 +369,8 @@ def ours_arm(args):
         "resident_dataset": {"value": resident_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
                              "note": "nerf_mipnerf_train_step_dataset: batch drawn and gathered on the device"},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": kernels,
+        "profile_region": {"ms_per_step": round(ms_step_prof, 4),
+                           "note": "per-kernel times come from a second region of the same K steps with in-stream CUDA events"},
         "cpu_baseline": cpu_baseline, "loss_last_step": loss,
     }
     print(json.dumps(out))
