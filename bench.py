@@ -190,7 +190,7 @@ def reference_arm(args):
     ms = 1e3 * float(np.mean(t))
     value = n / (ms / 1e3)
     sample = f"{n} of {RAYS_PER_GPU} rays per step (same config), gradient + Adam, fp32"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -373,7 +373,7 @@ def ours_arm(args):
                            "note": "per-kernel times come from a second region of the same K steps with in-stream CUDA events"},
         "cpu_baseline": cpu_baseline, "loss_last_step": loss,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,7 +439,7 @@ def render_arm(args):
         work, n_params = algorithmic_work(n, N_SAMPLES)
         fwd_ms = prof.get("mlp_fwd_gemm", (0, 0))[0] / args.steps
         ach = work["mlp_fwd_gemm"][1] / 1e12 / (fwd_ms / 1e3) if fwd_ms else None
-        print(json.dumps({
+        emit(({
             "metric": "render rays/sec (forward only)", "value": total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
@@ -504,20 +504,39 @@ def sweep_arm(args):
                 return round(nbytes / 1e9 / (t / 1e3), 1) if t > 0 else None
 
             cf, cb = gb("composite_fwd", M * 24 + 2 * R * 32), gb("composite_bwd", M * 36 + 2 * R * 24)
-            print(json.dumps({"sweep": f"{depth}x{width}", "rays": R, "precision": args.precision, "ms_per_step": round(ms, 3),
+            emit(({"sweep": f"{depth}x{width}", "rays": R, "precision": args.precision, "ms_per_step": round(ms, 3),
                               "train_rays_per_s": round(R / (ms / 1e3)), "chunk_launches_composite": prof.get("composite_fwd", (0, 0))[1] / steps,
                               "fwd_tflops": tf("mlp_fwd_gemm", fwd), "dgrad_tflops": tf("mlp_dgrad_gemm", dgr), "wgrad_tflops": tf("mlp_wgrad_gemm", fwd),
                               "tensor_peak_tflops": tc_peak, "composite_fwd_gbs": cf, "composite_bwd_gbs": cb, "hbm_peak_gbs": hbm_peak,
                               "composite_fwd_frac": None if cf is None else round(cf / hbm_peak, 3),
-                              "composite_bwd_frac": None if cb is None else round(cb / hbm_peak, 3), "peak_source": peak_src}), flush=True)
+                              "composite_bwd_frac": None if cb is None else round(cb / hbm_peak, 3), "peak_source": peak_src}))
             model.close(); opt.close()
             del db
             torch.cuda.empty_cache()
         except Exception as e:  # a cell that does not fit is reported, not fatal
-            print(json.dumps({"sweep": f"{depth}x{width}", "rays": R, "error": str(e)[:200]}), flush=True)
+            emit({"sweep": f"{depth}x{width}", "rays": R, "error": str(e)[:200]})
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries the JSON result line(s) and nothing else: libraries that printf to fd 1 (NCCL prints its version banner
+    there) are pointed at stderr for the rest of the process."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
