@@ -220,3 +220,35 @@ def test_fused_dgrad_chain_matches_layered_bf16(monkeypatch):
     print(f"fused vs layered dgrad chain: grad max-norm err {rel_err(g1, g2):.2e}")
     assert np.isfinite(g1).all()
     assert rel_err(g1, g2) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
+def test_fused_kernels_many_tiles_per_cta(precision, monkeypatch):
+    """More row tiles than CTAs (700 rays x 64 samples = 350 tiles / 175 tile pairs on 148 SMs, ragged tail): every CTA of
+    the persistent fused kernels walks several tiles, so the mbarrier phase bookkeeping across tiles is exercised.  Render
+    and a whole gradient step must match the layer-by-layer kernels."""
+    R = 700
+    m, ncfg, ocfg = _model(R, precision, **NET)
+    S = ncfg.n_samples
+    rays, pix, u = batch(R, S)
+    m.set_params(_params_with_biases(ocfg))
+    m.set_pixels(pix)
+    m.set_sampling_uniforms(u)
+    rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    for var in ("NERF_NO_FUSED_FORWARD", "NERF_NO_FUSED_TRAIN_FORWARD", "NERF_NO_FUSED_DGRAD"):
+        monkeypatch.delenv(var, raising=False)
+    rgb1, _, acc1 = m.render(*rargs)
+    m.GetGradient(*rargs, rays["loss_mults"])
+    g1, l1 = m.get_gradients().copy(), m.get_loss()[1]
+    for var in ("NERF_NO_FUSED_FORWARD", "NERF_NO_FUSED_TRAIN_FORWARD", "NERF_NO_FUSED_DGRAD"):
+        monkeypatch.setenv(var, "1")
+    rgb2, _, acc2 = m.render(*rargs)
+    m.GetGradient(*rargs, rays["loss_mults"])
+    g2, l2 = m.get_gradients().copy(), m.get_loss()[1]
+    print(f"{precision}: render rgb diff {np.abs(rgb1 - rgb2).max():.2e}, loss {l1:.8f} vs {l2:.8f}, grad err {rel_err(g1, g2):.2e}")
+    tol = TOL[precision]
+    assert np.isfinite(rgb1).all() and np.isfinite(g1).all()
+    np.testing.assert_allclose(rgb1, rgb2, atol=0.1 * tol)
+    np.testing.assert_allclose(acc1, acc2, atol=0.1 * tol)
+    assert abs(l1 - l2) <= 1e-5 * abs(l2)
+    assert rel_err(g1, g2) <= 2e-3
