@@ -486,9 +486,11 @@ __global__ void k_thin_dgrad_planes(const float* __restrict__ dZ, const float* _
   }
 }
 
-// Thin-head wgrad partials: dW[n, k] = sum_m dz[m, n] x[m, k] over this block's rows.  Each warp walks rows
-// (stride 8 within the block's range), each lane owns 8 consecutive columns (16-byte plane loads), 4 rows in flight;
-// the 8 warps are then summed through shared memory.  part[block][n*K + k], partb[block][n].   K <= 256.
+// Thin-head wgrad partials: dW[n, k] = sum_m dz[m, n] x[m, k] over this block's rows.  Each lane owns 8 consecutive
+// columns (16-byte plane loads); a warp covers 32 / (K/8) rows per load instruction (two rows when K = 128), 4 loads in
+// flight; row groups and the 8 warps are then summed through shuffles / shared memory.  part[block][n*K + k],
+// partb[block][n].   K <= 256, K a multiple of 8.  NN = compile-time head width (1 or 3): no FMAs on absent heads.
+template <int NN>
 __global__ void __launch_bounds__(256)
 k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int ldx,
                             const float* __restrict__ dZ, long M, int N, int K, long chunk, float* __restrict__ part,
@@ -496,25 +498,31 @@ k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
   __shared__ float red[8][3][256 + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long m0 = (long)blockIdx.x * chunk, m1 = min(M, m0 + chunk);
-  const int k = lane * 8;
+  const int lpr = K <= 128 ? 16 : 32;        // lanes per row
+  const int rpw = 32 / lpr;                  // rows per warp-wide load
+  const int sub = lane / lpr;                // which of those rows this lane reads
+  const int k = (lane % lpr) * 8;
   const bool active = k < K;
-  float acc[3][8];
+  float acc[NN][8];
 #pragma unroll
-  for (int n = 0; n < 3; n++)
+  for (int n = 0; n < NN; n++)
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[n][j] = 0.f;
-  float bsum[3] = {0.f, 0.f, 0.f};
-  for (long m = m0 + warp; m < m1; m += 32) {  // rows m, m+8, m+16, m+24 in flight
+  float bsum[NN];
+#pragma unroll
+  for (int n = 0; n < NN; n++) bsum[n] = 0.f;
+  const int step = 8 * rpw;                  // rows consumed by the 8 warps per load slot
+  for (long m = m0 + warp * rpw + sub; m < m1; m += 4 * step) {  // rows m, m+step, m+2 step, m+3 step in flight
     uint4 h[4], l[4];
-    float g[4][3];
+    float g[4][NN];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const long mm = m + 8 * u;
+      const long mm = m + (long)step * u;
       const bool ok = mm < m1;
       h[u] = (ok && active) ? __ldg(reinterpret_cast<const uint4*>(xh + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
       l[u] = (ok && active && xl) ? __ldg(reinterpret_cast<const uint4*>(xl + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int n = 0; n < 3; n++) g[u][n] = (ok && n < N) ? __ldg(dZ + mm * N + n) : 0.f;
+      for (int n = 0; n < NN; n++) g[u][n] = ok ? __ldg(dZ + mm * NN + n) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -526,16 +534,24 @@ k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
         x[2 * q + 1] = __uint_as_float(hw[q] & 0xFFFF0000u) + __uint_as_float(lw[q] & 0xFFFF0000u);
       }
 #pragma unroll
-      for (int n = 0; n < 3; n++) {
+      for (int n = 0; n < NN; n++) {
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[n][j] = fmaf(g[u][n], x[j], acc[n][j]);
         bsum[n] += g[u][n];
       }
     }
   }
+  if (rpw == 2) {  // fold the two row groups of the warp: lane i += lane i + 16
 #pragma unroll
-  for (int n = 0; n < 3; n++)
-    if (n < N && active)
+    for (int n = 0; n < NN; n++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[n][j] += __shfl_down_sync(0xffffffffu, acc[n][j], 16);
+      bsum[n] += __shfl_down_sync(0xffffffffu, bsum[n], 16);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NN; n++)
+    if (active && sub == 0)
 #pragma unroll
       for (int j = 0; j < 8; j++) red[warp][n][k + j] = acc[n][j];
   __syncthreads();
@@ -549,8 +565,7 @@ k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int n = 0; n < 3; n++)
-      if (n < N) red[warp][n][0] = bsum[n];
+    for (int n = 0; n < NN; n++) red[warp][n][0] = bsum[n];
   }
   __syncthreads();
   if (threadIdx.x < N) {
@@ -581,14 +596,56 @@ k_colsum_planes_partial(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16
   }
 }
 
-__global__ void k_reduce_partials_tc(const float* __restrict__ ws, int splits, long stride, int rows, int cols, int ldw,
-                                     float* __restrict__ out, int ldo, int coff) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)rows * cols) return;
-  const int i = (int)(idx / cols), j = (int)(idx % cols);
-  float s = 0.f;
-  for (int z = 0; z < splits; z++) s += ws[(long)z * stride + (long)i * ldw + j];  // fixed order: deterministic
-  out[(long)i * ldo + coff + j] += s;
+// out[i, coff + j] += sum_z ws[z, i, j] in a FIXED order (deterministic, no atomics).  A block is 64 column quads x 4
+// z-groups: thread (q, g) sums the splits z = g, g+4, ... of 4 consecutive columns with 128-bit loads (ldw is a multiple
+// of 4), the four groups meet in shared memory as (g0 + g1) + (g2 + g3).  A second, optional segment reduces the bias
+// partials in the same launch.
+__global__ void __launch_bounds__(256)
+k_reduce_partials_tc(const float* __restrict__ ws, int splits, long stride, int rows, int cols, int ldw, float* __restrict__ out, int ldo,
+                     int coff, const float* __restrict__ ws2, int n2, long stride2, float* __restrict__ out2) {
+  __shared__ float4 red[4][64];
+  const int q = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int c4 = (cols + 3) >> 2;
+  const long n1 = (long)rows * c4;
+  const long idx = (long)blockIdx.x * 64 + q;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = 0, j = 0;
+  if (idx < n1) {
+    i = (int)(idx / c4); j = (int)(idx % c4) * 4;
+    const float* src = ws + (long)i * ldw + j;
+    if ((ldw & 3) == 0 && (stride & 3) == 0) {
+#pragma unroll 4
+      for (int z = g; z < splits; z += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long)z * stride));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    } else {
+      for (int z = g; z < splits; z += 4) {
+        const float* p = src + (long)z * stride;
+        s.x += p[0];
+        if (j + 1 < cols) s.y += p[1];
+        if (j + 2 < cols) s.z += p[2];
+        if (j + 3 < cols) s.w += p[3];
+      }
+    }
+  } else if (idx - n1 < n2) {  // bias segment: one column per thread quad slot
+    const int jb = (int)(idx - n1);
+    for (int z = g; z < splits; z += 4) s.x += ws2[(long)z * stride2 + jb];
+  }
+  red[g][q] = s;
+  __syncthreads();
+  if (g != 0) return;
+  const float4 a = red[0][q], b = red[1][q], c = red[2][q], d = red[3][q];
+  const float4 t = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+  if (idx < n1) {
+    float* o = out + (long)i * ldo + coff + j;
+    o[0] += t.x;
+    if (j + 1 < cols) o[1] += t.y;
+    if (j + 2 < cols) o[2] += t.z;
+    if (j + 3 < cols) o[3] += t.w;
+  } else if (idx - n1 < n2) {
+    out2[idx - n1] += t.x;
+  }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
@@ -762,12 +819,18 @@ int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int
   return 0;
 }
 
-int launch_reduce_partials(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo,
-                           int coff, cudaStream_t st) {
-  const long n = (long)rows * cols;
-  k_reduce_partials_tc<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff);
+int launch_reduce_partials2(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo, int coff,
+                            const float* ws2, int n2, long stride2, float* out2, cudaStream_t st) {
+  const long n = (long)rows * ((cols + 3) / 4) + (ws2 ? n2 : 0);
+  k_reduce_partials_tc<<<(unsigned)cdiv(n, 64), 256, 0, st>>>(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff, ws2, ws2 ? n2 : 0,
+                                                               stride2, out2);
   NERF_CHECK_LAUNCH();
   return 0;
+}
+
+int launch_reduce_partials(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo,
+                           int coff, cudaStream_t st) {
+  return launch_reduce_partials2(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff, nullptr, 0, 0, nullptr, st);
 }
 
 long thin_wgrad_chunk(long M) {  // ~4 blocks per SM, at least 256 rows each
@@ -786,10 +849,11 @@ int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __n
   float* partb = workspace + (size_t)chunks * N * 256;
   for (int k0 = 0; k0 < K; k0 += 256) {  // the kernel covers 256 columns (8 per lane) per pass
     const int kp = K - k0 < 256 ? K - k0 : 256;
-    k_thin_wgrad_planes_partial<<<chunks, 256, 0, st>>>(xh + k0, xl ? xl + k0 : nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    if (N == 1) k_thin_wgrad_planes_partial<1><<<chunks, 256, 0, st>>>(xh + k0, xl ? xl + k0 : nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    else if (N == 3) k_thin_wgrad_planes_partial<3><<<chunks, 256, 0, st>>>(xh + k0, xl ? xl + k0 : nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    else { set_error("thin_wgrad_planes: N=%d unsupported", N); return 100001; }
     NERF_CHECK_LAUNCH();
-    NERF_TRY(launch_reduce_partials(part, chunks, (long)N * kp, N, kp, kp, dW, K, k0, st));
-    if (db && k0 == 0) NERF_TRY(launch_reduce_partials(partb, chunks, N, 1, N, N, db, N, 0, st));
+    NERF_TRY(launch_reduce_partials2(part, chunks, (long)N * kp, N, kp, kp, dW, K, k0, (db && k0 == 0) ? partb : nullptr, N, N, db, st));
   }
   return 0;
 }

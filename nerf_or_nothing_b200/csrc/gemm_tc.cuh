@@ -101,6 +101,9 @@ int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __n
 int launch_colsum_planes(const __nv_bfloat16* h, const __nv_bfloat16* l, int ld, long M, int N, float* db, float* workspace,
                          cudaStream_t st);
 // out[i*ldo + coff + j] += sum_z ws[z*stride + i*ldw + j]
+// the same plus a second segment out2[j] += sum_z ws2[z * stride2 + j] (bias partials) in the same launch
+int launch_reduce_partials2(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo, int coff,
+                            const float* ws2, int n2, long stride2, float* out2, cudaStream_t st);
 int launch_reduce_partials(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo,
                            int coff, cudaStream_t st);
 

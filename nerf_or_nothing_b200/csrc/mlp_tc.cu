@@ -470,8 +470,7 @@ class TcMlp : public MlpEngine {
       float* bias_ws = ws_ + (size_t)splits * N * ldf;
       if (bias_here) { p.bias_out = bias_ws; p.bias_split_stride = N; }
       NERF_TRY(tc_launch(p, true, dim3((unsigned)cdiv(N, 128), (unsigned)cdiv(K, BN), (unsigned)splits), st));
-      NERF_TRY(launch_reduce_partials(ws_, splits, p.split_stride, N, K, ldf, dW, ldw, coff, st));
-      if (bias_here) NERF_TRY(launch_reduce_partials(bias_ws, splits, N, 1, N, N, db, N, 0, st));
+      NERF_TRY(launch_reduce_partials2(ws_, splits, p.split_stride, N, K, ldf, dW, ldw, coff, bias_here ? bias_ws : nullptr, N, N, db, st));
     }
     return 0;
   }
