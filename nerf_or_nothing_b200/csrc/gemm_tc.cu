@@ -399,9 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm_persist(const __grid_co
 
 // ------------------------------------------------------------------------------------------------ plane helpers
 
-__global__ void k_f32_to_planes(const float* __restrict__ src, int sp, long rows, int cols, __nv_bfloat16* __restrict__ hi,
-                                __nv_bfloat16* __restrict__ lo, int dp, int dcols, int transpose, long drows_t) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void f32_to_planes_elem(long idx, const float* __restrict__ src, int sp, long rows, int cols,
+                                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int dp, int dcols,
+                                                   int transpose, long drows_t) {
   if (!transpose) {
     if (idx >= rows * dcols) return;
     const long r = idx / dcols;
@@ -419,6 +419,18 @@ __global__ void k_f32_to_planes(const float* __restrict__ src, int sp, long rows
     hi[c * dp + r] = h;
     if (lo) lo[c * dp + r] = __float2bfloat16_rn(x - __bfloat162float(h));
   }
+}
+
+__global__ void k_f32_to_planes(const float* __restrict__ src, int sp, long rows, int cols, __nv_bfloat16* __restrict__ hi,
+                                __nv_bfloat16* __restrict__ lo, int dp, int dcols, int transpose, long drows_t) {
+  f32_to_planes_elem((long)blockIdx.x * blockDim.x + threadIdx.x, src, sp, rows, cols, hi, lo, dp, dcols, transpose, drows_t);
+}
+
+// every weight plane (and transposed plane) of the network in ONE launch: blockIdx.y = job
+__global__ void k_f32_to_planes_batch(const __grid_constant__ PlaneJobs jobs) {
+  const PlaneJobs::Job& j = jobs.job[blockIdx.y];
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < j.n; idx += (long)gridDim.x * blockDim.x)
+    f32_to_planes_elem(idx, j.src, j.sp, j.rows, j.cols, j.hi, j.lo, j.dp, j.dcols, j.transpose, j.drows_t);
 }
 
 __device__ __forceinline__ float plane_val(const __nv_bfloat16* h, const __nv_bfloat16* l, long i) {
@@ -799,6 +811,30 @@ int launch_f32_to_planes(const float* src, int src_pitch, long rows, int cols, _
   if (n <= 0) return 0;
   k_f32_to_planes<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(src, src_pitch, rows, cols, hi, lo, dst_pitch, dst_cols,
                                                          transpose ? 1 : 0, dst_rows_t);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+// dst[job.dst + i] = src[job.src + i]: the fused kernels' constants (biases, head weights) in one launch
+__global__ void k_gather_f32(const float* __restrict__ src, float* __restrict__ dst, const __grid_constant__ GatherJobs jobs) {
+  const GatherJobs::Job j = jobs.job[blockIdx.x];
+  for (int i = threadIdx.x; i < j.n; i += blockDim.x) dst[j.dst + i] = src[j.src + i];
+}
+
+int launch_gather_f32(const float* src, float* dst, const GatherJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  k_gather_f32<<<jobs.n, 128, 0, st>>>(src, dst, jobs);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_f32_to_planes_batch(const PlaneJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  long nmax = 0;
+  for (int i = 0; i < jobs.n; i++) nmax = jobs.job[i].n > nmax ? jobs.job[i].n : nmax;
+  long bx = cdiv(nmax, 256);
+  if (bx > 64) bx = 64;
+  k_f32_to_planes_batch<<<dim3((unsigned)bx, (unsigned)jobs.n), 256, 0, st>>>(jobs);
   NERF_CHECK_LAUNCH();
   return 0;
 }

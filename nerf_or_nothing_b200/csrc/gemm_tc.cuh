@@ -90,6 +90,21 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]
 int launch_f32_to_planes(const float* src, int src_pitch, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
                          int dst_pitch, int dst_cols, bool transpose, long dst_rows_t, cudaStream_t st);
+// the same conversion for a list of tensors in one launch (all weight planes of the network once per step)
+struct PlaneJobs {
+  struct Job {
+    const float* src; __nv_bfloat16 *hi, *lo;
+    long rows, drows_t, n;  // n = elements written: transpose ? drows_t * dcols : rows * dcols
+    int sp, cols, dp, dcols, transpose;
+  } job[32];
+  int n;
+};
+int launch_f32_to_planes_batch(const PlaneJobs& jobs, cudaStream_t st);
+struct GatherJobs {
+  struct Job { long src; int dst, n; } job[24];
+  int n;
+};
+int launch_gather_f32(const float* src, float* dst, const GatherJobs& jobs, cudaStream_t st);  // dst[job.dst + i] = src[job.src + i]
 // heads on planes (N <= 4)
 int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, const float* W, const float* b,
                            float* Y, long M, int N, int K, cudaStream_t st);

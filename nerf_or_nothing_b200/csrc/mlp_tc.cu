@@ -98,14 +98,23 @@ class TcMlp : public MlpEngine {
   int prepare(const float* params, cudaStream_t st) override {
     ProfScope ps(PC_CAST, st);
     fconsts_dirty_ = true;
+    PlaneJobs jobs;
+    jobs.n = 0;
+    auto add = [&](const float* src, int sp, long rows, int cols, const Plane& d, int dcols, bool transpose, long drows_t) {
+      PlaneJobs::Job& j = jobs.job[jobs.n++];
+      j.src = src; j.sp = sp; j.rows = rows; j.cols = cols; j.hi = d.hi; j.lo = d.lo; j.dp = d.pitch; j.dcols = dcols;
+      j.transpose = transpose ? 1 : 0; j.drows_t = drows_t;
+      j.n = transpose ? drows_t * dcols : rows * dcols;
+    };
     for (int l = 0; l < s_.L; l++) {
       const LayerInfo& L = s_.layers[l];
       if (L.out <= 4) continue;
       const int K = L.in_a + L.in_b;
-      NERF_TRY(launch_f32_to_planes(params + L.w_off, K, L.out, K, wp_[l].hi, wp_[l].lo, wp_[l].pitch, wp_[l].pitch, false, 0, st));
-      if (needs_dgrad(l))  // WT[k, n] = W[n, k] for k < in_a
-        NERF_TRY(launch_f32_to_planes(params + L.w_off, K, L.out, L.in_a, wtp_[l].hi, wtp_[l].lo, wtp_[l].pitch, L.out, true, L.in_a, st));
+      if (jobs.n + 2 > 32) { NERF_TRY(launch_f32_to_planes_batch(jobs, st)); jobs.n = 0; }
+      add(params + L.w_off, K, L.out, K, wp_[l], wp_[l].pitch, false, 0);
+      if (needs_dgrad(l)) add(params + L.w_off, K, L.out, L.in_a, wtp_[l], L.out, true, L.in_a);  // WT[k, n] = W[n, k] for k < in_a
     }
+    NERF_TRY(launch_f32_to_planes_batch(jobs, st));
     return 0;
   }
 
@@ -157,7 +166,7 @@ class TcMlp : public MlpEngine {
   // Rendering: no backward follows, so in bf16 mode the whole net runs as one kernel with the activations kept in
   // tensor memory (mlp_fused.cu) instead of one GEMM launch per layer with the activations written to HBM.
   bool can_fuse_forward() const {
-    return s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 20 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
+    return s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 12 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
            getenv("NERF_NO_FUSED_FORWARD") == nullptr;
   }
 
@@ -178,16 +187,18 @@ class TcMlp : public MlpEngine {
     }
     if (!fconsts_dirty_) return 0;
     ProfScope ps(PC_CAST, st);
+    GatherJobs jobs;
+    jobs.n = 0;
+    auto add = [&](int dst, long src, int n) { jobs.job[jobs.n].dst = dst; jobs.job[jobs.n].src = src; jobs.job[jobs.n].n = n; jobs.n++; };
     for (int s = 0; s <= D; s++) {
       const LayerInfo& L = s_.layers[s < D ? s : D + 1];
-      NERF_CUDA(cudaMemcpyAsync(fconsts_ + s * 256, params + L.b_off, L.out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      add(s * 256, L.b_off, L.out);
     }
     const LayerInfo& Ld = s_.layers[D];
     const LayerInfo& Lr = s_.layers[D + 2];
-    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off, params + Ld.w_off, 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_d_off + 256, params + Ld.b_off, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off, params + Lr.w_off, 3 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    NERF_CUDA(cudaMemcpyAsync(fconsts_ + head_rgb_off + 384, params + Lr.b_off, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    add(head_d_off, Ld.w_off, 256); add(head_d_off + 256, Ld.b_off, 1);
+    add(head_rgb_off, Lr.w_off, 3 * 128); add(head_rgb_off + 384, Lr.b_off, 3);
+    NERF_TRY(launch_gather_f32(params, fconsts_, jobs, st));
     fconsts_dirty_ = false;
     return 0;
   }
