@@ -252,3 +252,24 @@ def test_fused_kernels_many_tiles_per_cta(precision, monkeypatch):
     np.testing.assert_allclose(acc1, acc2, atol=0.1 * tol)
     assert abs(l1 - l2) <= 1e-5 * abs(l2)
     assert rel_err(g1, g2) <= 2e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
+def test_tc_step_is_bitwise_reproducible(precision):
+    """No atomics anywhere on the tensor-core path (wgrad partials and head partials are reduced in a fixed order): the same
+    batch gives bit-identical gradients, loss and rendered pixels on every run."""
+    R = 48
+    m, ncfg, ocfg = _model(R, precision, **NET)
+    S = ncfg.n_samples
+    rays, pix, u = batch(R, S)
+    m.set_pixels(pix)
+    m.set_sampling_uniforms(u)
+    args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"])
+    runs = []
+    for _ in range(3):
+        m.GetGradient(*args)
+        runs.append((m.get_gradients().copy(), m.get_loss()[1], m.render(*args[:5])[0].copy()))
+    for g, l, img in runs[1:]:
+        np.testing.assert_array_equal(g, runs[0][0])
+        assert l == runs[0][1]
+        np.testing.assert_array_equal(img, runs[0][2])
