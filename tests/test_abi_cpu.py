@@ -58,6 +58,11 @@ def test_no_cpu_fallback_without_gpu():
         nb.AcceleratedAdamOptimizer([16, 4])
     with pytest.raises(nb.NerfError, match="no CPU path"):
         nb.AcceleratedGradientCalculator(8)
+    import numpy as np
+    with pytest.raises(nb.NerfError, match="no CPU path"):
+        nb.BinDataset(np.zeros((4, 16), np.float32))        # the resident dataset lives in device memory only
+    with pytest.raises(nb.NerfError):
+        nb.BinDataset("/nonexistent/train_data.bin")         # a missing file is an error, not an empty dataset
     # per-stage entry points refuse too (null pointers are never dereferenced without a device)
     assert nb.lib().nerf_adam_optimizer_step(None, None, None, None, 0.1, 0.9, 0.999, 1.0, 1.0, 4, 0) == 100002
 
