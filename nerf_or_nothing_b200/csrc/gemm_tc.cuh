@@ -86,6 +86,12 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
                                    uint32_t* const* bits_out, cudaStream_t st);
 
+int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfloat16* dz_cond_lo, int dz_cond_pitch,
+                                 const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
+                                 int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
+                                 __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
+                                 cudaStream_t st);
+
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]
 int launch_f32_to_planes(const float* src, int src_pitch, long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,

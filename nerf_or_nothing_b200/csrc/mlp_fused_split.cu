@@ -57,6 +57,7 @@ struct alignas(64) SplitParams {
   int n_consts, head_d_off, head_rgb_off;
   float* raw_density;
   float* raw_rgb;
+  const float* r1;  // dgrad chain: [M] dL/d raw_density (rank-1 term of step 0); bits[] are then READ as ReLU masks
   long long* dbg;  // NERF_FUSED_DBG=1: clock64 stamps of CTA 0's first steps (development aid, normally null)
 };
 
@@ -109,12 +110,31 @@ __device__ __forceinline__ uint32_t split_chunk(const uint32_t (&r)[32], const f
   return mask;
 }
 
+// dgrad chain: one 32-column chunk of dX = dZ W (+ r1 v1^T), masked by the ReLU bits of the layer below, split into hi/lo
+__device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint32_t mask, float r1, const float* v1, uint32_t* hw,
+                                                  uint32_t* lw) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    float x0 = __uint_as_float(r[2 * q]), x1 = __uint_as_float(r[2 * q + 1]);
+    if (v1) { x0 = fmaf(r1, v1[2 * q], x0); x1 = fmaf(r1, v1[2 * q + 1], x1); }
+    x0 = ((mask >> (2 * q)) & 1u) ? x0 : 0.f;
+    x1 = ((mask >> (2 * q + 1)) & 1u) ? x1 : 0.f;
+    hw[q] = pack2s(x0, x1);
+    lw[q] = pack2s(x0 - __uint_as_float(hw[q] << 16), x1 - __uint_as_float(hw[q] & 0xFFFF0000u));
+  }
+}
+
 // One CTA walks 128-row tiles.  A layer is two N-halves with their own accumulator columns: while the MMAs of the second
 // half run, the eight epilogue warps (TMEM lane quarter = warp % 4, 64 of the half's 128 columns each) finish the first
 // half into registers; its hi/lo words are written into ACT — in place — only after the second half's MMAs have read
 // ACT, together with the second half's.
-template <bool TRAIN>
+// MODE 0: inference forward; 1: training forward (activation planes + ReLU bits written); 2: backward dgrad chain (step 0:
+// A = dZ of the condition layer streamed through the ring like an encoding, epilogue = density-head rank-1 term + ReLU
+// mask of the layer below; every step's dZ planes written for the wgrad GEMMs).
+template <int MODE>
 __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
+  constexpr bool TRAIN = MODE != 0;
+  constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready;
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
   if (warp == kEpiWarps) {
     tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
-      for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_pos[q]); prefetch_tmap(&p.map_dir[q]); }
+      for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_pos[q]); if (!DGRAD) prefetch_tmap(&p.map_dir[q]); }
       for (int s = 0; s < p.n_steps; s++)
         for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_w[s][q]); if (TRAIN) prefetch_tmap(&p.map_act[s][q]); }
     }
@@ -255,6 +275,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
       const int row_t = qtr * 32 + lane;         // row within the tile
       const long row = (long)row_w + lane;
       const bool row_ok = row < p.M;
+      const float r1v = (DGRAD && row_ok) ? __ldg(p.r1 + row) : 0.f;
       uint32_t held_h[32], held_l[32];           // first half's words wait here until the second half's MMAs have read ACT
       for (int s = 0; s < p.n_steps; s++) {
         const SplitParams::Step st = p.steps[s];
@@ -284,6 +305,16 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
           const float* head_w = s_const + (st.head == 3 ? p.head_rgb_off : p.head_d_off) + col_t;
           const uint32_t acc = ACC + 128 * h + lane_off + ch * 64;
           uint32_t m0, m1;
+          uint2 mk = make_uint2(0u, 0u);  // DGRAD: ReLU mask words of this thread's 64 columns (requested before the wait)
+          if (DGRAD && row_ok) mk = __ldg(reinterpret_cast<const uint2*>(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5)));
+          const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + col_t : nullptr;
+          auto chunk = [&](const uint32_t (&r)[32], int c, uint32_t* hw_, uint32_t* lw_) -> uint32_t {
+            if (DGRAD) {
+              dgrad_split_chunk(r, c == 0 ? mk.x : mk.y, r1v, v1 ? v1 + c * 32 : nullptr, hw_, lw_);
+              return 0u;
+            }
+            return split_chunk<MODE == 1>(r, bias + c * 32, st.head, head_w + c * 32, head, hw_, lw_);
+          };
           mbar_wait(&acc_full[h], n_full[h] & 1);
           n_full[h]++;
           tc_fence_after_sync();
@@ -302,17 +333,17 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
           if (lane == 0) mbar_arrive(&acc_empty[h]);  // accumulator half in registers: its next MMAs may start
           if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 3] = clock64();
           if (!last_half) {
-            m0 = split_chunk<TRAIN>(r0, bias, st.head, head_w, head, held_h, held_l);
+            m0 = chunk(r0, 0, held_h, held_l);
             ship(col_t, held_h, held_l);
-            m1 = split_chunk<TRAIN>(r1, bias + 32, st.head, head_w + 32, head, held_h + 16, held_l + 16);
+            m1 = chunk(r1, 1, held_h + 16, held_l + 16);
             ship(col_t + 32, held_h + 16, held_l + 16);
           } else {
             uint32_t hw[16], lw[16];
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
-            m0 = split_chunk<TRAIN>(r0, bias, st.head, head_w, head, hw, lw);
+            m0 = chunk(r0, 0, hw, lw);
             if (st.produces) { tmem_st_16(ACT_HI + out, hw); tmem_st_16(ACT_LO + out, lw); }
             ship(col_t, hw, lw);
-            m1 = split_chunk<TRAIN>(r1, bias + 32, st.head, head_w + 32, head, hw, lw);
+            m1 = chunk(r1, 1, hw, lw);
             if (st.produces) {
               tmem_st_16(ACT_HI + out + 16, hw); tmem_st_16(ACT_LO + out + 16, lw);
               tmem_st_wait();
@@ -322,10 +353,10 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
             }
             ship(col_t + 32, hw, lw);
           }
-          if (TRAIN && row_ok) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5)) = make_uint2(m0, m1);
+          if (MODE == 1 && row_ok) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5)) = make_uint2(m0, m1);
           if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 4] = clock64();
         }
-        if (st.head) {  // the column halves of a row meet in shared memory
+        if (!DGRAD && st.head) {  // the column halves of a row meet in shared memory
           if (ch == 1) { head_part[row_t][0] = head[0]; head_part[row_t][1] = head[1]; head_part[row_t][2] = head[2]; }
           named_barrier_sync(1 + qtr, 64);
           if (ch == 0 && row_ok) {
@@ -368,8 +399,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   static int sms = 148;
   const size_t smem = (size_t)(train ? kNSTrain : kNSInfer) * kStageB + (train ? kEpiWarps * kSlotB : 0) + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_mlp_fused_split<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_split<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    attr_err = cudaFuncSetAttribute(k_mlp_fused_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -411,8 +442,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   }
   const int tiles = (int)cdiv(M, 128);
   const int grid = tiles < sms ? tiles : sms;
-  if (train) k_mlp_fused_split<true><<<grid, kThreadsS, smem, st>>>(p);
-  else k_mlp_fused_split<false><<<grid, kThreadsS, smem, st>>>(p);
+  if (train) k_mlp_fused_split<1><<<grid, kThreadsS, smem, st>>>(p);
+  else k_mlp_fused_split<0><<<grid, kThreadsS, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   if (p.dbg) {
     long long h[32 * 8];
@@ -424,6 +455,52 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
       fprintf(stderr, "  (%d,%d): %7lld %7lld | %7lld %7lld %7lld\n", i / 2, i % 2, h[i * 8] - t0, h[i * 8 + 1] - t0, h[i * 8 + 2] - t0,
               h[i * 8 + 3] - t0, h[i * 8 + 4] - t0);
   }
+  return 0;
+}
+
+
+// The backward dgrad chain of the trunk in the fp32-accurate mode (see launch_mlp_fused_dgrad in mlp_fused.cu for the step
+// order): dz_cond hi/lo [M, Wc]; wt_hi/lo[0] = W_cond^T [W, Wc], wt[i] = W_{D-i}^T [W, W]; dz_out[i] = dZ of trunk layer D-1-i.
+int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfloat16* dz_cond_lo, int dz_cond_pitch,
+                                 const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
+                                 int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
+                                 __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
+                                 cudaStream_t st) {
+  if (W != 256 || Wc != 128 || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  static int sms = 148;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(k_mlp_fused_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
+  const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
+  if (smem > 218 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
+  SplitParams p;
+  memset(&p, 0, sizeof(p));
+  NERF_TRY(tc_make_tmap(&p.map_pos[0], dz_cond_hi, M, 128, dz_cond_pitch, 128));  // A of step 0, streamed like an encoding
+  NERF_TRY(tc_make_tmap(&p.map_pos[1], dz_cond_lo, M, 128, dz_cond_pitch, 128));
+  for (int s = 0; s < D; s++) {
+    NERF_TRY(tc_make_tmap(&p.map_w[s][0], wt_hi[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_w[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
+    NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], dz_out_hi[s], M, W, W, 32, 32));
+    NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
+    p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
+    SplitParams::Step& stp = p.steps[s];
+    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
+    else { stp.n_act_kb = 4; stp.enc_kind = 0; stp.n_enc_kb = 0; }
+    stp.n_halves = 2;
+    stp.produces = s < D - 1 ? 1 : 0;
+    stp.head = 0; stp.bias_off = 0;
+  }
+  p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
+  p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
+  const int tiles = (int)cdiv(M, 128);
+  k_mlp_fused_split<2><<<tiles < sms ? tiles : sms, kThreadsS, smem, st>>>(p);
+  NERF_CHECK_LAUNCH();
   return 0;
 }
 

@@ -245,7 +245,10 @@ class TcMlp : public MlpEngine {
       NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st));
       NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st));
     }
-    if (!split_ && can_fuse_forward() && getenv("NERF_NO_FUSED_DGRAD") == nullptr)
+    // bf16: fused chain by default.  fp32-accurate mode: the fused chain (k_mlp_fused_split<2>) moves half the bytes but is
+    // bound by its three MMA passes + epilogue tail and measures the same 3.4 ms as the HBM-bound per-layer launches, so it is
+    // opt-in (NERF_FUSED_DGRAD_SPLIT=1) and the per-layer path, which needs no extra dZ planes, stays the default.
+    if (can_fuse_forward() && getenv("NERF_NO_FUSED_DGRAD") == nullptr && (!split_ || getenv("NERF_FUSED_DGRAD_SPLIT") != nullptr))
       return backward_fused_chain(level, M, params, grads, d_raw_density, *cur, st);
     for (int i = C - 1; i >= 0; i--) {
       const int l = D + 1 + i;
@@ -286,7 +289,7 @@ class TcMlp : public MlpEngine {
     return 0;
   }
 
-  // bf16 mode: the whole dgrad chain (condition layer -> trunk layers D-1..1) is ONE kernel that keeps dZ in tensor
+  // The whole dgrad chain (condition layer -> trunk layers D-1..1) is ONE kernel that keeps dZ in tensor
   // memory between layers and writes every layer's dZ once; the wgrad GEMMs then read those planes.
   int backward_fused_chain(int level, long M, const float* params, float* grads, const float* d_raw_density, const Plane& dz_cond,
                            cudaStream_t st) {
@@ -309,8 +312,16 @@ class TcMlp : public MlpEngine {
     }
     {
       ProfScope ps(PC_MLP_DGRAD, st);
-      NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
-                                      d_raw_density, dz_out.data(), masks.data(), st));
+      if (split_) {
+        std::vector<const __nv_bfloat16*> wt_lo(D);
+        std::vector<__nv_bfloat16*> dz_lo(D);
+        for (int j = 0; j < D; j++) { wt_lo[j] = wtp_[j == 0 ? D + 1 : D - j].lo; dz_lo[j] = dzs_[j].lo; }
+        NERF_TRY(launch_mlp_fused_dgrad_split(dz_cond.hi, dz_cond.lo, dz_cond.pitch, wt.data(), wt_lo.data(), wt_pitch.data(), D, W, s_.Wc, M,
+                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), st));
+      } else {
+        NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
+                                        d_raw_density, dz_out.data(), masks.data(), st));
+      }
     }
     {  // condition layer
       const LayerInfo& L = s_.layers[D + 1];

@@ -198,12 +198,13 @@ def test_fused_training_forward_matches_layered(precision, monkeypatch):
     assert rel_err(g1, g2) <= 1e-3
 
 
-def test_fused_dgrad_chain_matches_layered_bf16(monkeypatch):
-    """bf16 mode: the backward dgrad chain of the trunk is one kernel (dZ resident in tensor memory between layers, each
-    layer's dZ written once for the wgrad GEMMs).  Same operands and the same bf16 roundings between layers as the
-    per-layer dgrad launches, so the parameter gradients agree to accumulation-order noise."""
+@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
+def test_fused_dgrad_chain_matches_layered(precision, monkeypatch):
+    """The backward dgrad chain of the trunk is one kernel (dZ resident in tensor memory between layers, each layer's dZ
+    written once for the wgrad GEMMs).  Same operands, the same ReLU bit masks and the same roundings between layers as
+    the per-layer dgrad launches, so the parameter gradients agree to accumulation-order noise."""
     R = 24
-    m, ncfg, ocfg = _model(R, "bf16", **NET)
+    m, ncfg, ocfg = _model(R, precision, **NET)
     S = ncfg.n_samples
     rays, pix, u = batch(R, S)
     m.set_params(_params_with_biases(ocfg))
@@ -211,13 +212,15 @@ def test_fused_dgrad_chain_matches_layered_bf16(monkeypatch):
     m.set_sampling_uniforms(u)
     args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"])
     monkeypatch.delenv("NERF_NO_FUSED_DGRAD", raising=False)
+    monkeypatch.setenv("NERF_FUSED_DGRAD_SPLIT", "1")   # the fp32-accurate chain is opt-in (same speed as per-layer)
     m.GetGradient(*args)
     g1 = m.get_gradients().copy()
     monkeypatch.setenv("NERF_NO_FUSED_DGRAD", "1")
     m.GetGradient(*args)
     g2 = m.get_gradients().copy()
     monkeypatch.delenv("NERF_NO_FUSED_DGRAD")
-    print(f"fused vs layered dgrad chain: grad max-norm err {rel_err(g1, g2):.2e}")
+    monkeypatch.delenv("NERF_FUSED_DGRAD_SPLIT")
+    print(f"{precision}: fused vs layered dgrad chain: grad max-norm err {rel_err(g1, g2):.2e}")
     assert np.isfinite(g1).all()
     assert rel_err(g1, g2) <= 1e-5
 
