@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
-  const int stage_bytes = kABytes + BN * 128;
+  // one ring stage = one 64-sample k-block: the dZ tile and the X tile of every plane, each fetched ONCE and shared by the
+  // passes of the split product (hi*hi, hi*lo, lo*hi): [A plane 0][A plane 1][B plane 0][B plane 1]
+  const int np = p.n_pass > 1 ? 2 : 1;
+  const int b_bytes = BN * 128;
+  const int stage_bytes = np * (kABytes + b_bytes);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ones = smem + (size_t)p.n_stages * stage_bytes;  // 8 KB of bf16 1.0
 
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
   long red1 = red0 + p.split_len;
   if (red1 > p.red_len) red1 = p.red_len;
   const long nblk = red1 > red0 ? (red1 - red0 + 63) / 64 : 0;
-  const int n_kb = (int)nblk * p.n_pass;
+  const int n_kb = (int)nblk;
   const bool want_bias = p.bias_out != nullptr && blockIdx.y == 0;
 
   if (threadIdx.x == 0) {
@@ -90,15 +94,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
         const uint32_t ph = (i / p.n_stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + kABytes;
+        uint8_t* b_dst = a_dst + np * kABytes;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-        const int blk = i / p.n_pass, ps = i % p.n_pass;
-        const int r = (int)(red0 + (long)blk * 64);
-        const CUtensorMap* ma = &p.maps[p.pass_a[ps]];
-        const CUtensorMap* mb = &p.maps[p.pass_b[ps]];
-        tma_load_2d(a_dst, ma, p.a_col0 + (int)row0, r, &full_bar[s]);
-        tma_load_2d(a_dst + 8192, ma, p.a_col0 + (int)row0 + 64, r, &full_bar[s]);
-        for (int c = 0; c < BN; c += 64) tma_load_2d(b_dst + (c >> 6) * 8192, mb, col0 + c, r, &full_bar[s]);
+        const int r = (int)(red0 + (long)i * 64);
+        for (int pl = 0; pl < np; pl++) {  // maps 0/1 = dZ hi/lo, 4/5 = X hi/lo
+          tma_load_2d(a_dst + pl * kABytes, &p.maps[pl], p.a_col0 + (int)row0, r, &full_bar[s]);
+          tma_load_2d(a_dst + pl * kABytes + 8192, &p.maps[pl], p.a_col0 + (int)row0 + 64, r, &full_bar[s]);
+          for (int c = 0; c < BN; c += 64) tma_load_2d(b_dst + pl * b_bytes + (c >> 6) * 8192, &p.maps[4 + pl], col0 + c, r, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 5) {
@@ -108,27 +111,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
       const uint32_t idesc_bias = make_idesc_bf16(128, 16, true, true);
       const uint64_t desc0 = make_smem_desc(0, 8192, 1024);  // + (shared address >> 4)
       const uint32_t ones_base = smem_u32(ones), smem_base = smem_u32(smem);
-      bool bias_started = false;
       for (int i = 0; i < n_kb; i++) {
         const int s = i % p.n_stages;
         const uint32_t ph = (i / p.n_stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after_sync();
         const uint32_t a_base = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
-        const uint64_t da = desc0 + (a_base >> 4), db = desc0 + ((a_base + kABytes) >> 4);
-        const bool bias_pass = want_bias && p.pass_b[i % p.n_pass] == 4;  // passes whose B plane is `hi`: (hi,hi) and (lo,hi) -> sum(hi + lo)
+        const uint32_t b_base = a_base + (uint32_t)(np * kABytes);
         if (leader) {
+          for (int q = 0; q < p.n_pass; q++) {  // (A plane, B plane) of each term of the split product
+            const uint64_t da = desc0 + ((a_base + (uint32_t)p.pass_a[q] * kABytes) >> 4);
+            const uint64_t db = desc0 + ((b_base + (uint32_t)(p.pass_b[q] - 4) * (uint32_t)b_bytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; k++)  // 16 reduction rows per MMA = 2 KB of each 64-column box
-            umma_bf16(tmem_base, da + k * 128, db + k * 128, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          if (bias_pass) {
+            for (int k = 0; k < 4; k++)  // 16 reduction rows per MMA = 2 KB of each 64-column box
+              umma_bf16(tmem_base, da + k * 128, db + k * 128, idesc, (i > 0 || q > 0 || k > 0) ? 1u : 0u);
+          }
+          if (want_bias) {  // colsum(dZ hi + dZ lo): every dZ plane once against the tile of ones
             const uint64_t d1 = desc0 + (ones_base >> 4);
+            for (int pl = 0; pl < np; pl++) {
+              const uint64_t da = desc0 + ((a_base + (uint32_t)pl * kABytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; k++) umma_bf16(tmem_base + 256, da + k * 128, d1 + k * 128, idesc_bias, (bias_started || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; k++) umma_bf16(tmem_base + 256, da + k * 128, d1 + k * 128, idesc_bias, (i > 0 || pl > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);
         }
-        if (bias_pass) bias_started = true;
       }
       if (leader) umma_commit(&done_bar);
       __syncwarp();
@@ -799,7 +806,11 @@ int tc_launch(const TcParams& p_in, bool mn_major, dim3 grid, cudaStream_t st) {
     NERF_CHECK_LAUNCH();
     return 0;
   }
-  const size_t smem = (size_t)tc_smem_bytes(p.BN, p.n_stages, mn_major);
+  const int np = p.n_pass > 1 ? 2 : 1;
+  const int stage_bytes = np * (kABytes + p.BN * 128);
+  int stages = (220 * 1024 - 1024 - 8192) / stage_bytes;
+  p.n_stages = stages > kMaxStages ? kMaxStages : (stages < 1 ? 1 : stages);
+  const size_t smem = (size_t)p.n_stages * stage_bytes + 8192 + 1024;
   k_tc_wgrad<<<grid, kThreads, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
