@@ -521,6 +521,83 @@ def sweep_arm(args):
             emit({"sweep": f"{depth}x{width}", "rays": R, "error": str(e)[:200]})
 
 
+def compositing_arm(args):
+    """The two HBM-bound per-ray kernels alone, against the copy-bandwidth roofline (north_star: >= 70 % of HBM peak):
+    `nerf_volumetric_rendering_async` / `nerf_volumetric_rendering_gradient_async` launched back to back on one stream,
+    S = 128 samples per ray, R rays per launch, inputs larger than the 126 MB L2 (R*S*20 B >= 168 MB), timed with CUDA events
+    on that stream.  Two forms: `activated` = the reference kernels' contract (.cu:318-344, 362-402: sigma and rgb in),
+    `raw` = what the training step runs (softplus / sigmoid and their derivatives fused).  Algorithmic bytes: SURVEY §8(d),
+    fwd 24 B/sample + 32 B/ray, bwd 36 B/sample + 24 B/ray.  One JSON line."""
+    import ctypes as C
+
+    import torch
+
+    import nerf_or_nothing_b200 as nb
+
+    torch.cuda.set_device(0)
+    hbm_peak, _, peak_src = peaks()
+    S = N_SAMPLES
+    lib = nb.lib()
+    st = torch.cuda.Stream()
+    sp = C.c_void_p(st.cuda_stream)
+    P = lambda x: C.c_void_p(x.data_ptr())
+    cells = []
+    launches = 0
+    clocks = ClockSampler(0)
+    clocks.start()
+    time.sleep(0.25)
+    t_begin = time.time()
+    for R in (65536, 262144):
+        gen = torch.Generator(device="cuda").manual_seed(R)
+        raw_rgb = torch.randn(R, S, 3, device="cuda", generator=gen) * 2.0
+        raw_den = torch.randn(R, S, device="cuda", generator=gen) * 3.0 - 1.0
+        act_rgb, act_den = torch.sigmoid(raw_rgb), torch.nn.functional.softplus(raw_den)
+        t = torch.sort(torch.rand(R, S + 1, device="cuda", generator=gen) * 4.0 + 2.0, dim=1).values.contiguous()
+        d = torch.randn(R, 3, device="cuda", generator=gen)
+        g = torch.randn(R, 3, device="cuda", generator=gen)
+        comp, depth, acc, w = (torch.empty(R, 3, device="cuda"), torch.empty(R, device="cuda"), torch.empty(R, device="cuda"),
+                               torch.empty(R, S, device="cuda"))
+        d_rgb, d_den = torch.empty(R, S, 3, device="cuda"), torch.empty(R, S, device="cuda")
+        torch.cuda.synchronize()
+        for form, rgb, den, raw in (("activated", act_rgb, act_den, 0), ("raw", raw_rgb, raw_den, 1)):
+            def fwd():
+                nb.check(lib.nerf_volumetric_rendering_async(P(rgb), P(den), P(t), P(d), P(comp), P(depth), P(acc), P(w), R, S, 1,
+                                                             raw, 0.0, 0.0, sp))
+
+            def bwd():
+                nb.check(lib.nerf_volumetric_rendering_gradient_async(P(g), P(rgb), P(den), P(t), P(d), P(d_rgb), P(d_den), R, S, 1, 0,
+                                                                      raw, 0.0, 0.0, sp))
+
+            for name, fn, nbytes in (("composite_fwd", fwd, R * S * 24 + R * 32), ("composite_bwd", bwd, R * S * 36 + R * 24)):
+                for _ in range(args.warmup):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                st.synchronize()
+                e0.record(st)
+                for _ in range(args.steps):
+                    fn()
+                e1.record(st)
+                st.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / args.steps
+                launches += args.steps
+                gbs = nbytes / 1e9 / (us / 1e6)
+                cells.append({"kernel": name, "form": form, "rays": R, "samples": S, "us_per_launch": round(us, 2),
+                              "algorithmic_bytes": nbytes, "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / hbm_peak, 4)})
+        assert torch.isfinite(comp).all() and torch.isfinite(d_den).all()
+        del raw_rgb, raw_den, act_rgb, act_den, t, w, d_rgb, d_den
+        torch.cuda.empty_cache()
+    clk = clocks.stop(t_begin, time.time())
+    head = [c for c in cells if c["rays"] == 262144 and c["form"] == "raw"]
+    worst = min(head, key=lambda c: c["frac"])
+    emit({"metric": "compositing fwd/bwd GB/s vs HBM roofline", "value": worst["achieved"], "unit": "GB/s", "n_gpus": 1,
+          "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "configs[4] compositing cells: S=128, 65536 / 262144 rays per launch, inputs larger than L2 (no flush)",
+                     "value_is": "the slower of fwd/bwd in the form the training step runs (raw), 262144 rays"},
+          "roofline": {"kernel": worst["kernel"], "bound": "hbm", "achieved": worst["achieved"], "peak": hbm_peak, "unit": "GB/s",
+                       "frac": worst["frac"], "traffic": None, "peak_source": peak_src},
+          "gpu_launches": launches, "clocks": clk, "cells": cells})
+
+
 _REAL_STDOUT = None
 
 
@@ -548,7 +625,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("NERF_BENCH_PRECISION", "fp32_tc"), choices=["fp32", "fp32_tc", "bf16"],
                     help="fp32_tc (default): fp32-accurate bf16x3 split on tcgen05; fp32: CUDA-core FFMA; bf16: configs[2] mode")
-    ap.add_argument("--mode", default="train", choices=["train", "render", "sweep"], help="render: configs[3], forward only; sweep: configs[4]")
+    ap.add_argument("--mode", default="train", choices=["train", "render", "sweep", "compositing"],
+                    help="render: configs[3], forward only; sweep: configs[4]; compositing: the per-ray kernels alone vs the HBM roofline")
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -559,6 +637,8 @@ def main():
         render_arm(args)
     elif args.mode == "sweep":
         sweep_arm(args)
+    elif args.mode == "compositing":
+        compositing_arm(args)
     else:
         ours_arm(args)
 

@@ -228,6 +228,21 @@ int nerf_volumetric_rendering_gradient(const float* comp_rgb_grad3, const float*
                                        const float* density, const float* t_vals,
                                        const float* directions3, float* color_grad3, float* density_grad,
                                        int R, int S, int white_bkgd, int last_sample_mode);
+/* The two compositing stages as the model runs them: enqueued on `stream` (a cudaStream_t; NULL = default stream)
+ * WITHOUT a synchronize, optionally with the output activations of SN/MipNerfModel.cs:81-83 fused in
+ * (raw != 0: density = softplus(raw + density_bias), rgb = sigmoid(raw)(1 + 2 rgb_padding) - rgb_padding, and the
+ * gradients come out w.r.t. the RAW head outputs, SN/MipNerfModel.cs:184-189).  Back-to-back launches on one
+ * stream are how bench.py measures these kernels against the HBM roofline. */
+int nerf_volumetric_rendering_async(const float* rgb3, const float* density, const float* t_vals,
+                                    const float* directions3, float* comp_rgb3, float* depth, float* acc,
+                                    float* weights, int R, int S, int white_bkgd, int raw, float density_bias,
+                                    float rgb_padding, void* stream);
+int nerf_volumetric_rendering_gradient_async(const float* comp_rgb_grad3, const float* rgb3,
+                                             const float* density, const float* t_vals,
+                                             const float* directions3, float* color_grad3,
+                                             float* density_grad, int R, int S, int white_bkgd,
+                                             int last_sample_mode, int raw, float density_bias,
+                                             float rgb_padding, void* stream);
 /* .cu:403-416 */
 int nerf_adam_optimizer_step(float* variables, const float* gradients, float* m, float* v, float lr,
                              float beta1, float beta2, float inv_1_minus_beta1_pow,

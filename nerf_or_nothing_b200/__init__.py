@@ -109,6 +109,8 @@ _SIGNATURES = {
     "nerf_get_output_gradient": [_VP, _VP, _VP, _VP, _F, _F, _I],
     "nerf_volumetric_rendering_gradient": [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I],
     "nerf_adam_optimizer_step": [_VP, _VP, _VP, _VP, _F, _F, _F, _F, _F, _L, _I],
+    "nerf_volumetric_rendering_async": [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _F, _VP],
+    "nerf_volumetric_rendering_gradient_async": [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _F, _F, _VP],
     "nerf_dataset_create": [_VP, _L, _I, C.POINTER(_VP)],
     "nerf_dataset_load": [C.c_char_p, _I, C.POINTER(_VP)],
     "nerf_dataset_size": [_VP, C.POINTER(_L)],

@@ -1164,6 +1164,22 @@ int nerf_volumetric_rendering_gradient(const float* g, const float* rgb, const f
   NERF_TRY(launch_composite_bwd(g, rgb, density, t, dirs, R, S, white, last_sample_mode, OutputAct{}, d_rgb, d_density, 0));
   STAGE_END();
 }
+int nerf_volumetric_rendering_async(const float* rgb, const float* density, const float* t, const float* dirs, float* comp, float* depth,
+                                    float* acc, float* weights, int R, int S, int white, int raw, float density_bias, float rgb_padding,
+                                    void* stream) {
+  STAGE_BEGIN();
+  OutputAct act; act.raw = raw != 0; act.density_bias = density_bias; act.rgb_padding = rgb_padding;
+  NERF_TRY(launch_composite_fwd(rgb, density, t, dirs, R, S, white, act, comp, depth, acc, weights, (cudaStream_t)stream));
+  return 0;
+}
+int nerf_volumetric_rendering_gradient_async(const float* g, const float* rgb, const float* density, const float* t, const float* dirs,
+                                             float* d_rgb, float* d_density, int R, int S, int white, int last_sample_mode, int raw,
+                                             float density_bias, float rgb_padding, void* stream) {
+  STAGE_BEGIN();
+  OutputAct act; act.raw = raw != 0; act.density_bias = density_bias; act.rgb_padding = rgb_padding;
+  NERF_TRY(launch_composite_bwd(g, rgb, density, t, dirs, R, S, white, last_sample_mode, act, d_rgb, d_density, (cudaStream_t)stream));
+  return 0;
+}
 int nerf_adam_optimizer_step(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float inv1, float inv2,
                              long size, int eps_mode) {
   STAGE_BEGIN();

@@ -4,219 +4,224 @@
 // get_output_gradient (.cu:347-361); semantics: SURVEY Appendix B.4/B.5.
 //
 // HBM-bound.  The reference walks each ray serially in ONE 1024-thread block with lane stride = S floats
-// (fully uncoalesced) and round-trips alpha/T/w caches.  Here: one warp per ray, V = S/32 consecutive
-// samples per lane, 128-bit loads of sigma / rgb / stores of w, t staged through shared memory, the
-// transmittance as a shuffle-based exclusive prefix PRODUCT, the backward as a shuffle-based suffix SUM
-// (dL/dsigma_i = delta_i |d| (T_{i+1} dLdw_i - sum_{j>i} dLdw_j w_j)), alpha/T recomputed instead of cached,
-// and the output activations (softplus / sigmoid, SN/MipNerfModel.cs:81-83) and their derivatives fused.
+// (fully uncoalesced) and round-trips alpha/T/w caches.  Here a ray is owned by LPR = S/8 consecutive lanes of a
+// warp (32/LPR rays per warp), each lane holding 8 consecutive samples: sigma / rgb arrive as 128-bit loads (2 + 6
+// per lane, the lanes of a ray covering its rows contiguously), w / dsigma / drgb leave as 128-bit stores, the
+// transmittance is a shuffle-based segmented exclusive prefix PRODUCT, the backward a segmented suffix SUM
+// (dL/dsigma_i = delta_i |d| (T_{i+1} dLdw_i - sum_{j>i} dLdw_j w_j)), alpha/T are recomputed instead of cached,
+// and the output activations (softplus / sigmoid, SN/MipNerfModel.cs:81-83) and their derivatives are fused.
 // Algorithmic bytes: fwd 24 B/sample + 32 B/ray, bwd 36 B/sample + 24 B/ray.
+//
+// Instruction budget: at 70 % of the measured copy bandwidth the forward pass has ~130 issue slots per sample
+// (148 SMs x 4 schedulers x 32 lanes against 190 G samples/s); the first version spent 156 (one ray per warp with 4
+// samples per lane: ~340 per-thread instructions of scan / reduction / addressing overhead amortised over 4 samples,
+// denormal-safe MUFU wrappers, a shared-memory detour for t).  8 samples per lane, .ftz MUFU forms and direct t loads
+// bring it to ~60.
 #include "kernels.cuh"
 
 namespace nerf {
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = 256;  // 8 warps per block
+constexpr int kV = 8;          // samples per lane
+constexpr unsigned kFull = 0xffffffffu;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
-// These kernels must stay HBM-bound: with libm expf/log1pf/IEEE division the ~7 transcendentals per sample cost more
-// issue slots than the 24-36 bytes per sample cost memory time.  ex2.approx / lg2.approx / rcp.approx keep every
-// quantity within ~4e-7 relative (1e-7 absolute near 0) — far inside the 1e-4 + 1e-6 parity tolerance.
-__device__ __forceinline__ float fast_sigmoid(float x) {
-  const float e = __expf(-fabsf(x));
-  const float r = __fdividef(1.f, 1.f + e);
-  return x >= 0.f ? r : e * r;
+// These kernels must stay HBM-bound: with libm expf/log1pf/IEEE division the ~9 transcendentals per sample cost more
+// issue slots than the 24-36 bytes per sample cost memory time.  The .ftz MUFU forms are ONE instruction each (the
+// non-ftz intrinsics wrap every MUFU in a denormal pre/post-scale) and keep every quantity within ~4e-7 relative
+// (1e-7 absolute near 0) — far inside the 1e-4 + 1e-6 parity tolerance.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1/(1+2^(-x log2 e)): the exponential saturates to +inf / 0 at the ends and rcp(inf) = 0, so no branch is needed
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-kLog2e * x)); }
+__device__ __forceinline__ float fast_softplus(float x) {
+  return fmaf(kLn2, lg2_ftz(1.f + ex2_ftz(-kLog2e * fabsf(x))), fmaxf(x, 0.f));
 }
-__device__ __forceinline__ float fast_softplus(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
 
-template <int V> struct VecLoad;
-template <> struct VecLoad<1> {
-  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
-  static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
-};
-template <> struct VecLoad<2> {
-  static __device__ __forceinline__ void ld(const float* p, float* v) { const float2 x = __ldg(reinterpret_cast<const float2*>(p)); v[0] = x.x; v[1] = x.y; }
-  static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
-};
-template <> struct VecLoad<4> {
-  static __device__ __forceinline__ void ld(const float* p, float* v) { const float4 x = __ldg(reinterpret_cast<const float4*>(p)); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
-  static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
-};
-// n consecutive floats (n = V or 3V) with the widest aligned vector op
-template <int N> __device__ __forceinline__ void load_n(const float* p, float* v) {
-  if constexpr (N % 4 == 0) { for (int i = 0; i < N; i += 4) VecLoad<4>::ld(p + i, v + i); }
-  else if constexpr (N % 2 == 0) { for (int i = 0; i < N; i += 2) VecLoad<2>::ld(p + i, v + i); }
-  else { for (int i = 0; i < N; i++) VecLoad<1>::ld(p + i, v + i); }
+template <int N> __device__ __forceinline__ void load_n(const float* p, float* v) {  // N % 4 == 0, 16-byte aligned
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p + i));
+    v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+  }
 }
 template <int N> __device__ __forceinline__ void store_n(float* p, const float* v) {
-  if constexpr (N % 4 == 0) { for (int i = 0; i < N; i += 4) VecLoad<4>::st(p + i, v + i); }
-  else if constexpr (N % 2 == 0) { for (int i = 0; i < N; i += 2) VecLoad<2>::st(p + i, v + i); }
-  else { for (int i = 0; i < N; i++) VecLoad<1>::st(p + i, v + i); }
+#pragma unroll
+  for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
 
-struct RayCtx { float dl; };
+// which ray / which part of it this lane owns.  Lanes past the last ray shadow ray R-1 (so every shuffle stays
+// warp-uniform) and skip their stores.
+template <int LPR> struct LaneRay {
+  int sub, r;
+  bool live;
+  __device__ __forceinline__ LaneRay(int R) {
+    const int lane = threadIdx.x & 31;
+    sub = lane & (LPR - 1);
+    const int ray = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * (32 / LPR) + lane / LPR;
+    live = ray < R;
+    r = live ? ray : R - 1;
+  }
+};
 
-// shared per-lane forward state for V consecutive samples
-template <int V, bool RAW>
+// per-lane forward state for kV consecutive samples of one ray
+template <int LPR, bool RAW>
 struct LaneSamples {
-  float sig[V], c[V][3], delta[V], tm[V];  // activated density, activated rgb, t_{i+1}-t_i, (t_i+t_{i+1})/2
-  float rs[V], rc[V][3];                   // raw values kept for the activation derivatives (RAW only)
-  float alpha[V], T[V], w[V];
-  float t_first, t_last;
+  static constexpr int V = kV, S = kV * LPR;
+  float c[V][3];   // RAW: s = sigmoid(raw rgb) (the padded colour is s*k - pad); else the colour itself
+  float rs[V];     // RAW: raw density + bias (for softplus'); else unused
+  float tv[V + 1]; // t_i .. t_{i+V}
+  float alpha[V], T[V];
 
-  __device__ __forceinline__ void load(const float* rgb, const float* density, const float* t, const float* tsm_in,
-                                       float* tsm, int r, int S, int lane, OutputAct act) {
-    const long base = (long)r * S + lane * V;
+  __device__ __forceinline__ float colour(int q, int a, float k, float pad) const { return RAW ? fmaf(c[q][a], k, -pad) : c[q][a]; }
+
+  // loads, activations, alpha_i = 1-exp(-sigma_i delta_i |d|), T_i = prod_{j<i}(1-alpha_j)   (.cu:330-332)
+  __device__ __forceinline__ void load(const float* __restrict__ rgb, const float* __restrict__ density,
+                                       const float* __restrict__ t, int r, int sub, float dl, OutputAct act) {
+    const long base = (long)r * S + sub * V;
     float dv[V], cv[3 * V];
     load_n<V>(density + base, dv);
     load_n<3 * V>(rgb + base * 3, cv);
-    // t row: coalesced into shared memory, then V+1 values per lane
-    const float* tr = t + (long)r * (S + 1);
-    for (int i = lane; i <= S; i += 32) tsm[i] = __ldg(tr + i);
-    __syncwarp();
-    (void)tsm_in;
-    float tv[V + 1];
+    const float* tr = t + (long)r * (S + 1) + sub * V;  // rows of S+1 floats: scalar loads, neighbours share the lines
 #pragma unroll
-    for (int q = 0; q <= V; q++) tv[q] = tsm[lane * V + q];
-    t_first = tsm[0]; t_last = tsm[S];
+    for (int q = 0; q <= V; q++) tv[q] = __ldg(tr + q);
+    float p = 1.f;
 #pragma unroll
     for (int q = 0; q < V; q++) {
-      delta[q] = tv[q + 1] - tv[q];
-      tm[q] = (tv[q] + tv[q + 1]) / 2;
+      float sig;
       if (RAW) {
         rs[q] = dv[q] + act.density_bias;
-        sig[q] = fast_softplus(rs[q]);
+        sig = fast_softplus(rs[q]);
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-          rc[q][a] = fast_sigmoid(cv[q * 3 + a]);  // keep s = sigmoid(raw) for s(1-s)
-          c[q][a] = rc[q][a] * (1.f + 2.f * act.rgb_padding) - act.rgb_padding;
-        }
+        for (int a = 0; a < 3; a++) c[q][a] = fast_sigmoid(cv[q * 3 + a]);
       } else {
-        sig[q] = dv[q];
+        sig = dv[q];
 #pragma unroll
         for (int a = 0; a < 3; a++) c[q][a] = cv[q * 3 + a];
       }
-    }
-  }
-
-  // alpha_i = 1-exp(-sigma_i delta_i |d|), T_i = prod_{j<i}(1-alpha_j), w_i = alpha_i T_i   (.cu:330-332)
-  __device__ __forceinline__ float weights(float dl, int lane) {
-    float om[V], p = 1.f;
-#pragma unroll
-    for (int q = 0; q < V; q++) {
       // alpha = 1 - exp(-s) (.cu:330); for small s the 3-term series keeps alpha's RELATIVE accuracy (no cancellation)
-      const float s = sig[q] * delta[q] * dl;
-      alpha[q] = s < 1e-2f ? s * (1.f - 0.5f * s * (1.f - s * (1.f / 3.f))) : 1.f - __expf(-s);
-      om[q] = 1.f - alpha[q];
-      p *= om[q];
+      const float s = sig * (tv[q + 1] - tv[q]) * dl;
+      const float big = 1.f - ex2_ftz(-kLog2e * s);
+      const float small = s * fmaf(-0.5f * s, fmaf(s, -1.f / 3.f, 1.f), 1.f);
+      alpha[q] = s < 1e-2f ? small : big;
+      p *= 1.f - alpha[q];
     }
-    float incl = p;  // inclusive prefix product over lanes
+    float incl = p;  // inclusive prefix product over the ray's lanes
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl *= up;
+    for (int o = 1; o < LPR; o <<= 1) {
+      const float up = __shfl_up_sync(kFull, incl, o, LPR);
+      if (sub >= o) incl *= up;
     }
-    float Tq = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) Tq = 1.f;
+    float Tq = __shfl_up_sync(kFull, incl, 1, LPR);
+    if (sub == 0) Tq = 1.f;
 #pragma unroll
-    for (int q = 0; q < V; q++) { T[q] = Tq; w[q] = alpha[q] * Tq; Tq *= om[q]; }
-    return Tq;  // T after this lane's last sample
+    for (int q = 0; q < V; q++) { T[q] = Tq; Tq *= 1.f - alpha[q]; }
   }
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
+template <int LPR> __device__ __forceinline__ float ray_sum(float v) {  // all-lanes sum over the LPR lanes of a ray
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+__device__ __forceinline__ float warp_sum(float v) { return ray_sum<32>(v); }
 
-template <int V, bool RAW>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__device__ __forceinline__ float dir_length(const float* __restrict__ dirs, int r) {
+  const float dx = __ldg(dirs + r * 3), dy = __ldg(dirs + r * 3 + 1), dz = __ldg(dirs + r * 3 + 2);
+  return sqrt_ftz(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+}
+
+template <int LPR, bool RAW>
+__global__ void __launch_bounds__(kThreads)
 k_composite_fwd(const float* __restrict__ rgb, const float* __restrict__ density, const float* __restrict__ t,
                 const float* __restrict__ dirs, int R, int white, OutputAct act, float* __restrict__ comp_rgb,
                 float* __restrict__ depth, float* __restrict__ acc, float* __restrict__ weights) {
-  constexpr int S = 32 * V;
-  __shared__ float tsm[kWarpsPerBlock][S + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kWarpsPerBlock + warp;
-  if (r >= R) return;
-  const float dx = __ldg(dirs + r * 3), dy = __ldg(dirs + r * 3 + 1), dz = __ldg(dirs + r * 3 + 2);
-  const float dl = sqrtf(dx * dx + dy * dy + dz * dz);
-  LaneSamples<V, RAW> ls;
-  ls.load(rgb, density, t, nullptr, tsm[warp], r, S, lane, act);
-  ls.weights(dl, lane);
-  float cr = 0.f, cg = 0.f, cb = 0.f, a = 0.f, wd = 0.f;
+  constexpr int V = kV, S = V * LPR;
+  const LaneRay<LPR> lr(R);
+  const int r = lr.r, sub = lr.sub;
+  const float dl = dir_length(dirs, r);
+  LaneSamples<LPR, RAW> ls;
+  ls.load(rgb, density, t, r, sub, dl, act);
+  const float k = 1.f + 2.f * act.rgb_padding, pad = act.rgb_padding;
+  float w[V], cr = 0.f, cg = 0.f, cb = 0.f, a = 0.f, wd = 0.f;
 #pragma unroll
   for (int q = 0; q < V; q++) {
-    cr += ls.w[q] * ls.c[q][0]; cg += ls.w[q] * ls.c[q][1]; cb += ls.w[q] * ls.c[q][2];
-    a += ls.w[q]; wd += ls.w[q] * ls.tm[q];
+    w[q] = ls.alpha[q] * ls.T[q];
+    cr = fmaf(w[q], ls.colour(q, 0, k, pad), cr); cg = fmaf(w[q], ls.colour(q, 1, k, pad), cg); cb = fmaf(w[q], ls.colour(q, 2, k, pad), cb);
+    a += w[q]; wd = fmaf(w[q], ls.tv[q] + ls.tv[q + 1], wd);  // 2 x sum w_i t_mid,i
   }
-  if (weights) store_n<V>(weights + (long)r * S + lane * V, ls.w);
-  cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); a = warp_sum(a); wd = warp_sum(wd);
-  if (lane == 0) {
+  if (weights && lr.live) store_n<V>(weights + (long)r * S + sub * V, w);
+  cr = ray_sum<LPR>(cr); cg = ray_sum<LPR>(cg); cb = ray_sum<LPR>(cb); a = ray_sum<LPR>(a); wd = ray_sum<LPR>(wd);
+  const float t_first = __shfl_sync(kFull, ls.tv[0], 0, LPR), t_last = __shfl_sync(kFull, ls.tv[V], LPR - 1, LPR);
+  if (sub == 0 && lr.live) {
     if (white) { cr += 1.f - a; cg += 1.f - a; cb += 1.f - a; }  // .cu:338-340
     comp_rgb[r * 3] = cr; comp_rgb[r * 3 + 1] = cg; comp_rgb[r * 3 + 2] = cb;
     if (depth) {  // SN/MipHelpers.cs:490
-      float dv = a > 0.f ? wd / a : INFINITY;
-      depth[r] = fminf(fmaxf(dv, ls.t_first), ls.t_last);
+      const float dv = a > 0.f ? 0.5f * wd / a : INFINITY;
+      depth[r] = fminf(fmaxf(dv, t_first), t_last);
     }
     if (acc) acc[r] = a;
   }
 }
 
-template <int V, bool RAW>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int LPR, bool RAW>
+__global__ void __launch_bounds__(kThreads)
 k_composite_bwd(const float* __restrict__ g, const float* __restrict__ rgb, const float* __restrict__ density,
                 const float* __restrict__ t, const float* __restrict__ dirs, int R, int white, int last_mode,
                 OutputAct act, float* __restrict__ d_rgb, float* __restrict__ d_density) {
-  constexpr int S = 32 * V;
-  __shared__ float tsm[kWarpsPerBlock][S + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kWarpsPerBlock + warp;
-  if (r >= R) return;
-  const float dx = __ldg(dirs + r * 3), dy = __ldg(dirs + r * 3 + 1), dz = __ldg(dirs + r * 3 + 2);
-  const float dl = sqrtf(dx * dx + dy * dy + dz * dz);
+  constexpr int V = kV, S = V * LPR;
+  const LaneRay<LPR> lr(R);
+  const int r = lr.r, sub = lr.sub;
+  const float dl = dir_length(dirs, r);
   const float gx = __ldg(g + r * 3), gy = __ldg(g + r * 3 + 1), gz = __ldg(g + r * 3 + 2);
   const float dLdAcc = white ? -(gx + gy + gz) : 0.f;  // .cu:370
-  LaneSamples<V, RAW> ls;
-  ls.load(rgb, density, t, nullptr, tsm[warp], r, S, lane, act);
-  ls.weights(dl, lane);
-  // dLdw_i = g.c_i + dLdAcc (.cu:385); last_mode 1 drops sample S-1 like the reference kernel (A-D12)
+  LaneSamples<LPR, RAW> ls;
+  ls.load(rgb, density, t, r, sub, dl, act);
+  const float k = 1.f + 2.f * act.rgb_padding, pad = act.rgb_padding;
+  // last_mode 1 drops sample S-1 like the reference kernel (A-D12)
+  const bool drop_last = last_mode == 1 && sub == LPR - 1;
+  // dLdw_i = g.c_i + dLdAcc (.cu:385)
   float dLdw[V], loc = 0.f;
 #pragma unroll
   for (int q = 0; q < V; q++) {
-    dLdw[q] = gx * ls.c[q][0] + gy * ls.c[q][1] + gz * ls.c[q][2] + dLdAcc;
-    if (last_mode == 1 && lane == 31 && q == V - 1) dLdw[q] = 0.f;
-    loc += dLdw[q] * ls.w[q];
+    dLdw[q] = fmaf(gx, ls.colour(q, 0, k, pad), fmaf(gy, ls.colour(q, 1, k, pad), fmaf(gz, ls.colour(q, 2, k, pad), dLdAcc)));
+    if (q == V - 1 && drop_last) dLdw[q] = 0.f;
+    loc = fmaf(dLdw[q], ls.alpha[q] * ls.T[q], loc);
   }
-  // exclusive suffix sum over lanes of loc
+  // exclusive suffix sum of loc over the ray's lanes
   float incl = loc;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float dn = __shfl_down_sync(0xffffffffu, incl, o);
-    if (lane + o < 32) incl += dn;
+  for (int o = 1; o < LPR; o <<= 1) {
+    const float dn = __shfl_down_sync(kFull, incl, o, LPR);
+    if (sub + o < LPR) incl += dn;
   }
-  float suffix = __shfl_down_sync(0xffffffffu, incl, 1);
-  if (lane == 31) suffix = 0.f;
+  float suffix = __shfl_down_sync(kFull, incl, 1, LPR);
+  if (sub == LPR - 1) suffix = 0.f;
   float dc[3 * V], ds[V];
 #pragma unroll
   for (int q = V - 1; q >= 0; q--) {
+    float wq = ls.alpha[q] * ls.T[q];
     const float Tnext = ls.T[q] * (1.f - ls.alpha[q]);
-    float dsig = ls.delta[q] * dl * (Tnext * dLdw[q] - suffix);
-    float wq = ls.w[q];
-    if (last_mode == 1 && lane == 31 && q == V - 1) { dsig = 0.f; wq = 0.f; }
-    suffix += dLdw[q] * ls.w[q];
+    float dsig = (ls.tv[q + 1] - ls.tv[q]) * dl * fmaf(Tnext, dLdw[q], -suffix);
+    suffix = fmaf(dLdw[q], wq, suffix);
+    if (q == V - 1 && drop_last) { dsig = 0.f; wq = 0.f; }
     float cx = gx * wq, cy = gy * wq, cz = gz * wq;  // .cu:388
-    if (RAW) {  // SN/MipNerfModel.cs:184-189
+    if (RAW) {  // SN/MipNerfModel.cs:184-189: softplus' = sigmoid, sigmoid' = s(1-s), colour = s*k - pad
       dsig *= fast_sigmoid(ls.rs[q]);
-      const float k = 1.f + 2.f * act.rgb_padding;
-      cx *= ls.rc[q][0] * (1.f - ls.rc[q][0]) * k;
-      cy *= ls.rc[q][1] * (1.f - ls.rc[q][1]) * k;
-      cz *= ls.rc[q][2] * (1.f - ls.rc[q][2]) * k;
+      cx *= fmaf(-ls.c[q][0], ls.c[q][0], ls.c[q][0]) * k;
+      cy *= fmaf(-ls.c[q][1], ls.c[q][1], ls.c[q][1]) * k;
+      cz *= fmaf(-ls.c[q][2], ls.c[q][2], ls.c[q][2]) * k;
     }
     ds[q] = dsig; dc[q * 3] = cx; dc[q * 3 + 1] = cy; dc[q * 3 + 2] = cz;
   }
-  const long base = (long)r * S + lane * V;
-  store_n<V>(d_density + base, ds);
-  store_n<3 * V>(d_rgb + base * 3, dc);
+  if (lr.live) {
+    const long base = (long)r * S + sub * V;
+    store_n<V>(d_density + base, ds);
+    store_n<3 * V>(d_rgb + base * 3, dc);
+  }
 }
 
 // g = 2*lm/lm_sum*(rgb-pix)*level_mult; optional loss = sum(lm |rgb-pix|^2)/lm_sum.  One block, fixed order.
@@ -264,30 +269,36 @@ __global__ void __launch_bounds__(1024) k_sum(const float* __restrict__ x, int n
 }
 
 template <bool RAW>
-int dispatch_fwd(int V, dim3 grid, cudaStream_t st, const float* rgb, const float* density, const float* t,
+int dispatch_fwd(int S, cudaStream_t st, const float* rgb, const float* density, const float* t,
                  const float* dirs, int R, int white, OutputAct act, float* comp, float* depth, float* acc, float* w) {
-  const int th = kWarpsPerBlock * 32;
-  switch (V) {
-    case 1: k_composite_fwd<1, RAW><<<grid, th, 0, st>>>(rgb, density, t, dirs, R, white, act, comp, depth, acc, w); break;
-    case 2: k_composite_fwd<2, RAW><<<grid, th, 0, st>>>(rgb, density, t, dirs, R, white, act, comp, depth, acc, w); break;
-    case 4: k_composite_fwd<4, RAW><<<grid, th, 0, st>>>(rgb, density, t, dirs, R, white, act, comp, depth, acc, w); break;
-    case 8: k_composite_fwd<8, RAW><<<grid, th, 0, st>>>(rgb, density, t, dirs, R, white, act, comp, depth, acc, w); break;
+#define NERF_FWD(LPR)                                                                                               \
+  k_composite_fwd<LPR, RAW><<<(unsigned)cdiv(R, (kThreads / 32) * (32 / LPR)), kThreads, 0, st>>>(rgb, density, t, dirs, R, white, \
+                                                                                                   act, comp, depth, acc, w)
+  switch (S / kV) {
+    case 4: NERF_FWD(4); break;
+    case 8: NERF_FWD(8); break;
+    case 16: NERF_FWD(16); break;
+    case 32: NERF_FWD(32); break;
     default: return 1;
   }
+#undef NERF_FWD
   return 0;
 }
 template <bool RAW>
-int dispatch_bwd(int V, dim3 grid, cudaStream_t st, const float* g, const float* rgb, const float* density,
+int dispatch_bwd(int S, cudaStream_t st, const float* g, const float* rgb, const float* density,
                  const float* t, const float* dirs, int R, int white, int last_mode, OutputAct act, float* d_rgb,
                  float* d_den) {
-  const int th = kWarpsPerBlock * 32;
-  switch (V) {
-    case 1: k_composite_bwd<1, RAW><<<grid, th, 0, st>>>(g, rgb, density, t, dirs, R, white, last_mode, act, d_rgb, d_den); break;
-    case 2: k_composite_bwd<2, RAW><<<grid, th, 0, st>>>(g, rgb, density, t, dirs, R, white, last_mode, act, d_rgb, d_den); break;
-    case 4: k_composite_bwd<4, RAW><<<grid, th, 0, st>>>(g, rgb, density, t, dirs, R, white, last_mode, act, d_rgb, d_den); break;
-    case 8: k_composite_bwd<8, RAW><<<grid, th, 0, st>>>(g, rgb, density, t, dirs, R, white, last_mode, act, d_rgb, d_den); break;
+#define NERF_BWD(LPR)                                                                                               \
+  k_composite_bwd<LPR, RAW><<<(unsigned)cdiv(R, (kThreads / 32) * (32 / LPR)), kThreads, 0, st>>>(g, rgb, density, t, dirs, R, white, \
+                                                                                                   last_mode, act, d_rgb, d_den)
+  switch (S / kV) {
+    case 4: NERF_BWD(4); break;
+    case 8: NERF_BWD(8); break;
+    case 16: NERF_BWD(16); break;
+    case 32: NERF_BWD(32); break;
     default: return 1;
   }
+#undef NERF_BWD
   return 0;
 }
 bool supported_S(int S) { return S == 32 || S == 64 || S == 128 || S == 256; }
@@ -298,10 +309,10 @@ int launch_composite_fwd(const float* rgb, const float* density, const float* t,
                          int white_bkgd, OutputAct act, float* comp_rgb, float* depth, float* acc, float* weights,
                          cudaStream_t st) {
   if (!supported_S(S)) { set_error("compositing: n_samples must be 32/64/128/256, got %d", S); return 100001; }
-  const dim3 grid((unsigned)cdiv(R, kWarpsPerBlock));
-  const int rc = act.raw ? dispatch_fwd<true>(S / 32, grid, st, rgb, density, t, dirs, R, white_bkgd, act, comp_rgb, depth, acc, weights)
-                         : dispatch_fwd<false>(S / 32, grid, st, rgb, density, t, dirs, R, white_bkgd, act, comp_rgb, depth, acc, weights);
-  if (rc) { set_error("compositing: bad V"); return 100001; }
+  if (R <= 0) return 0;
+  const int rc = act.raw ? dispatch_fwd<true>(S, st, rgb, density, t, dirs, R, white_bkgd, act, comp_rgb, depth, acc, weights)
+                         : dispatch_fwd<false>(S, st, rgb, density, t, dirs, R, white_bkgd, act, comp_rgb, depth, acc, weights);
+  if (rc) { set_error("compositing: bad S"); return 100001; }
   NERF_CHECK_LAUNCH();
   return 0;
 }
@@ -310,10 +321,10 @@ int launch_composite_bwd(const float* g, const float* rgb, const float* density,
                          int R, int S, int white_bkgd, int last_sample_mode, OutputAct act, float* d_rgb,
                          float* d_density, cudaStream_t st) {
   if (!supported_S(S)) { set_error("compositing: n_samples must be 32/64/128/256, got %d", S); return 100001; }
-  const dim3 grid((unsigned)cdiv(R, kWarpsPerBlock));
-  const int rc = act.raw ? dispatch_bwd<true>(S / 32, grid, st, g, rgb, density, t, dirs, R, white_bkgd, last_sample_mode, act, d_rgb, d_density)
-                         : dispatch_bwd<false>(S / 32, grid, st, g, rgb, density, t, dirs, R, white_bkgd, last_sample_mode, act, d_rgb, d_density);
-  if (rc) { set_error("compositing: bad V"); return 100001; }
+  if (R <= 0) return 0;
+  const int rc = act.raw ? dispatch_bwd<true>(S, st, g, rgb, density, t, dirs, R, white_bkgd, last_sample_mode, act, d_rgb, d_density)
+                         : dispatch_bwd<false>(S, st, g, rgb, density, t, dirs, R, white_bkgd, last_sample_mode, act, d_rgb, d_density);
+  if (rc) { set_error("compositing: bad S"); return 100001; }
   NERF_CHECK_LAUNCH();
   return 0;
 }

@@ -2,6 +2,8 @@
 
 Tolerances (stated per BASELINE.md): index/ordering work (sampling) bit-exact; fp32 stages
 |x - x_oracle| <= 1e-6 + 1e-4*|x_oracle| elementwise unless a test says why it is looser."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -104,6 +106,50 @@ def test_volumetric_rendering_fwd_bwd(R, S, white):
         # d_density sums ~S signed terms: tolerance on the ray's gradient scale
         scale = np.abs(r_den).max(axis=1, keepdims=True) + 1e-6
         assert np.abs(host(d_den) - r_den).max() <= 1e-4 * scale.max()
+        assert (np.abs(host(d_den) - r_den) / scale).max() <= 2e-4
+
+
+@pytest.mark.parametrize("R,S", [(5, 32), (77, 64), (1001, 128), (40, 256)])
+@pytest.mark.parametrize("bias,pad", [(0.0, 0.0), (-1.0, 0.001)])
+def test_volumetric_rendering_fused_activations(R, S, bias, pad):
+    """The form the model runs (SN/MipNerfModel.cs:81-83, 184-189 fused into the compositing kernels), through the
+    asynchronous entry on a non-default stream: raw head outputs in, gradients w.r.t. the raw head outputs out."""
+    rng = np.random.default_rng(7 * R + S)
+    rays = _rays(R, 3)
+    raw_rgb = rng.normal(0, 2.5, (R, S, 3)).astype(np.float32)
+    raw_den = rng.normal(-1, 3, (R, S)).astype(np.float32)
+    raw_den[0] = -60.0   # softplus underflows: empty ray
+    raw_rgb[1] = 30.0    # saturated sigmoid
+    t = np.sort(rng.uniform(2, 6, (R, S + 1)).astype(np.float32), 1)
+    d = rays["directions"]
+    g = rng.normal(size=(R, 3)).astype(np.float32)
+    cfg = orc.default_config(density_bias=bias, rgb_padding=pad)
+    den64, rgb64 = orc.output_activations(cfg, raw_den, raw_rgb, prec="f64")
+    den64, rgb64 = den64.reshape(R, S), rgb64.reshape(R, S, 3)
+    o64 = orc.volumetric_rendering(rgb64, den64, t, d, 1, prec="f64")
+    comp, depth, acc, w = empty(R, 3), empty(R), empty(R), empty(R, S)
+    st = torch.cuda.Stream()
+    sp = C.c_void_p(st.cuda_stream)
+    args = [dev(raw_rgb), dev(raw_den), dev(t), dev(d), dev(g)]
+    torch.cuda.synchronize()
+    call("nerf_volumetric_rendering_async", ptr(args[0]), ptr(args[1]), ptr(args[2]), ptr(args[3]), ptr(comp), ptr(depth),
+         ptr(acc), ptr(w), R, S, 1, 1, bias, pad, sp)
+    st.synchronize()
+    for got, key in ((comp, "comp_rgb"), (acc, "acc"), (w, "weights")):
+        np.testing.assert_allclose(host(got), o64[key], rtol=1e-4, atol=2e-6, err_msg=key)
+    # ray 0: fp32 softplus(-60) is exactly 0 (as in the reference's fp32 arithmetic) -> acc = 0 -> depth clamps to t_S
+    np.testing.assert_allclose(host(depth)[1:], o64["depth"][1:], rtol=1e-4, atol=2e-6, err_msg="depth")
+    assert host(depth)[0] == t[0, -1] and host(acc)[0] == 0.0
+    for mode in (0, 1):
+        d_rgb, d_den = empty(R, S, 3), empty(R, S)
+        call("nerf_volumetric_rendering_gradient_async", ptr(args[4]), ptr(args[0]), ptr(args[1]), ptr(args[2]), ptr(args[3]),
+             ptr(d_rgb), ptr(d_den), R, S, 1, mode, 1, bias, pad, sp)
+        st.synchronize()
+        a_rgb, a_den = orc.volumetric_rendering_gradient(g, rgb64, den64, t, d, 1, mode, prec="f64")
+        r_den, r_rgb = orc.output_activations_grad(cfg, raw_den, raw_rgb, a_den, a_rgb, prec="f64")
+        r_den, r_rgb = r_den.reshape(R, S), r_rgb.reshape(R, S, 3)
+        np.testing.assert_allclose(host(d_rgb), r_rgb, rtol=1e-4, atol=1e-6)
+        scale = np.abs(r_den).max(axis=1, keepdims=True) + 1e-6
         assert (np.abs(host(d_den) - r_den) / scale).max() <= 2e-4
 
 
