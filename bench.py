@@ -629,8 +629,9 @@ def main():
                     help="render: configs[3], forward only; sweep: configs[4]; compositing: the per-ray kernels alone vs the HBM roofline")
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-run", action="store_true", help="under ncu only: do not raise --warmup to 3 (the line printed is not a bench value)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" and not args.profiler_run else args.warmup
     if args.impl == "reference":
         reference_arm(args)
     elif args.mode == "render":

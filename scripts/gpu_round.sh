@@ -16,12 +16,12 @@ timeout 300 python bench.py --precision bf16 --no-cpu-baseline > $out/${tag}_ben
 cat $out/${tag}_compositing.json | cut -c1-1500
 cut -c1-600 $out/${tag}_bench_fp32_tc.json
 cut -c1-400 $out/${tag}_bench_bf16.json
-# 3. ncu: full capture of the compositing kernels at 262144 rays (launches 17-32 of the compositing bench), then the
+# 3. ncu: full capture of the compositing kernels at 262144 rays (launches 9-16 of a 1+1-launch compositing run), then the
 #    launch list of the default bench, then a full capture of one step's GEMM-family kernels
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_composite --launch-skip 16 --launch-count 16 \
-  -o $out/${tag}_ncu_compositing python bench.py --mode compositing --steps 1 --warmup 3 > $out/${tag}_ncu_compositing.log 2>&1; echo "ncu compositing rc=$?" | tee -a $out/${tag}_status.txt
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_composite --launch-skip 8 --launch-count 8 \
+  -o $out/${tag}_ncu_compositing python bench.py --mode compositing --steps 1 --warmup 1 --profiler-run > $out/${tag}_ncu_compositing.log 2>&1; echo "ncu compositing rc=$?" | tee -a $out/${tag}_status.txt
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/${tag}_launches_fp32_tc.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1; echo "ncu launch list rc=$?" | tee -a $out/${tag}_status.txt
-timeout 500 ncu --set full --clock-control none --import-source on -k 'regex:k_tc_wgrad|k_mlp_fused|k_tc_gemm_persist' --launch-skip 120 --launch-count 40 \
+timeout 500 ncu --set full --clock-control none -k 'regex:k_tc_wgrad|k_mlp_fused|k_tc_gemm_persist' --launch-skip 120 --launch-count 40 \
   -o $out/${tag}_ncu_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_gemm.log 2>&1; echo "ncu gemm rc=$?" | tee -a $out/${tag}_status.txt
 ls -la $out | tail -20
