@@ -177,7 +177,9 @@ k_composite_bwd(const float* __restrict__ g, const float* __restrict__ rgb, cons
   const int r = lr.r, sub = lr.sub;
   const float dl = dir_length(dirs, r);
   const float gx = __ldg(g + r * 3), gy = __ldg(g + r * 3 + 1), gz = __ldg(g + r * 3 + 2);
-  const float dLdAcc = white ? -(gx + gy + gz) : 0.f;  // .cu:370
+  // .cu:370.  Same association as the colour dot product below, so a saturated white sample (c = 1) on a white
+  // background gets dLdw = 0 exactly, as in the reference's arithmetic.
+  const float dLdAcc = white ? -((gx + gy) + gz) : 0.f;
   LaneSamples<LPR, RAW> ls;
   ls.load(rgb, density, t, r, sub, dl, act);
   const float k = 1.f + 2.f * act.rgb_padding, pad = act.rgb_padding;
@@ -187,7 +189,7 @@ k_composite_bwd(const float* __restrict__ g, const float* __restrict__ rgb, cons
   float dLdw[V], loc = 0.f;
 #pragma unroll
   for (int q = 0; q < V; q++) {
-    dLdw[q] = fmaf(gx, ls.colour(q, 0, k, pad), fmaf(gy, ls.colour(q, 1, k, pad), fmaf(gz, ls.colour(q, 2, k, pad), dLdAcc)));
+    dLdw[q] = fmaf(gz, ls.colour(q, 2, k, pad), fmaf(gy, ls.colour(q, 1, k, pad), gx * ls.colour(q, 0, k, pad))) + dLdAcc;
     if (q == V - 1 && drop_last) dLdw[q] = 0.f;
     loc = fmaf(dLdw[q], ls.alpha[q] * ls.T[q], loc);
   }

@@ -37,6 +37,54 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// One slot of a ReduceJob: slot idx < rows*ceil(cols/4) sums 4 consecutive columns of one output row over the splits with
+// 128-bit loads, later slots one bias column each.  The order is the one k_reduce_partials_tc uses — four interleaved
+// split groups z = g, g+4, ... combined as (g0 + g1) + (g2 + g3) — so a job gives bitwise the same result whether it runs
+// stand-alone or inside the next wgrad launch.  Needs ldw % 4 == 0 and stride % 4 == 0.
+__device__ __forceinline__ void f4_add(float4& s, const float4 v) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+__device__ __forceinline__ void reduce_job_slot(const ReduceJob& j, long idx) {
+  const int c4 = (j.cols + 3) >> 2;
+  const long n1 = (long)j.rows * c4;
+  if (idx < n1) {
+    const int i = (int)(idx / c4), c = (int)(idx % c4) * 4;
+    const float* src = j.ws + (long)i * j.ldw + c;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+    int z = 0;
+    for (; z + 4 <= j.splits; z += 4) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (long)z * j.stride));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (long)(z + 1) * j.stride));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(src + (long)(z + 2) * j.stride));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(src + (long)(z + 3) * j.stride));
+      f4_add(s0, v0); f4_add(s1, v1); f4_add(s2, v2); f4_add(s3, v3);
+    }
+    if (z < j.splits) f4_add(s0, __ldg(reinterpret_cast<const float4*>(src + (long)z * j.stride)));
+    if (z + 1 < j.splits) f4_add(s1, __ldg(reinterpret_cast<const float4*>(src + (long)(z + 1) * j.stride)));
+    if (z + 2 < j.splits) f4_add(s2, __ldg(reinterpret_cast<const float4*>(src + (long)(z + 2) * j.stride)));
+    float* o = j.out + (long)i * j.ldo + j.coff + c;
+    o[0] += (s0.x + s1.x) + (s2.x + s3.x);
+    if (c + 1 < j.cols) o[1] += (s0.y + s1.y) + (s2.y + s3.y);
+    if (c + 2 < j.cols) o[2] += (s0.z + s1.z) + (s2.z + s3.z);
+    if (c + 3 < j.cols) o[3] += (s0.w + s1.w) + (s2.w + s3.w);
+  } else if (idx - n1 < j.n2) {
+    const int jb = (int)(idx - n1);
+    const float* src = j.ws2 + jb;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= j.splits; z += 4) {
+      s0 += src[(long)z * j.stride2]; s1 += src[(long)(z + 1) * j.stride2];
+      s2 += src[(long)(z + 2) * j.stride2]; s3 += src[(long)(z + 3) * j.stride2];
+    }
+    if (z < j.splits) s0 += src[(long)z * j.stride2];
+    if (z + 1 < j.splits) s1 += src[(long)(z + 1) * j.stride2];
+    if (z + 2 < j.splits) s2 += src[(long)(z + 2) * j.stride2];
+    j.out2[jb] += (s0 + s1) + (s2 + s3);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_reduce_job(const ReduceJob j) {
+  reduce_job_slot(j, (long)blockIdx.x * 128 + threadIdx.x);
+}
+
 // MN-major kernel (wgrad): one CTA = one 128 x BN tile of dW over a slice of the samples.
 //   warp 4 lane 0  TMA producer   boxes {64 cols, 64 rows} of the dZ / X planes, 128B-swizzled, n_stages-deep ring
 //   warp 5 lane 0  MMA issuer     tcgen05.mma M=128, N=BN, K=16, both operands MN-major (a_major = b_major = 1);
@@ -142,6 +190,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3: TMEM lanes 32w..32w+31)
+    // idle until the last k-block has been multiplied: first reduce the previous launch's partial tiles
+    if (p.red.ws != nullptr) {
+      const long cta = ((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      const long step = (long)gridDim.x * gridDim.y * gridDim.z * 128;
+      const long total = (long)p.red.rows * ((p.red.cols + 3) >> 2) + p.red.n2;
+      for (long idx = cta * 128 + threadIdx.x; idx < total; idx += step) reduce_job_slot(p.red, idx);
+    }
     const long row = row0 + threadIdx.x;
     if (n_kb > 0) {
       mbar_wait(&done_bar, 0);
@@ -871,6 +926,15 @@ int launch_reduce_partials2(const float* ws, int splits, long split_stride, int 
   const long n = (long)rows * ((cols + 3) / 4) + (ws2 ? n2 : 0);
   k_reduce_partials_tc<<<(unsigned)cdiv(n, 64), 256, 0, st>>>(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff, ws2, ws2 ? n2 : 0,
                                                                stride2, out2);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_reduce_job(const ReduceJob& job, cudaStream_t st) {
+  if (!job.ws) return 0;
+  if ((job.ldw & 3) || (job.stride & 3)) { set_error("reduce job: ldw and stride must be multiples of 4"); return 100001; }
+  const long n = (long)job.rows * ((job.cols + 3) / 4) + job.n2;
+  k_reduce_job<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(job);
   NERF_CHECK_LAUNCH();
   return 0;
 }

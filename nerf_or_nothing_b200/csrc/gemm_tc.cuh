@@ -13,6 +13,17 @@ constexpr int TC_MAX_KB = 30;
 // Operands are bf16 "planes" in global memory (x ~= hi [+ lo]) described by TMA tensor maps; a k-block names
 // which A plane / B plane it multiplies, so conjoined inputs (two K segments) and the bf16x3 split passes
 // (hi*hi + hi*lo + lo*hi) are just longer k-block lists over the same kernel.
+// out[i*ldo + coff + j] += sum_z ws[z*stride + i*ldw + j]  (+ the bias segment out2[j] += sum_z ws2[z*stride2 + j]) in a
+// FIXED order: the reduction of a wgrad launch's fp32 partial tiles.  ws == nullptr: no job.
+struct ReduceJob {
+  const float* ws;
+  float* out;
+  const float* ws2;
+  float* out2;
+  long stride, stride2;
+  int splits, rows, cols, ldw, ldo, coff, n2;
+};
+
 struct alignas(64) TcParams {
   CUtensorMap maps[8];  // [0..3] A-side planes, [4..5] B-side planes, [6..7] output planes (K-major epilogue TMA stores)
   // ---- K-major mode (forward, dgrad): grid = (ceil(M/128), ceil(N/BN))
@@ -45,6 +56,9 @@ struct alignas(64) TcParams {
   long split_stride;  // floats between splits
   float* bias_out;    // epi 2, optional: [split][rows] column sums of the A operand (bias gradient)
   long bias_split_stride;
+  // epi 2, optional: the reduction of the PREVIOUS wgrad launch's partials, run by this launch's epilogue warps while
+  // they wait for the MMA pipeline (they are idle until the last k-block): the reduction leaves the critical path
+  ReduceJob red;
   // ReLU masks as bit planes: 1 bit per output element instead of re-reading the 2-byte activation in dgrad
   uint32_t* bits_out;         // epi 0, optional: [M, ld_bits] words, bit j of word c <=> Y[m, 32c + j] > 0
   const uint32_t* mask_bits;  // epi 1, optional (replaces `mask`)
@@ -127,5 +141,6 @@ int launch_reduce_partials2(const float* ws, int splits, long split_stride, int 
                             const float* ws2, int n2, long stride2, float* out2, cudaStream_t st);
 int launch_reduce_partials(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo,
                            int coff, cudaStream_t st);
+int launch_reduce_job(const ReduceJob& job, cudaStream_t st);  // stand-alone launch of a job (same arithmetic, same order)
 
 }  // namespace nerf

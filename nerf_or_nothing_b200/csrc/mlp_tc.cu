@@ -78,6 +78,14 @@ class TcMlp : public MlpEngine {
     NERF_CUDA(cudaMalloc(&ws_, ws * sizeof(float)));
     owned_.push_back(ws_);
     bytes_ += ws * sizeof(float);
+    // wgrad partial tiles alternate between two buffers: a launch's partials are reduced by the NEXT wgrad launch
+    for (int i = 0; i < 2; i++) {
+      NERF_CUDA(cudaMalloc(&wsw_[i], ws * sizeof(float)));
+      owned_.push_back(wsw_[i]);
+      bytes_ += ws * sizeof(float);
+    }
+    pending_.ws = nullptr;
+    defer_reduce_ = getenv("NERF_NO_DEFERRED_REDUCE") == nullptr;
     return 0;
   }
 
@@ -234,6 +242,20 @@ class TcMlp : public MlpEngine {
 
   int backward(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
                cudaStream_t st) override {
+    const int s = backward_impl(level, M, params, grads, d_raw_density, d_raw_rgb, st);
+    ProfScope ps(PC_MLP_WGRAD, st);
+    const int f = flush_reduce(st);  // the last wgrad launch's partials have no successor to ride in
+    return s ? s : f;
+  }
+
+  int flush_reduce(cudaStream_t st) {
+    const ReduceJob job = pending_;
+    pending_.ws = nullptr;
+    return launch_reduce_job(job, st);
+  }
+
+  int backward_impl(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
+                    cudaStream_t st) {
     Level& lv = levels_[level];
     const int D = s_.D, C = s_.C, W = s_.W, Wc = s_.Wc;
     Plane* cur = &dz_[0];
@@ -487,12 +509,20 @@ class TcMlp : public MlpEngine {
       const int ldf = round_up(K, 4);
       p.split_len = (int)split_len; p.red_len = M; p.BN = BN; p.n_valid = K; p.rows_valid = N;
       p.n_stages = tc_pick_stages(BN, 1 << 20, true);
-      p.epi = 2; p.out_f32 = ws_; p.ld_f32 = ldf; p.split_stride = (long)N * ldf;
+      float* wsp = wsw_[ws_flip_];
+      ws_flip_ ^= 1;
+      p.epi = 2; p.out_f32 = wsp; p.ld_f32 = ldf; p.split_stride = (long)N * ldf;
       const bool bias_here = db != nullptr && src == 0;  // db = colsum(dZ) rides along as a 16-column MMA against ones
-      float* bias_ws = ws_ + (size_t)splits * N * ldf;
+      float* bias_ws = wsp + (size_t)splits * N * ldf;
       if (bias_here) { p.bias_out = bias_ws; p.bias_split_stride = N; }
+      p.red = pending_;  // the previous launch's partials are summed by this launch's waiting epilogue warps
+      pending_.ws = nullptr;
       NERF_TRY(tc_launch(p, true, dim3((unsigned)cdiv(N, 128), (unsigned)cdiv(K, BN), (unsigned)splits), st));
-      NERF_TRY(launch_reduce_partials2(ws_, splits, p.split_stride, N, K, ldf, dW, ldw, coff, bias_here ? bias_ws : nullptr, N, N, db, st));
+      ReduceJob job;
+      job.ws = wsp; job.out = dW; job.ws2 = bias_here ? bias_ws : nullptr; job.out2 = db; job.stride = p.split_stride; job.stride2 = N;
+      job.splits = splits; job.rows = N; job.cols = K; job.ldw = ldf; job.ldo = ldw; job.coff = coff; job.n2 = bias_here ? N : 0;
+      if (defer_reduce_) pending_ = job;
+      else NERF_TRY(launch_reduce_job(job, st));
     }
     return 0;
   }
@@ -505,7 +535,11 @@ class TcMlp : public MlpEngine {
   Plane dz_[2];
   std::vector<Plane> dzs_;  // bf16 fused dgrad chain: dZ of trunk layer D-1-j, kept for the wgrad GEMMs
   std::vector<Plane> wp_, wtp_;
-  float* ws_ = nullptr;
+  float* ws_ = nullptr;               // thin heads / column sums
+  float* wsw_[2] = {nullptr, nullptr};  // wgrad partial tiles, alternating
+  int ws_flip_ = 0;
+  ReduceJob pending_{};               // reduction of the last wgrad launch, not yet run
+  bool defer_reduce_ = true;
   float* fconsts_ = nullptr;  // fused forward: biases + head weights, gathered per parameter version
   bool fconsts_dirty_ = true;
   size_t bytes_ = 0;

@@ -1,27 +1,46 @@
 #!/bin/bash
-# One gpurun call: parity tests, bench lines and ncu captures of the current build.  Everything lands in gpurun_out/.
-#   gpurun --timeout 1500 -- bash scripts/gpu_round.sh [tag]
-tag=${1:-r01b}
+# One gpurun call: parity tests, bench lines and ncu captures of the current build.  Everything lands in gpurun_out/
+# (kept under the 64 MiB that gpurun copies back: big .ncu-rep files are exported to CSV on the box and deleted).
+#   gpurun --timeout 1200 -- bash scripts/gpu_round.sh [tag]
+tag=${1:-r01c}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/${tag}_gpu.txt 2>&1
-# 1. the compositing stage tests first (new kernels), then the whole GPU suite
-timeout 300 python -m pytest tests/test_stages_gpu.py -x -q -m gpu -k "volumetric" > $out/${tag}_pytest_stage.log 2>&1; echo "stage tests rc=$?" | tee -a $out/${tag}_status.txt
-timeout 900 python -m pytest tests -x -q -m gpu --durations=8 > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_status.txt
-tail -15 $out/${tag}_pytest.log
+# 1. the whole GPU suite (no -x: one failure must not hide the rest)
+timeout 900 python -m pytest tests -q -m gpu --durations=5 > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_status.txt
+tail -12 $out/${tag}_pytest.log
 # 2. bench lines (no profiler)
 timeout 300 python bench.py --mode compositing --steps 20 --warmup 5 > $out/${tag}_compositing.json 2> $out/${tag}_compositing.err; echo "bench compositing rc=$?" | tee -a $out/${tag}_status.txt
 timeout 400 python bench.py > $out/${tag}_bench_fp32_tc.json 2> $out/${tag}_bench_fp32_tc.err; echo "bench fp32_tc rc=$?" | tee -a $out/${tag}_status.txt
 timeout 300 python bench.py --precision bf16 --no-cpu-baseline > $out/${tag}_bench_bf16.json 2> $out/${tag}_bench_bf16.err; echo "bench bf16 rc=$?" | tee -a $out/${tag}_status.txt
-cat $out/${tag}_compositing.json | cut -c1-1500
-cut -c1-600 $out/${tag}_bench_fp32_tc.json
-cut -c1-400 $out/${tag}_bench_bf16.json
-# 3. ncu: full capture of the compositing kernels at 262144 rays (launches 9-16 of a 1+1-launch compositing run), then the
-#    launch list of the default bench, then a full capture of one step's GEMM-family kernels
+NERF_NO_DEFERRED_REDUCE=1 timeout 300 python bench.py --no-cpu-baseline > $out/${tag}_bench_fp32_tc_nodefer.json 2> $out/${tag}_bench_nodefer.err; echo "bench fp32_tc (stand-alone reductions) rc=$?" | tee -a $out/${tag}_status.txt
+NERF_NO_DEFERRED_REDUCE=1 timeout 300 python bench.py --precision bf16 --no-cpu-baseline > $out/${tag}_bench_bf16_nodefer.json 2> $out/${tag}_bench_bf16_nodefer.err; echo "bench bf16 (stand-alone reductions) rc=$?" | tee -a $out/${tag}_status.txt
+python - <<PY
+import json
+for f in ("bench_fp32_tc", "bench_fp32_tc_nodefer", "bench_bf16", "bench_bf16_nodefer"):
+    try:
+        d = json.loads(open("$out/${tag}_" + f + ".json").read().strip().splitlines()[-1])
+        print(f, round(d["ms_per_step"], 3), "ms", round(d["value"]), "rays/s e2e", round(d["e2e"]["value"]), "launches", d["gpu_launches"],
+              {k: v["ms_per_step"] for k, v in d["kernels"].items() if v["ms_per_step"] > 0.05}, d["roofline"], d["clocks"])
+    except Exception as e:
+        print(f, "unreadable", e)
+try:
+    d = json.loads(open("$out/${tag}_compositing.json").read().strip().splitlines()[-1])
+    for c in d["cells"]:
+        print(c["kernel"], c["form"], c["rays"], c["us_per_launch"], "us", c["achieved"], "GB/s", c["frac"])
+except Exception as e:
+    print("compositing unreadable", e)
+PY
+# 3. ncu: full capture of the compositing kernels at 262144 rays (launches 9-16 of a 1+1-launch compositing run), the
+#    launch list of the default bench, and a full capture of the first 12 GEMM-family kernels of a steady-state step
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_composite --launch-skip 8 --launch-count 8 \
   -o $out/${tag}_ncu_compositing python bench.py --mode compositing --steps 1 --warmup 1 --profiler-run > $out/${tag}_ncu_compositing.log 2>&1; echo "ncu compositing rc=$?" | tee -a $out/${tag}_status.txt
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/${tag}_launches_fp32_tc.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1; echo "ncu launch list rc=$?" | tee -a $out/${tag}_status.txt
-timeout 500 ncu --set full --clock-control none -k 'regex:k_tc_wgrad|k_mlp_fused|k_tc_gemm_persist' --launch-skip 120 --launch-count 40 \
+timeout 500 ncu --set full --clock-control none -k 'regex:k_tc_wgrad|k_mlp_fused|k_tc_gemm_persist' --launch-skip 80 --launch-count 12 \
   -o $out/${tag}_ncu_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_gemm.log 2>&1; echo "ncu gemm rc=$?" | tee -a $out/${tag}_status.txt
-ls -la $out | tail -20
+for r in ncu_compositing ncu_gemm; do
+  [ -f $out/${tag}_$r.ncu-rep ] && ncu -i $out/${tag}_$r.ncu-rep --page raw --csv > $out/${tag}_${r}_raw.csv 2>/dev/null
+done
+rm -f $out/${tag}_ncu_gemm.ncu-rep
+du -sh $out; ls -la $out | tail -25

@@ -149,7 +149,9 @@ def test_volumetric_rendering_fused_activations(R, S, bias, pad):
         r_den, r_rgb = orc.output_activations_grad(cfg, raw_den, raw_rgb, a_den, a_rgb, prec="f64")
         r_den, r_rgb = r_den.reshape(R, S), r_rgb.reshape(R, S, 3)
         np.testing.assert_allclose(host(d_rgb), r_rgb, rtol=1e-4, atol=1e-6)
-        scale = np.abs(r_den).max(axis=1, keepdims=True) + 1e-6
+        # d_density sums ~S signed terms of size |g| each: tolerance on the ray's gradient scale, floored at 1e-4 |g| so that
+        # the saturated white ray (true gradient ~0 by cancellation of g.c against sum(g)) is judged against fp32 rounding
+        scale = np.abs(r_den).max(axis=1, keepdims=True) + 1e-4 * np.abs(g).sum(axis=1, keepdims=True) + 1e-6
         assert (np.abs(host(d_den) - r_den) / scale).max() <= 2e-4
 
 
