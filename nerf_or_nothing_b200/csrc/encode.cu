@@ -100,21 +100,30 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
              float* __restrict__ enc_f32, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
              int pitch_h) {
   extern __shared__ float tile[];  // [kTileSamples][P]
+  __shared__ Gauss gs[kTileSamples];
   const int P = 6 * deg;
   const int ls = threadIdx.x / kFreqLanes, fl = threadIdx.x % kFreqLanes;
   const long m0 = (long)blockIdx.x * kTileSamples;
   const long m = m0 + ls;
-  if (m < M) {
+  // the Gaussian of a sample (a dozen IEEE divisions) is computed ONCE, by one lane of the first warp, not by each of
+  // the 8 lanes that share the sample's frequencies: a warp issues an instruction for all its samples at the price of one
+  if (threadIdx.x < kTileSamples && m0 + threadIdx.x < M) {
+    const long mm = m0 + threadIdx.x;
     Gauss g;
     if (FUSED) {
-      const int r = (int)(m / S), s = (int)(m % S);
+      const int r = (int)(mm / S), s = (int)(mm % S);
       const float3 oo = make_float3(o[r * 3], o[r * 3 + 1], o[r * 3 + 2]);
       const float3 dd = make_float3(d[r * 3], d[r * 3 + 1], d[r * 3 + 2]);
       g = frustum_to_gaussian(in0[(long)r * (S + 1) + s], in0[(long)r * (S + 1) + s + 1], radii[r], oo, dd);
     } else {
-      g.mx = in0[m * 3]; g.my = in0[m * 3 + 1]; g.mz = in0[m * 3 + 2];
-      g.cx = in1[m * 3]; g.cy = in1[m * 3 + 1]; g.cz = in1[m * 3 + 2];
+      g.mx = in0[mm * 3]; g.my = in0[mm * 3 + 1]; g.mz = in0[mm * 3 + 2];
+      g.cx = in1[mm * 3]; g.cy = in1[mm * 3 + 1]; g.cz = in1[mm * 3 + 2];
     }
+    gs[threadIdx.x] = g;
+  }
+  __syncthreads();
+  if (m < M) {
+    const Gauss g = gs[ls];
     const HalfTurns hx = to_half_turns(g.mx), hy = to_half_turns(g.my), hz = to_half_turns(g.mz);
     const bool fast = enc_f32 == nullptr && lo == nullptr;  // single bf16 plane out
     for (int f = fl; f < deg; f += kFreqLanes) {

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kWStages - 1 : kWStages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[kWStages], w_empty[kWStages], pos_full, pos_empty, dir_full, dir_empty, acc_full, acc_empty, act_ready;
+  __shared__ uint64_t w_full[kWStages], w_empty[kWStages], pos_full, pos_empty, dir_full, dir_empty, acc_full, acc_empty, act_ready, act_lo_ready;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(&pos_full, 1); mbar_init(&pos_empty, 1); mbar_init(&dir_full, 1); mbar_init(&dir_empty, 1);
-    mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8); mbar_init(&act_ready, 8);
+    mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8); mbar_init(&act_ready, 8); mbar_init(&act_lo_ready, 8);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.n_consts; i += kThreadsF) s_const[i] = __ldg(p.consts + i);
@@ -235,13 +235,18 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
         for (int h = 0; h < st.n_halves; h++) {
           mbar_wait(&acc_empty, (n_acc & 1) ^ 1);  // both tiles' accumulators drained by the epilogue warps
           n_acc++;
+          // ACT of both tiles is rewritten in place in two instalments: the layer below's first N-half (this layer's k-blocks
+          // 0,1; parked in registers during its second half's MMAs) as soon as those MMAs are complete, its second N-half
+          // when that half's epilogue is done — this layer's first k-blocks run under that epilogue instead of after it
+          const bool wait_act = h == 0 && st.n_act_kb > 0;
           if (h == 0) {
-            if (st.n_act_kb > 0) { mbar_wait(&act_ready, n_act & 1); n_act++; }  // ACT of both tiles rewritten in place
+            if (wait_act) mbar_wait(&act_lo_ready, n_act & 1);
             if (s == 0) mbar_wait(&pos_full, pl & 1);
             if (st.enc_kind == 2) mbar_wait(&dir_full, pl & 1);
           }
           tc_fence_after_sync();
           for (int kb = 0; kb < st.n_act_kb; kb++, wit++) {  // A = activations resident in tensor memory
+            if (wait_act && kb == st.n_act_kb / 2) { mbar_wait(&act_ready, n_act & 1); tc_fence_after_sync(); }
             const uint32_t ws = wit % NS;
             mbar_wait(&w_full[ws], (wit / NS) & 1);
             tc_fence_after_sync();
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
               umma_commit(&w_empty[ws]);
             }
           }
+          if (wait_act) n_act++;
           for (int kb = 0; kb < st.n_enc_kb; kb++, wit++) {  // A = this pair's encodings in shared memory
             const uint32_t ws = wit % NS;
             mbar_wait(&w_full[ws], (wit / NS) & 1);
@@ -352,7 +358,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
             ship(h * 128 + 64, 1, held + 48);
           } else {
             // every MMA of the layer is complete: ACT may be overwritten in place
-            if (st.n_halves == 2 && st.produces) {
+            const bool unpark = st.n_halves == 2 && st.produces;
+            if (unpark) {
 #pragma unroll
               for (int c = 0; c < 4; c++) tmem_st_16(act + c * 16, held + 16 * c);
             }
@@ -361,6 +368,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
             uint32_t ra[32], rb[32], pk[16];
             tmem_ld_32x32(acc, ra);
             tmem_ld_wait();
+            if (unpark) {  // the next layer's k-blocks 0,1 may start
+              tmem_st_wait();
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&act_lo_ready);
+            }
             tmem_ld_32x32(acc + 32, rb);
             m0 = chunk(ra, 0, hw, pk);
             if (st.produces) tmem_st_16(out, pk);

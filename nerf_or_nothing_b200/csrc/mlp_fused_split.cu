@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready;
+  __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready, act_lo_ready;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float head_part[128][4];  // partial head dot products of the upper-column warps
 
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
     for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int h = 0; h < 2; h++) { mbar_init(&acc_full[h], 1); mbar_init(&acc_empty[h], kEpiWarps); }
     mbar_init(&act_ready, kEpiWarps);
+    mbar_init(&act_lo_ready, kEpiWarps);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.n_consts; i += kThreadsS) s_const[i] = __ldg(p.consts + i);
@@ -216,13 +217,18 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
         for (int h = 0; h < st.n_halves; h++) {
           mbar_wait(&acc_empty[h], (n_acc[h] & 1) ^ 1);
           n_acc[h]++;
-          if (h == 0 && st.n_act_kb > 0) { mbar_wait(&act_ready, n_act & 1); n_act++; }
+          // the layer below rewrites ACT in two instalments: its first N-half (= this layer's k-blocks 0,1; parked in
+          // registers during its second half's MMAs) lands as soon as those MMAs are complete, its second N-half when that
+          // half's epilogue is done — this layer's first k-blocks run under that epilogue instead of after it
+          const bool wait_act = h == 0 && st.n_act_kb > 0;
+          if (wait_act) mbar_wait(&act_lo_ready, n_act & 1);
           tc_fence_after_sync();
           const uint32_t acc = ACC + 128 * h;
           const bool stamp = p.dbg && blockIdx.x == 0 && leader && n_acc[0] <= 16;
           if (stamp) p.dbg[((n_acc[0] - 1) * 2 + h) * 8 + 0] = clock64();
           for (int kb = 0; kb < n_kb; kb++) {
             const bool from_act = kb < st.n_act_kb;
+            if (wait_act && kb == st.n_act_kb / 2) { mbar_wait(&act_ready, n_act & 1); tc_fence_after_sync(); }
             uint32_t a_stage = 0, a_hi = 0;
             if (!from_act) {  // the encoding tiles of this k-block arrive in their own stage
               a_stage = it % NS;
@@ -256,6 +262,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
             }
             it++;
           }
+          if (wait_act) n_act++;
           if (leader) umma_commit(&acc_full[h]);
           if (stamp) p.dbg[((n_acc[0] - 1) * 2 + h) * 8 + 1] = clock64();
         }
@@ -320,7 +327,8 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
           tc_fence_after_sync();
           const bool stamp = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && n_full[0] <= 16;
           if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 2] = clock64();
-          if (last_half && st.n_halves == 2 && st.produces) {  // every MMA of the layer is complete: ACT is rewritten in place
+          const bool unpark = last_half && st.n_halves == 2 && st.produces;
+          if (unpark) {  // every MMA of the layer is complete: ACT is rewritten in place
             tmem_st_16(ACT_HI + lane_off + ch * 32, held_h); tmem_st_16(ACT_HI + lane_off + ch * 32 + 16, held_h + 16);
             tmem_st_16(ACT_LO + lane_off + ch * 32, held_l); tmem_st_16(ACT_LO + lane_off + ch * 32 + 16, held_l + 16);
           }
@@ -328,9 +336,13 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
           tmem_ld_32x32(acc, r0);
           tmem_ld_32x32(acc + 32, r1);
           tmem_ld_wait();
+          if (unpark) tmem_st_wait();
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[h]);  // accumulator half in registers: its next MMAs may start
+          if (lane == 0) {
+            mbar_arrive(&acc_empty[h]);                 // accumulator half in registers: its next MMAs may start
+            if (unpark) mbar_arrive(&act_lo_ready);     // the next layer's k-blocks 0,1 may start
+          }
           if (stamp) p.dbg[((n_full[0] - 1) * 2 + h) * 8 + 3] = clock64();
           if (!last_half) {
             m0 = chunk(r0, 0, held_h, held_l);
