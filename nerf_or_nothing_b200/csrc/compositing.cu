@@ -168,7 +168,7 @@ k_composite_fwd(const float* __restrict__ rgb, const float* __restrict__ density
 }
 
 template <int LPR, bool RAW>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)  // <= 80 registers: three blocks (24 warps) per SM keep the loads in flight
 k_composite_bwd(const float* __restrict__ g, const float* __restrict__ rgb, const float* __restrict__ density,
                 const float* __restrict__ t, const float* __restrict__ dirs, int R, int white, int last_mode,
                 OutputAct act, float* __restrict__ d_rgb, float* __restrict__ d_density) {
