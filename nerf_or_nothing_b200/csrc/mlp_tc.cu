@@ -267,10 +267,11 @@ class TcMlp : public MlpEngine {
       NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st));
       NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st));
     }
-    // bf16: fused chain by default.  fp32-accurate mode: the fused chain (k_mlp_fused_split<2>) moves half the bytes but is
-    // bound by its three MMA passes + epilogue tail and measures the same 3.4 ms as the HBM-bound per-layer launches, so it is
-    // opt-in (NERF_FUSED_DGRAD_SPLIT=1) and the per-layer path, which needs no extra dZ planes, stays the default.
-    if (can_fuse_forward() && getenv("NERF_NO_FUSED_DGRAD") == nullptr && (!split_ || getenv("NERF_FUSED_DGRAD_SPLIT") != nullptr))
+    // The trunk's dgrad chain is one fused kernel in both tensor-core modes.  In the fp32-accurate mode it moves half the
+    // bytes of the per-layer launches (each dZ is written once instead of written and re-read) and, since the next layer's
+    // first k-blocks run under the second-half epilogue, measures 3.24 ms against their 3.60 ms per step at configs[1].
+    // NERF_NO_FUSED_DGRAD=1 selects the per-layer launches (parity tests compare the two).
+    if (can_fuse_forward() && getenv("NERF_NO_FUSED_DGRAD") == nullptr)
       return backward_fused_chain(level, M, params, grads, d_raw_density, *cur, st);
     for (int i = C - 1; i >= 0; i--) {
       const int l = D + 1 + i;

@@ -212,14 +212,12 @@ def test_fused_dgrad_chain_matches_layered(precision, monkeypatch):
     m.set_sampling_uniforms(u)
     args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"])
     monkeypatch.delenv("NERF_NO_FUSED_DGRAD", raising=False)
-    monkeypatch.setenv("NERF_FUSED_DGRAD_SPLIT", "1")   # the fp32-accurate chain is opt-in (same speed as per-layer)
     m.GetGradient(*args)
     g1 = m.get_gradients().copy()
     monkeypatch.setenv("NERF_NO_FUSED_DGRAD", "1")
     m.GetGradient(*args)
     g2 = m.get_gradients().copy()
     monkeypatch.delenv("NERF_NO_FUSED_DGRAD")
-    monkeypatch.delenv("NERF_FUSED_DGRAD_SPLIT")
     print(f"{precision}: fused vs layered dgrad chain: grad max-norm err {rel_err(g1, g2):.2e}")
     assert np.isfinite(g1).all()
     assert rel_err(g1, g2) <= 1e-5
