@@ -107,3 +107,26 @@ def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 2 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
     else:
         assert r.returncode == 0 and "Step 3/3, Loss:" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_header_is_plain_c_and_every_entry_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/nerfb200.h must compile as C99 (what a P/Invoke, cgo or ctypes binding
+    assumes: no C++ types, no overloads, no default arguments) and every declared entry must resolve when a C host links
+    against libnerfb200.so.  The host only takes addresses and calls the two device-free entries."""
+    import subprocess
+
+    nb.lib()
+    names = sorted(_declared())
+    src = ['#include "nerfb200.h"', "#include <stdio.h>", "int main(void) {", "  const void* syms[] = {"]
+    src += [f"    (const void*)&{n}," for n in names]
+    src += ["  };", "  nerf_config c; nerf_default_config(&c);",
+            '  printf("%d %d %d %d\\n", (int)(sizeof(syms) / sizeof(syms[0])), nerf_version(), c.n_samples, (int)sizeof(nerf_config));',
+            "  return 0;", "}"]
+    c_file, exe = tmp_path / "abi_c99.c", tmp_path / "abi_c99"
+    c_file.write_text("\n".join(src) + "\n")
+    libdir = ROOT / "nerf_or_nothing_b200"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(c_file), f"-L{libdir}", "-lnerfb200",
+                        f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout.split()
+    assert out == [str(len(names)), "100", "128", str(ctypes.sizeof(nb.default_config()))], out
