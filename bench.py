@@ -164,6 +164,11 @@ def cpu_port_rate(target_seconds, rank0=True):
 
     ocfg = orc.default_config(**model_kw())
     params = orc.init_params(ocfg, 7)
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would turn the
+    # multi-threaded CPU port into a single-threaded one (only rank 0 runs this arm, the other ranks exit)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if orc.max_threads() < avail:
+        orc.set_threads(avail)
     threads = orc.max_threads()
 
     def run(n, seed):
