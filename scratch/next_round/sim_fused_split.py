@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import heapq
 import sys
-from dataclasses import dataclass, field
 
 T_MMA128, T_MMA64 = 73.0, 36.5      # cycles per tcgen05.mma M=128, N=128 / N=64 (K=16) as issued back to back
 T_TMA = 400.0                       # ring stage load latency (L2-resident weights / encodings)
@@ -43,19 +42,9 @@ class Bar:
         return (self.completed & 1) != parity
 
 
-@dataclass
 class Step:
-    n_act_kb: int
-    n_enc_kb: int
-    n_halves: int
-    produces: int
-
-
-@dataclass(order=True)
-class Ev:
-    t: float
-    seq: int
-    fn: object = field(compare=False)
+    def __init__(self, n_act_kb, n_enc_kb, n_halves, produces):
+        self.n_act_kb, self.n_enc_kb, self.n_halves, self.produces = n_act_kb, n_enc_kb, n_halves, produces
 
 
 class Sim:
@@ -83,7 +72,7 @@ class Sim:
     # ---- engine
     def at(self, t, fn):
         self.seq += 1
-        heapq.heappush(self.q, Ev(t, self.seq, fn))
+        heapq.heappush(self.q, (t, self.seq, fn))
 
     def spawn(self, name, gen):
         self.threads[name] = gen
@@ -121,9 +110,8 @@ class Sim:
 
     def run(self):
         while self.q:
-            ev = heapq.heappop(self.q)
-            self.t = ev.t
-            ev.fn()
+            self.t, _, fn = heapq.heappop(self.q)
+            fn()
         if self.threads:
             raise Deadlock(f"t={self.t:.0f}: blocked {self.blocked}")
 
