@@ -1,5 +1,5 @@
 """CPU: the mbarrier protocol of the fused split kernels (mlp_fused_split.cu) replayed in a discrete-event model
-(scratch/next_round/sim_fused_split.py: producer, MMA issuer and the eight epilogue warps as coroutines with the kernels'
+(tests/protocol_model.py: producer, MMA issuer and the eight epilogue warps as coroutines with the kernels'
 own parity expressions, a FIFO tensor pipe, hazard checks on tensor memory).  The shipped "two-instalment" schedule must be
 deadlock- and hazard-free over several tiles for the forward (skip layer, condition layer) and the dgrad chain, for every
 ring depth the kernels use, and the checker must notice a broken protocol."""
@@ -8,12 +8,12 @@ from pathlib import Path
 
 import pytest
 
-SIM = Path(__file__).resolve().parent.parent / "scratch" / "next_round" / "sim_fused_split.py"
+SIM = Path(__file__).resolve().parent / "protocol_model.py"
 
 
 def _load(text=None):
     if text is None:
-        spec = importlib.util.spec_from_file_location("sim_fused_split", SIM)
+        spec = importlib.util.spec_from_file_location("protocol_model", SIM)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         return mod.__dict__
