@@ -72,24 +72,29 @@ def algorithmic_work(R, S, levels=2):
     M = R * S * levels
     lay = layer_table()
     dense = [l for l in lay if l[0] > 4]
-    heads = [l for l in lay if l[0] <= 4]
     fwd = 2 * M * sum(o * (a + b) for o, a, b in dense)
     wgrad = fwd
     dgrad = 2 * M * sum(o * a for i, (o, a, b) in enumerate(dense) if i > 0)  # no gradient into the encodings
     n_params = sum(o * (a + b) + o for o, a, b in lay)
     return {
         "mlp_fwd_gemm": ("TFLOP/s", fwd), "mlp_wgrad_gemm": ("TFLOP/s", wgrad), "mlp_dgrad_gemm": ("TFLOP/s", dgrad),
-        "mlp_fwd_heads": ("GB/s", M * 4 * (256 + 128 + 4)), "mlp_bwd_heads": ("GB/s", M * 4 * (2 * (256 + 128) + 128 + 4 + 4)),
+        "mlp_fwd_heads": ("GB/s", M * 4 * (256 + 128 + 4)),  # fp32 CUDA-core mode only (the TC modes fuse the heads into the GEMM epilogue)
         "composite_fwd": ("GB/s", M * 24 + levels * R * 32), "composite_bwd": ("GB/s", M * 36 + levels * R * 24),
         "cast_rays+encode": ("GB/s", M * (4 + 96 * 4 + 28 * 4) + levels * R * 32),
         "adam": ("GB/s", n_params * 28), "sample_t_vals": ("GB/s", M * 8), "loss_gradient": ("GB/s", levels * R * 40),
     }, n_params
 
 
-def config_dict(R, world, precision):
+def config_dict(R, world, precision, global_batch=0):
     n_params = sum(o * (a + b) + o for o, a, b in layer_table())
-    return {"workload": f"configs[1]: 800x800 Blender-shape scene, {R}-ray batch per GPU, {N_SAMPLES}+{N_SAMPLES} samples, "
-                        f"8x256 MipNeRF MLP ({n_params} params), fp32 training",
+    if global_batch:
+        what = (f"configs[2]: same 800x800 Blender-shape scene, {global_batch}-ray global batch split over {world} GPU(s) "
+                f"({R} rays per GPU), NCCL gradient allreduce")
+    else:
+        what = f"configs[1]: 800x800 Blender-shape scene, {R}-ray batch per GPU"
+    mode = {"fp32": "fp32 training (CUDA cores)", "fp32_tc": "fp32 training (fp32-accurate bf16x3 tensor-core MLP)",
+            "bf16": "bf16 tensor-core MLP"}[precision]
+    return {"workload": f"{what}, {N_SAMPLES}+{N_SAMPLES} samples, 8x256 MipNeRF MLP ({n_params} params), {mode}",
             "rays_per_gpu": R, "global_batch": world * R, "precision": precision,
             "parallelism": f"ray-sharded dp{world}" if world > 1 else "single GPU",
             "l2": "per-step working set (activation cache, >4 GB) exceeds the 126 MB L2; no flush needed"}
@@ -118,10 +123,20 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        out = self.window(t0, t1)
+        self.close()
+        return out
+
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
+            self.proc = None
+
+    def window(self, t0, t1):
+        """clocks / throttle reasons of the samples taken in [t0, t1] (the sampler keeps running)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
@@ -209,49 +224,135 @@ def reference_arm(args):
     }))
 
 
+# ------------------------------------------------------------------------------------------------ roofline arithmetic (pure)
+
+GEMM_FAMILIES = ("mlp_fwd_gemm", "mlp_dgrad_gemm", "mlp_wgrad_gemm")
+
+
+def kernel_table(prof, steps, R, S, precision, hbm_peak, tc_peak):
+    """Per-kernel-family figures from the in-stream CUDA-event profile {name: (total ms, launches)}.
+
+    SURVEY §8(d): the MLP GEMM families are bounded by the TENSOR pipe and are reported against it — `achieved` =
+    algorithmic FLOPs (2 M sum(out x in); bias / activation / encoding FLOPs not counted) / time, `frac` = achieved /
+    measured dense bf16 peak.  Side fields say what else loads the kernel: `hbm_gbs` / `frac_hbm` (the activation /
+    gradient planes it must stream, `gemm_bytes`) and, in the fp32-accurate mode, `frac_tensor_issued` (every product is
+    three bf16 MMAs).  Everything else is bounded by HBM: algorithmic bytes / time against the measured copy bandwidth."""
+    work, _ = algorithmic_work(R, S)
+    gbytes = gemm_bytes(R, S, precision)
+    out = {}
+    for name, (ms, nl) in prof.items():
+        per_step_ms = ms / steps
+        k = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": nl / steps, "achieved": None, "unit": "GB/s", "bound": "hbm",
+             "frac": None}
+        if per_step_ms > 0:
+            if name in GEMM_FAMILIES:
+                tf = work[name][1] / 1e12 / (per_step_ms / 1e3)
+                gbs = gbytes[name] / 1e9 / (per_step_ms / 1e3)
+                k.update({"achieved": round(tf, 2), "unit": "TFLOP/s", "bound": "tensor", "frac": round(tf / tc_peak, 4),
+                          "hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
+                if precision == "fp32_tc":
+                    k["frac_tensor_issued"] = round(3 * tf / tc_peak, 4)
+            else:
+                nbytes = gbytes.get(name) or work.get(name, ("GB/s", 0))[1]
+                if nbytes:
+                    gbs = nbytes / 1e9 / (per_step_ms / 1e3)
+                    k.update({"achieved": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)})
+        out[name] = k
+    return out
+
+
+def pick_roofline(kernels, ms_step_prof, traffic_table, hbm_peak, tc_peak, peak_src):
+    """`roofline` of the JSON line: the kernel family with the largest share of the step, against ITS roof (§8(d))."""
+    top = max((k for k in kernels if kernels[k]["achieved"] is not None), key=lambda k: kernels[k]["ms_per_step"])
+    tk = kernels[top]
+    r = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": tc_peak if tk["bound"] == "tensor" else hbm_peak,
+         "unit": tk["unit"], "frac": tk["frac"], "traffic": (traffic_table or {}).get(top, {}).get("dram_bytes_per_launch"),
+         "peak_source": peak_src, "avg_launch_ms": round(tk["ms_per_step"] / max(1.0, tk["launches_per_step"]), 5),
+         "share_of_step": round(tk["ms_per_step"] / ms_step_prof, 4)}
+    for side in ("hbm_gbs", "frac_hbm", "frac_tensor_issued"):
+        if side in tk:
+            r[side] = tk[side]
+    if "frac_tensor_issued" in tk:
+        r["note"] = ("fp32-accurate mode: `achieved`/`frac` count ALGORITHMIC FLOPs; each product is three bf16 MMAs (hi*hi + lo*hi + "
+                     "hi*lo), so the tensor pipe's load is frac_tensor_issued of the measured bf16 peak")
+    return r
+
+
+def traffic_table(precision):
+    tpath = ROOT / "profiles" / "ncu_traffic.json"  # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full`
+    return json.loads(tpath.read_text()).get(precision, {}) if tpath.exists() else {}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 
 
-def ours_arm(args):
-    import torch
-    import torch.distributed as dist
+class Job:
+    """Process-wide state of a GPU arm: rank / world, torch.distributed, ONE clock sampler for every timed window."""
 
-    import nerf_or_nothing_b200 as nb
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            args.gpus = self.world
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.clocks = ClockSampler(self.local)
+        self.clocks.start()
+        time.sleep(0.25)
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        self.clocks.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def make_batches(job, R, pool=4):
     from nerf_or_nothing_b200.scene import synthetic_rays
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    R, S = args.rays, N_SAMPLES
-    cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[args.precision], device=local, **model_kw())
-    model = nb.AcceleratedMipNeRF(cfg)
-    opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes(), device=local)
-    if world > 1:
-        from nerf_or_nothing_b200 import dist as nd
-
-        nd.attach(model, device="cuda")  # rank 0's NCCL unique id -> every rank; library allreduces the flat gradient
-    stream = torch.cuda.ExternalStream(model.stream())
-
-    # a pool of distinct ray batches: host copies for e2e, device copies for `value`
-    pool = 4
     host_batches, dev_batches = [], []
     for b in range(pool):
-        rays, pix = synthetic_rays(R, width=800, height=800, seed=2024 + 1000 * rank + b)
+        rays, pix = synthetic_rays(R, width=800, height=800, seed=2024 + 1000 * job.rank + b)
         hb = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"], pix)
         host_batches.append(hb)
-        dev_batches.append(tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb))
-    lr = nb.learning_rate_decay(1000)
+        dev_batches.append(tuple(job.torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb))
+    return host_batches, dev_batches
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+
+def measure_train(job, args, precision, R, host_batches, dev_batches, want_e2e=True, want_dataset=True):
+    """configs[1] / configs[2] step at R rays per GPU in `precision`.  Region 1: the headline — K steps, device-resident
+    inputs, CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.  Region 2: the same K
+    steps with the per-kernel in-stream events.  Then e2e (host arrays in, loss out) and the resident-dataset loop."""
+    import nerf_or_nothing_b200 as nb
+
+    torch = job.torch
+    S, pool = N_SAMPLES, len(dev_batches)
+    cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[precision], device=job.local, **model_kw())
+    model = nb.AcceleratedMipNeRF(cfg)
+    opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes(), device=job.local)
+    if job.world > 1:
+        from nerf_or_nothing_b200 import dist as nd
+
+        nd.attach(model, device="cuda")  # rank 0's NCCL unique id -> every rank; the library allreduces [gradient | sum(lm) | losses]
+    stream = torch.cuda.ExternalStream(model.stream())
+    lr = nb.learning_rate_decay(1000)
 
     def dev_step(i):
         model.train_step_dev(opt, *dev_batches[i % pool], R, lr, want_loss=False)
@@ -260,9 +361,8 @@ def ours_arm(args):
         dev_step(i)
 
     def timed_region(profile):
-        """EXACTLY args.steps steps between barriers; device time from CUDA events on the library's stream, max over ranks."""
         model.set_profiling(profile)
-        sync_all()
+        job.sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = model.launch_count()
         t0 = time.time()
@@ -272,281 +372,125 @@ def ours_arm(args):
         e1.record(stream)
         model.synchronize()
         t1 = time.time()
-        sync_all()
-        tt = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()) / args.steps, model.launch_count() - l0, t0, t1
+        job.sync_all()
+        return job.max_over_ranks(e0.elapsed_time(e1)) / args.steps, model.launch_count() - l0, t0, t1
 
-    clocks = ClockSampler(local)
-    clocks.start()
-    time.sleep(0.25)
-    # region 1: the headline `value` — nothing but the step's own kernels on the stream
     ms_step, launches, t0, t1 = timed_region(False)
-    # region 2: the same K steps again with the in-stream CUDA events of the per-kernel profile (two event records per
-    # kernel family instance perturb the stream a little, so they stay out of the headline region)
     ms_step_prof, _, _, t1 = timed_region(True)
-    clk = clocks.stop(t0, t1)
+    clk = job.clocks.window(t0, t1)
     prof = model.read_profile()
     model.set_profiling(False)
-    value = world * R / (ms_step / 1e3)
+    res = {"ms_step": ms_step, "ms_step_prof": ms_step_prof, "launches": int(launches), "clocks": clk, "prof": prof,
+           "value": job.world * R / (ms_step / 1e3), "n_levels": cfg.n_levels}
 
-    # e2e: host arrays in, loss out, every step
-    for i in range(min(3, args.warmup)):
-        model.train_step(opt, *host_batches[i % pool], lr, want_loss=True)
-    sync_all()
-    w0 = time.perf_counter()
-    loss = 0.0
-    for i in range(args.steps):
-        loss = model.train_step(opt, *host_batches[i % pool], lr, want_loss=True)
-    model.synchronize()
-    w1 = time.perf_counter()
-    te = torch.tensor([(w1 - w0) * 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * R / (float(te.item()) / args.steps / 1e3)
-    h2d = R * 13 * 4
-    d2h = (1 + cfg.n_levels) * 4
+    if want_e2e:  # host arrays in, loss out, every step
+        for i in range(min(3, args.warmup)):
+            model.train_step(opt, *host_batches[i % pool], lr, want_loss=True)
+        job.sync_all()
+        w0 = time.perf_counter()
+        loss = 0.0
+        for i in range(args.steps):
+            loss = model.train_step(opt, *host_batches[i % pool], lr, want_loss=True)
+        model.synchronize()
+        ms = job.max_over_ranks((time.perf_counter() - w0) * 1e3)
+        res.update({"e2e_value": job.world * R / (ms / args.steps / 1e3), "loss": loss})
+    if want_dataset:  # the same loop fed from the device-resident BinDataset
+        from nerf_or_nothing_b200.scene import pack_records
 
-    # the same loop fed from the device-resident BinDataset: batch drawn + gathered on the GPU, loss read back
-    from nerf_or_nothing_b200.scene import pack_records
-    ds = nb.BinDataset(np.concatenate([pack_records(dict(zip(("origins", "directions", "radii", "nears", "fars", "loss_mults"), hb[:6])), hb[6])
-                                       for hb in host_batches]), device=local)
-    for i in range(min(3, args.warmup)):
-        model.train_step_dataset(opt, ds, R, 2024, lr, want_loss=True)
-    sync_all()
-    w0 = time.perf_counter()
-    for i in range(args.steps):
-        model.train_step_dataset(opt, ds, R, 2024, lr, want_loss=True)
-    model.synchronize()
-    w1 = time.perf_counter()
-    td = torch.tensor([(w1 - w0) * 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(td, op=dist.ReduceOp.MAX)
-    resident_value = world * R / (float(td.item()) / args.steps / 1e3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    hbm_peak, tc_peak, peak_src = peaks()
-    work, n_params = algorithmic_work(R, S)
-    gbytes = gemm_bytes(R, S, args.precision)
-    kernels = {}
-    for name, (ms, nl) in prof.items():
-        unit, amount = work.get(name, ("GB/s", 0))
-        per_step_ms = ms / args.steps
-        ach = (amount / 1e12 if unit == "TFLOP/s" else amount / 1e9) / (per_step_ms / 1e3) if per_step_ms > 0 and amount else None
-        peak = tc_peak if unit == "TFLOP/s" else hbm_peak
-        kernels[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": nl / args.steps,
-                         "achieved": None if ach is None else round(ach, 2), "unit": unit,
-                         "frac": None if ach is None else round(ach / peak, 4)}
-        if name in gbytes and per_step_ms > 0:
-            # a GEMM family is bounded by whichever roofline it sits closer to: the tensor pipe (FLOPs) or HBM (the
-            # activation / gradient planes it must stream; the fp32-accurate mode moves 4 B per element)
-            gbs = gbytes[name] / 1e9 / (per_step_ms / 1e3)
-            kernels[name].update({"hbm_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4), "frac_tensor": kernels[name]["frac"]})
-            if args.precision == "fp32_tc" and kernels[name]["frac_tensor"] is not None and name != "mlp_bwd_heads":
-                # every fp32-accurate product is three bf16 MMAs (hi*hi + lo*hi + hi*lo): what the tensor pipe actually issues
-                kernels[name]["frac_tensor_issued"] = round(3 * kernels[name]["frac_tensor"], 4)
-            if unit == "GB/s" or gbs / hbm_peak > (kernels[name]["frac"] or 0):
-                kernels[name].update({"achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / hbm_peak, 4)})
-    top = max((k for k in kernels if kernels[k]["achieved"] is not None), key=lambda k: kernels[k]["ms_per_step"])
-    tk = kernels[top]
-    traffic = None
-    tpath = ROOT / "profiles" / "ncu_traffic.json"
-    if tpath.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-        traffic = json.loads(tpath.read_text()).get(args.precision, {}).get(top, {}).get("dram_bytes_per_launch")
-    roofline = {"kernel": top, "bound": "tensor" if tk["unit"] == "TFLOP/s" else "hbm", "achieved": tk["achieved"],
-                "peak": tc_peak if tk["unit"] == "TFLOP/s" else hbm_peak, "unit": tk["unit"], "frac": tk["frac"],
-                "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": round(tk["ms_per_step"] / max(1.0, tk["launches_per_step"]), 5),
-                "share_of_step": round(tk["ms_per_step"] / ms_step_prof, 4)}
-    if "frac_tensor_issued" in tk:
-        roofline["tensor_issued_frac"] = tk["frac_tensor_issued"]
-        roofline["note"] = ("fp32-accurate mode: `achieved` counts algorithmic bytes / FLOPs; the tensor pipe issues 3 bf16 MMAs per "
-                            "product, so its load is tensor_issued_frac of the measured bf16 peak")
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        run, n, threads = cpu_port_rate(15.0)
-        dt = run(n, 7)
-        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{n} of {R} rays, one training step (gradient + Adam), fp32, {dt:.1f} s"}
-
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "fp32_tc": "f32 (bf16x3 tensor-core split)", "bf16": "bf16"}[args.precision],
-        "data": "synthetic",
-        "config": config_dict(R, world, args.precision),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "resident_dataset": {"value": resident_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                             "note": "nerf_mipnerf_train_step_dataset: batch drawn and gathered on the device"},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": kernels,
-        "profile_region": {"ms_per_step": round(ms_step_prof, 4),
-                           "note": "per-kernel times come from a second region of the same K steps with in-stream CUDA events"},
-        "cpu_baseline": cpu_baseline, "loss_last_step": loss,
-    }
-    emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+        keys = ("origins", "directions", "radii", "nears", "fars", "loss_mults")
+        ds = nb.BinDataset(np.concatenate([pack_records(dict(zip(keys, hb[:6])), hb[6]) for hb in host_batches]), device=job.local)
+        for i in range(min(3, args.warmup)):
+            model.train_step_dataset(opt, ds, R, 2024, lr, want_loss=True)
+        job.sync_all()
+        w0 = time.perf_counter()
+        for i in range(args.steps):
+            model.train_step_dataset(opt, ds, R, 2024, lr, want_loss=True)
+        model.synchronize()
+        ms = job.max_over_ranks((time.perf_counter() - w0) * 1e3)
+        res["resident_value"] = job.world * R / (ms / args.steps / 1e3)
+        del ds
+    if job.world > 1:
+        # replicated training is only correct if every rank holds the same bits: compare a checksum of the parameters
+        p = model.get_params()
+        mine = torch.tensor([int(np.frombuffer(p.tobytes(), np.uint32).astype(np.uint64).sum() & 0x7FFFFFFFFFFFFFFF)], device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(job.world)]
+        job.dist.all_gather(allv, mine)
+        res["dp_check"] = bool(all(int(v.item()) == int(allv[0].item()) for v in allv))
+        if not res["dp_check"]:
+            raise RuntimeError("data-parallel check failed: parameters differ between ranks after the timed steps")
+    model.close(); opt.close()
+    torch.cuda.empty_cache()
+    return res
 
 
-def render_arm(args):
-    """configs[3]: full-image 800x800 render (640 000 rays, 128+128 samples), forward only, rays split over the ranks;
-    no collective.  value = render rays/s with the rays resident on the device; e2e = host arrays in, host image out."""
-    import torch
-    import torch.distributed as dist
-
+def measure_render(job, args, precision, steps=None):
+    """configs[3]: one 800x800 view = 640 000 rays, 128+128 samples, forward only, rays split over the ranks, no collective."""
     import nerf_or_nothing_b200 as nb
     from nerf_or_nothing_b200 import dist as nd
     from nerf_or_nothing_b200.scene import synthetic_rays
 
-    rank, world, local = nd.env_rank_world()
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    total = 640000
-    lo, hi = nd.shard_range(total, rank, world)
+    torch = job.torch
+    steps = steps or args.steps
+    total, chunk = 640000, 16384
+    lo, hi = nd.shard_range(total, job.rank, job.world)
     n = hi - lo
-    chunk = 16384
-    cfg = nb.default_config(n_rays=chunk, precision=nb.PRECISIONS[args.precision], device=local, randomized=0, **model_kw())
+    cfg = nb.default_config(n_rays=chunk, precision=nb.PRECISIONS[precision], device=job.local, **model_kw())
     model = nb.AcceleratedMipNeRF(cfg)
-    rays, _ = synthetic_rays(n, width=800, height=800, n_views=1, seed=7 + rank)
+    rays, _ = synthetic_rays(n, width=800, height=800, n_views=1, seed=7 + job.rank)
     hb = [rays[k] for k in ("origins", "directions", "radii", "nears", "fars")]
     db = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb]
     rgb, depth, acc = torch.empty(n, 3, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
     stream = torch.cuda.ExternalStream(model.stream())
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(max(1, args.warmup // 3)):
+    for _ in range(3):  # >= 3 untimed passes
         model.render_dev(*db, n, rgb, depth, acc)
     model.set_profiling(True)
-    sync_all()
+    job.sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = model.launch_count()
+    t0 = time.time()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         model.render_dev(*db, n, rgb, depth, acc)
     e1.record(stream)
     model.synchronize()
-    sync_all()
+    t1 = time.time()
+    job.sync_all()
     prof = model.read_profile()
     launches = model.launch_count() - l0
-    tt = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = float(tt.item()) / args.steps
+    ms = job.max_over_ranks(e0.elapsed_time(e1)) / steps
     w0 = time.perf_counter()
-    out = model.render(*hb)
-    w1 = time.perf_counter()
-    te = torch.tensor([(w1 - w0) * 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        hbm_peak, tc_peak, peak_src = peaks()
-        work, n_params = algorithmic_work(n, N_SAMPLES)
-        fwd_ms = prof.get("mlp_fwd_gemm", (0, 0))[0] / args.steps
-        ach = work["mlp_fwd_gemm"][1] / 1e12 / (fwd_ms / 1e3) if fwd_ms else None
-        emit(({
-            "metric": "render rays/sec (forward only)", "value": total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "configs[3]: full-image 800x800 render (640000 rays, 128+128 samples), forward only, rays split "
-                                   f"across {world} GPU(s)", "rays_per_gpu": n, "chunk_rays": chunk, "precision": args.precision},
-            "e2e": {"value": total / (float(te.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n * 5 * 4},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "mlp_fwd_gemm", "bound": "tensor", "achieved": None if ach is None else round(ach, 2), "peak": tc_peak,
-                         "unit": "TFLOP/s", "frac": None if ach is None else round(ach / tc_peak, 4), "traffic": None, "peak_source": peak_src},
-            "kernels": {k: {"ms_per_step": round(v[0] / args.steps, 4), "launches_per_step": v[1] / args.steps} for k, v in prof.items()},
-        }))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def sweep_arm(args):
-    """configs[4]: MLP (depth x width) x batch sweep on one GPU — tensor-pipe throughput of the GEMM families and HBM GB/s of
-    compositing fwd/bwd against the roofline.  One JSON line per cell (not the driver's headline line)."""
-    import torch
-
-    import nerf_or_nothing_b200 as nb
-    from nerf_or_nothing_b200.scene import synthetic_rays
-
-    torch.cuda.set_device(0)
+    model.render(*hb)
+    ms_e2e = job.max_over_ranks((time.perf_counter() - w0) * 1e3)
+    clk = job.clocks.window(t0, t1)
     hbm_peak, tc_peak, peak_src = peaks()
-    cells = [(d, w, r) for (d, w) in ((4, 128), (8, 256), (8, 512)) for r in (4096, 16384, 65536)]
-    for depth, width, R in cells:
-        kw = dict(n_samples=N_SAMPLES, net_depth=depth, net_width=width, net_depth_condition=1, net_width_condition=width // 2,
-                  skip_layer=4, deg_point=16, deg_view=4)
-        try:
-            cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[args.precision], **kw)
-            model = nb.AcceleratedMipNeRF(cfg)
-            opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes())
-            rays, pix = synthetic_rays(R, width=800, height=800, seed=1)
-            hb = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"], pix)
-            db = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb)
-            for _ in range(3):
-                model.train_step_dev(opt, *db, R, 1e-4)
-            model.set_profiling(True)
-            stream = torch.cuda.ExternalStream(model.stream())
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            steps = 3
-            e0.record(stream)
-            for _ in range(steps):
-                model.train_step_dev(opt, *db, R, 1e-4)
-            e1.record(stream)
-            model.synchronize()
-            ms = e0.elapsed_time(e1) / steps
-            prof = model.read_profile()
-            P, Dd, Wc = 96, 27, width // 2
-            lay = [(width, P, 0)] + [(width, width, P if (i % 4 == 0) else 0) for i in range(1, depth)] + [(Wc, width, Dd)]
-            M = R * N_SAMPLES * 2
-            fwd = 2 * M * sum(o * (a + b) for o, a, b in lay)
-            dgr = 2 * M * sum(o * a for i, (o, a, b) in enumerate(lay) if i > 0)
-
-            def tf(name, flops):
-                t = prof.get(name, (0, 0))[0] / steps
-                return round(flops / 1e12 / (t / 1e3), 1) if t > 0 else None
-
-            def gb(name, nbytes):
-                t = prof.get(name, (0, 0))[0] / steps
-                return round(nbytes / 1e9 / (t / 1e3), 1) if t > 0 else None
-
-            cf, cb = gb("composite_fwd", M * 24 + 2 * R * 32), gb("composite_bwd", M * 36 + 2 * R * 24)
-            emit(({"sweep": f"{depth}x{width}", "rays": R, "precision": args.precision, "ms_per_step": round(ms, 3),
-                              "train_rays_per_s": round(R / (ms / 1e3)), "chunk_launches_composite": prof.get("composite_fwd", (0, 0))[1] / steps,
-                              "fwd_tflops": tf("mlp_fwd_gemm", fwd), "dgrad_tflops": tf("mlp_dgrad_gemm", dgr), "wgrad_tflops": tf("mlp_wgrad_gemm", fwd),
-                              "tensor_peak_tflops": tc_peak, "composite_fwd_gbs": cf, "composite_bwd_gbs": cb, "hbm_peak_gbs": hbm_peak,
-                              "composite_fwd_frac": None if cf is None else round(cf / hbm_peak, 3),
-                              "composite_bwd_frac": None if cb is None else round(cb / hbm_peak, 3), "peak_source": peak_src}))
-            model.close(); opt.close()
-            del db
-            torch.cuda.empty_cache()
-        except Exception as e:  # a cell that does not fit is reported, not fatal
-            emit({"sweep": f"{depth}x{width}", "rays": R, "error": str(e)[:200]})
+    work, _ = algorithmic_work(n, N_SAMPLES)
+    fwd_ms = prof.get("mlp_fwd_gemm", (0, 0))[0] / steps
+    ach = work["mlp_fwd_gemm"][1] / 1e12 / (fwd_ms / 1e3) if fwd_ms else None
+    model.close()
+    del db, rgb, depth, acc
+    torch.cuda.empty_cache()
+    return {"value": total / (ms / 1e3), "unit": UNIT, "ms_per_image": ms, "steps": steps, "precision": precision, "rays": total,
+            "rays_per_gpu": n, "chunk_rays": chunk, "gpu_launches": int(launches), "clocks": clk,
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n * 5 * 4},
+            "roofline": {"kernel": "mlp_fwd_gemm", "bound": "tensor", "achieved": None if ach is None else round(ach, 2), "peak": tc_peak,
+                         "unit": "TFLOP/s", "frac": None if ach is None else round(ach / tc_peak, 4), "traffic": None, "peak_source": peak_src,
+                         "share_of_step": round(fwd_ms / ms, 4) if ms else None},
+            "kernels": {k: {"ms_per_step": round(v[0] / steps, 4), "launches_per_step": v[1] / steps} for k, v in prof.items()}}
 
 
-def compositing_arm(args):
+def measure_compositing(job, args, sizes=(65536, 262144), steps=None, warmup=None):
     """The two HBM-bound per-ray kernels alone, against the copy-bandwidth roofline (north_star: >= 70 % of HBM peak):
     `nerf_volumetric_rendering_async` / `nerf_volumetric_rendering_gradient_async` launched back to back on one stream,
     S = 128 samples per ray, R rays per launch, inputs larger than the 126 MB L2 (R*S*20 B >= 168 MB), timed with CUDA events
     on that stream.  Two forms: `activated` = the reference kernels' contract (.cu:318-344, 362-402: sigma and rgb in),
     `raw` = what the training step runs (softplus / sigmoid and their derivatives fused).  Algorithmic bytes: SURVEY §8(d),
-    fwd 24 B/sample + 32 B/ray, bwd 36 B/sample + 24 B/ray.  One JSON line."""
+    fwd 24 B/sample + 32 B/ray, bwd 36 B/sample + 24 B/ray."""
     import ctypes as C
-
-    import torch
 
     import nerf_or_nothing_b200 as nb
 
-    torch.cuda.set_device(0)
+    torch = job.torch
+    steps, warmup = steps or args.steps, warmup or args.warmup
     hbm_peak, _, peak_src = peaks()
     S = N_SAMPLES
     lib = nb.lib()
@@ -555,11 +499,8 @@ def compositing_arm(args):
     P = lambda x: C.c_void_p(x.data_ptr())
     cells = []
     launches = 0
-    clocks = ClockSampler(0)
-    clocks.start()
-    time.sleep(0.25)
     t_begin = time.time()
-    for R in (65536, 262144):
+    for R in sizes:
         gen = torch.Generator(device="cuda").manual_seed(R)
         raw_rgb = torch.randn(R, S, 3, device="cuda", generator=gen) * 2.0
         raw_den = torch.randn(R, S, device="cuda", generator=gen) * 3.0 - 1.0
@@ -581,33 +522,187 @@ def compositing_arm(args):
                                                                       raw, 0.0, 0.0, sp))
 
             for name, fn, nbytes in (("composite_fwd", fwd, R * S * 24 + R * 32), ("composite_bwd", bwd, R * S * 36 + R * 24)):
-                for _ in range(args.warmup):
+                for _ in range(warmup):
                     fn()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 st.synchronize()
                 e0.record(st)
-                for _ in range(args.steps):
+                for _ in range(steps):
                     fn()
                 e1.record(st)
                 st.synchronize()
-                us = e0.elapsed_time(e1) * 1e3 / args.steps
-                launches += args.steps
+                us = e0.elapsed_time(e1) * 1e3 / steps
+                launches += steps
                 gbs = nbytes / 1e9 / (us / 1e6)
                 cells.append({"kernel": name, "form": form, "rays": R, "samples": S, "us_per_launch": round(us, 2),
                               "algorithmic_bytes": nbytes, "achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / hbm_peak, 4)})
         assert torch.isfinite(comp).all() and torch.isfinite(d_den).all()
         del raw_rgb, raw_den, act_rgb, act_den, t, w, d_rgb, d_den
         torch.cuda.empty_cache()
-    clk = clocks.stop(t_begin, time.time())
-    head = [c for c in cells if c["rays"] == 262144 and c["form"] == "raw"]
+    clk = job.clocks.window(t_begin, time.time())
+    head = [c for c in cells if c["rays"] == max(sizes) and c["form"] == "raw"]
     worst = min(head, key=lambda c: c["frac"])
+    return {"worst": worst, "cells": cells, "clocks": clk, "gpu_launches": launches, "steps": steps,
+            "roofline": {"kernel": worst["kernel"], "bound": "hbm", "achieved": worst["achieved"], "peak": hbm_peak, "unit": "GB/s",
+                         "frac": worst["frac"], "traffic": None, "peak_source": peak_src}}
+
+
+def train_record(res, args, R, precision, job):
+    """roofline + kernel table of one measure_train() result."""
+    hbm_peak, tc_peak, peak_src = peaks()
+    kernels = kernel_table(res["prof"], args.steps, R, N_SAMPLES, precision, hbm_peak, tc_peak)
+    roofline = pick_roofline(kernels, res["ms_step_prof"], traffic_table(precision), hbm_peak, tc_peak, peak_src)
+    return kernels, roofline
+
+
+def ours_arm(args):
+    job = Job(args)
+    R = args.rays if not args.global_batch else args.global_batch // job.world
+    host_batches, dev_batches = make_batches(job, R)
+    res = measure_train(job, args, args.precision, R, host_batches, dev_batches)
+    kernels, roofline = train_record(res, args, R, args.precision, job)
+    extra = {}
+    if not args.no_extras:
+        # the other configurations of BASELINE.json's metric, measured in the same process with their own clock windows:
+        # configs[2] (bf16 tensor-core mode; at N ranks this is the N x R-ray global batch with the NCCL allreduce),
+        # configs[3] (render of one 800x800 view split over the ranks) and, on one GPU, configs[4]'s compositing cells
+        other = "bf16" if args.precision != "bf16" else "fp32_tc"
+        o = measure_train(job, args, other, R, host_batches, dev_batches, want_e2e=True, want_dataset=False)
+        ok, orf = train_record(o, args, R, other, job)
+        extra["modes"] = {other: {"value": o["value"], "unit": UNIT, "ms_per_step": o["ms_step"], "e2e": {"value": o["e2e_value"], "unit": UNIT},
+                                  "gpu_launches": o["launches"], "clocks": o["clocks"], "roofline": orf, "dp_check": o.get("dp_check"),
+                                  "kernels": {k: {f: v[f] for f in ("ms_per_step", "achieved", "unit", "frac")} for k, v in ok.items()
+                                              if v["ms_per_step"] >= 0.02}}}
+        extra["render"] = {p: {k: v for k, v in measure_render(job, args, p, steps=3).items() if k != "kernels"} for p in ("bf16", "fp32_tc")}
+        if job.world == 1:
+            c = measure_compositing(job, args, sizes=(262144,), steps=20, warmup=5)
+            extra["compositing"] = {"worst": c["worst"], "clocks": c["clocks"], "cells": c["cells"],
+                                    "note": "stand-alone launches, 262144 rays x 128 samples (inputs > L2); `worst` = slower of fwd/bwd in the raw form"}
+    if job.rank != 0:
+        job.close()
+        return
+    cpu_baseline = None
+    if job.world == 1 and not args.no_cpu_baseline:
+        run, n, threads = cpu_port_rate(15.0)
+        dt = run(n, 7)
+        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n} of {R} rays, one training step (gradient + Adam), fp32, {dt:.1f} s"}
+    out = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": job.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_step"], "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "fp32_tc": "f32 (bf16x3 tensor-core split)", "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": config_dict(R, job.world, args.precision, args.global_batch),
+        "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": R * 13 * 4, "d2h_bytes_per_step": (1 + res["n_levels"]) * 4},
+        "resident_dataset": {"value": res["resident_value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": (1 + res["n_levels"]) * 4,
+                             "note": "nerf_mipnerf_train_step_dataset: batch drawn and gathered on the device"},
+        "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roofline, "kernels": kernels,
+        "profile_region": {"ms_per_step": round(res["ms_step_prof"], 4),
+                           "note": "per-kernel times come from a second region of the same K steps with in-stream CUDA events"},
+        "cpu_baseline": cpu_baseline, "loss_last_step": res["loss"],
+    }
+    if job.world > 1:
+        out["dp_check"] = res["dp_check"]  # parameters bit-identical on every rank after the timed steps
+    out.update(extra)
+    emit(out)
+    job.close()
+
+
+def render_arm(args):
+    """configs[3] as a line of its own.  value = render rays/s with the rays resident on the device; e2e = host arrays in,
+    host image out."""
+    job = Job(args)
+    r = measure_render(job, args, args.precision)
+    if job.rank == 0:
+        emit({"metric": "render rays/sec (forward only)", "value": r["value"], "unit": UNIT, "n_gpus": job.world, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": r["ms_per_image"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": args.precision, "data": "synthetic",
+              "config": {"workload": "configs[3]: full-image 800x800 render (640000 rays, 128+128 samples), forward only, rays split "
+                                     f"across {job.world} GPU(s)", "rays_per_gpu": r["rays_per_gpu"], "chunk_rays": r["chunk_rays"],
+                         "precision": args.precision, "l2": "per-chunk working set (>1 GB of encodings / heads) exceeds the 126 MB L2; no flush needed"},
+              "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "roofline": r["roofline"], "kernels": r["kernels"]})
+    job.close()
+
+
+def sweep_arm(args):
+    """configs[4]: MLP (depth x width) x batch sweep on one GPU — tensor-pipe throughput of the GEMM families and HBM GB/s of
+    compositing fwd/bwd against the roofline.  One JSON line per cell (not the driver's headline line), each with the
+    clocks sampled during its own timed region."""
+    import nerf_or_nothing_b200 as nb
+    from nerf_or_nothing_b200.scene import synthetic_rays
+
+    job = Job(args)
+    torch = job.torch
+    hbm_peak, tc_peak, peak_src = peaks()
+    cells = [(d, w, r) for (d, w) in ((4, 128), (8, 256), (8, 512)) for r in (4096, 16384, 65536)]
+    for depth, width, R in cells:
+        kw = dict(n_samples=N_SAMPLES, net_depth=depth, net_width=width, net_depth_condition=1, net_width_condition=width // 2,
+                  skip_layer=4, deg_point=16, deg_view=4)
+        try:
+            cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[args.precision], **kw)
+            model = nb.AcceleratedMipNeRF(cfg)
+            opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes())
+            rays, pix = synthetic_rays(R, width=800, height=800, seed=1)
+            hb = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"], pix)
+            db = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in hb)
+            for _ in range(3):
+                model.train_step_dev(opt, *db, R, 1e-4)
+            model.set_profiling(True)
+            stream = torch.cuda.ExternalStream(model.stream())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = max(3, min(20, int(0.4 / (2e-6 * R * (width / 256) ** 2 + 1e-3))))  # ~0.4 s per cell: enough nvidia-smi samples
+            model.synchronize()
+            t0 = time.time()
+            e0.record(stream)
+            for _ in range(steps):
+                model.train_step_dev(opt, *db, R, 1e-4)
+            e1.record(stream)
+            model.synchronize()
+            t1 = time.time()
+            ms = e0.elapsed_time(e1) / steps
+            prof = model.read_profile()
+            P, Dd, Wc = 96, 27, width // 2
+            lay = [(width, P, 0)] + [(width, width, P if (i % 4 == 0) else 0) for i in range(1, depth)] + [(Wc, width, Dd)]
+            M = R * N_SAMPLES * 2
+            fwd = 2 * M * sum(o * (a + b) for o, a, b in lay)
+            dgr = 2 * M * sum(o * a for i, (o, a, b) in enumerate(lay) if i > 0)
+
+            def tf(name, flops):
+                t = prof.get(name, (0, 0))[0] / steps
+                return round(flops / 1e12 / (t / 1e3), 1) if t > 0 else None
+
+            def gb(name, nbytes):
+                t = prof.get(name, (0, 0))[0] / steps
+                return round(nbytes / 1e9 / (t / 1e3), 1) if t > 0 else None
+
+            cf, cb = gb("composite_fwd", M * 24 + 2 * R * 32), gb("composite_bwd", M * 36 + 2 * R * 24)
+            tfs = {k: tf(n, f) for k, n, f in (("fwd", "mlp_fwd_gemm", fwd), ("dgrad", "mlp_dgrad_gemm", dgr), ("wgrad", "mlp_wgrad_gemm", fwd))}
+            emit(({"sweep": f"{depth}x{width}", "rays": R, "precision": args.precision, "ms_per_step": round(ms, 3), "steps": steps,
+                   "train_rays_per_s": round(R / (ms / 1e3)), "chunk_launches_composite": prof.get("composite_fwd", (0, 0))[1] / steps,
+                   "fwd_tflops": tfs["fwd"], "dgrad_tflops": tfs["dgrad"], "wgrad_tflops": tfs["wgrad"],
+                   "tensor_frac": {k: None if v is None else round(v / tc_peak, 3) for k, v in tfs.items()},
+                   "tensor_peak_tflops": tc_peak, "composite_fwd_gbs": cf, "composite_bwd_gbs": cb, "hbm_peak_gbs": hbm_peak,
+                   "composite_fwd_frac": None if cf is None else round(cf / hbm_peak, 3),
+                   "composite_bwd_frac": None if cb is None else round(cb / hbm_peak, 3), "peak_source": peak_src,
+                   "clocks": job.clocks.window(t0, t1)}))
+            model.close(); opt.close()
+            del db
+            torch.cuda.empty_cache()
+        except Exception as e:  # a cell that does not fit is reported, not fatal
+            emit({"sweep": f"{depth}x{width}", "rays": R, "error": str(e)[:200]})
+    job.close()
+
+
+def compositing_arm(args):
+    job = Job(args)
+    c = measure_compositing(job, args)
+    worst = c["worst"]
     emit({"metric": "compositing fwd/bwd GB/s vs HBM roofline", "value": worst["achieved"], "unit": "GB/s", "n_gpus": 1,
           "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
           "config": {"workload": "configs[4] compositing cells: S=128, 65536 / 262144 rays per launch, inputs larger than L2 (no flush)",
                      "value_is": "the slower of fwd/bwd in the form the training step runs (raw), 262144 rays"},
-          "roofline": {"kernel": worst["kernel"], "bound": "hbm", "achieved": worst["achieved"], "peak": hbm_peak, "unit": "GB/s",
-                       "frac": worst["frac"], "traffic": None, "peak_source": peak_src},
-          "gpu_launches": launches, "clocks": clk, "cells": cells})
+          "roofline": c["roofline"], "gpu_launches": c["gpu_launches"], "clocks": c["clocks"], "cells": c["cells"]})
+    job.close()
 
 
 _REAL_STDOUT = None
@@ -639,11 +734,16 @@ def main():
                     help="fp32_tc (default): fp32-accurate bf16x3 split on tcgen05; fp32: CUDA-core FFMA; bf16: configs[2] mode")
     ap.add_argument("--mode", default="train", choices=["train", "render", "sweep", "compositing"],
                     help="render: configs[3], forward only; sweep: configs[4]; compositing: the per-ray kernels alone vs the HBM roofline")
-    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="configs[2] strong scaling: total rays per step, split evenly over the ranks (overrides --rays)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline configuration (no modes / render / compositing sub-records)")
     ap.add_argument("--profiler-run", action="store_true", help="under ncu only: do not raise --warmup to 3 (the line printed is not a bench value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" and not args.profiler_run else args.warmup
+    if args.profiler_run:
+        args.no_extras = True
     if args.impl == "reference":
         reference_arm(args)
     elif args.mode == "render":

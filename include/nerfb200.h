@@ -65,7 +65,15 @@ typedef struct nerf_config {
   float coarse_loss_mult;  /* 0.1 (.cu:345)                                               */
   float resample_padding;  /* 0.01 (.cu:243)                                              */
   uint64_t seed;           /* weights + sampling RNG (reference: time(nullptr), A-D7)     */
+  uint32_t engine_flags;   /* NERF_FLAG_*: A/B switches of the tensor-core engine (0 = the shipped schedule) */
 } nerf_config;
+
+/* engine_flags: bits 0-3 select the slower, simpler path the default replaced (parity tests compare the two); bit 4 an alternative schedule. */
+#define NERF_FLAG_NO_FUSED_FORWARD 1u       /* render / forward-only: one GEMM launch per layer instead of the fused kernel */
+#define NERF_FLAG_NO_FUSED_TRAIN_FORWARD 2u /* training forward: per-layer launches */
+#define NERF_FLAG_NO_FUSED_DGRAD 4u         /* backward: per-layer dgrad launches instead of the fused chain */
+#define NERF_FLAG_NO_DEFERRED_REDUCE 8u     /* wgrad partial tiles reduced by a launch of their own */
+#define NERF_FLAG_QUARTER_SCHEDULE 16u      /* fp32-accurate fused kernels: quarter-granular accumulators, two-phase k order */
 
 typedef struct nerf_mipnerf nerf_mipnerf;   /* AcceleratedMipNeRF + its embedded AcceleratedMLP */
 typedef struct nerf_adam nerf_adam;         /* AcceleratedAdamOptimizer */
@@ -116,8 +124,10 @@ int nerf_mipnerf_get_gradient_dev(nerf_mipnerf* h, const float* origins3_dev,
                                   const float* directions3_dev, const float* radii_dev,
                                   const float* nears_dev, const float* fars_dev,
                                   const float* loss_mults_dev, const float* pixels3_dev, int n_rays);
-/* forward only (SN/MipNerfModel.cs:36-97), any n_rays (chunked by cfg.n_rays); outputs of the LAST
- * level on the host; any output may be NULL.  The reference has no render entry (SN/Dataset.cs:107). */
+/* forward only (SN/MipNerfModel.cs:36-97), any n_rays (processed in passes of chunk_rays rays); outputs of the
+ * LAST level on the host; any output may be NULL.  Evaluation is deterministic whatever cfg.randomized says
+ * (bin midpoints, no jitter; explicit sampling uniforms are ignored), so two renders of the same rays are
+ * bitwise equal and do not consume training RNG counters.  The reference has no render entry (SN/Dataset.cs:107). */
 int nerf_mipnerf_render(nerf_mipnerf* h, const float* origins3, const float* directions3,
                         const float* radii, const float* nears, const float* fars, long n_rays,
                         float* rgb3, float* depth, float* acc);
@@ -152,6 +162,11 @@ int nerf_mlp_get_output(nerf_mipnerf* h, const float* enc_pos_dev, const float* 
 int nerf_mlp_get_gradient(nerf_mipnerf* h, const float* color_grad_dev, const float* density_grad_dev,
                           int level, float** grad_dev_ptrs);
 int nerf_mlp_reset_gradients(nerf_mipnerf* h, int level); /* ANU/AcceleratedMLP.cpp:113-129 (A-D4) */
+/* Parity hook on the cached activations (the reference exposes them as the weighted_sums_ / outputs_ buffers,
+ * ANU/AcceleratedMLP.h:35-44): the ReLU masks the backward pass of `level` uses, hidden layer `layer` (trunk
+ * 0..depth-1, then the condition layers), as a device bit plane [rows, words_per_row] — bit j of word c of row m
+ * <=> output[m, 32 c + j] > 0.  Tensor-core precision modes only (NERF_ERR_STATE otherwise). */
+int nerf_mlp_relu_bits(nerf_mipnerf* h, int level, int layer, uint64_t* bits_dev, int* words_per_row);
 
 /* ---- AcceleratedAdamOptimizer (ANU/AcceleratedAdamOptimizer.h:5-20) -------------------------------- */
 int nerf_adam_create(const int* sizes, int n, int eps_mode, int device, nerf_adam** out); /* .cpp:6-21, m=v=0 (A-D14) */
@@ -190,8 +205,12 @@ int nerf_mipnerf_train_step_dev(nerf_mipnerf* h, nerf_adam* a, const float* orig
 /* ---- multi-GPU: rays sharded per rank, ONE exchange per step -------------------------- */
 #define NERF_COMM_ID_BYTES 128
 int nerf_comm_get_unique_id(void* id_out); /* rank 0; ship the bytes to the other ranks */
-/* attach rank `rank` of `world` to the model: every get_gradient then uses the GLOBAL sum(loss_mults)
- * and train_step allreduces (NCCL sum, fp32) the flat gradient before Adam. */
+/* attach rank `rank` of `world` to the model.  A step then has exactly ONE collective: each rank accumulates its
+ * gradient UN-normalised (g = 2 lm (rgb - pix) lambda), the local sum(loss_mults) and the per-level loss numerators
+ * ride as the last 1 + n_levels floats of the flat gradient buffer, one ncclAllReduce(sum, fp32) covers all of it, and
+ * the global 1 / sum(loss_mults) is applied inside the Adam pass (train_step) or by nerf_mipnerf_allreduce_gradients
+ * (GetGradient + explicit allreduce + nerf_adam_step).  After either, the gradient buffers hold the global mean
+ * gradient and nerf_mipnerf_get_loss returns the GLOBAL loss on every rank. */
 int nerf_mipnerf_comm_init(nerf_mipnerf* h, const void* id, int rank, int world);
 int nerf_mipnerf_allreduce_gradients(nerf_mipnerf* h);
 int nerf_mipnerf_comm_destroy(nerf_mipnerf* h);

@@ -28,6 +28,8 @@ PRECISION_FP32_TC = 1
 PRECISION_BF16_TC = 2
 PRECISIONS = {"fp32": PRECISION_FP32, "fp32_tc": PRECISION_FP32_TC, "bf16": PRECISION_BF16_TC, "bf16_tc": PRECISION_BF16_TC}
 COMM_ID_BYTES = 128
+# nerf_config.engine_flags (include/nerfb200.h)
+FLAG_NO_FUSED_FORWARD, FLAG_NO_FUSED_TRAIN_FORWARD, FLAG_NO_FUSED_DGRAD, FLAG_NO_DEFERRED_REDUCE, FLAG_QUARTER_SCHEDULE = 1, 2, 4, 8, 16
 
 
 class NerfError(RuntimeError):
@@ -44,7 +46,7 @@ class NerfConfig(C.Structure):
         ("randomized", C.c_int), ("adam_eps_mode", C.c_int), ("last_sample_mode", C.c_int),
         ("precision", C.c_int), ("device", C.c_int), ("chunk_rays", C.c_int),
         ("density_bias", C.c_float), ("rgb_padding", C.c_float), ("coarse_loss_mult", C.c_float),
-        ("resample_padding", C.c_float), ("seed", C.c_uint64),
+        ("resample_padding", C.c_float), ("seed", C.c_uint64), ("engine_flags", C.c_uint32),
     ]
 
 
@@ -84,6 +86,7 @@ _SIGNATURES = {
     "nerf_mlp_get_output": [_VP, _VP, _VP, _I, _I, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     "nerf_mlp_get_gradient": [_VP, _VP, _VP, _I, C.POINTER(_VP)],
     "nerf_mlp_reset_gradients": [_VP, _I],
+    "nerf_mlp_relu_bits": [_VP, _I, _I, C.POINTER(C.c_uint64), C.POINTER(_I)],
     "nerf_adam_create": [C.POINTER(_I), _I, _I, _I, C.POINTER(_VP)],
     "nerf_adam_step": [_VP, C.POINTER(_VP), C.POINTER(_VP), _F],
     "nerf_adam_state": [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_L), C.POINTER(_I)],
@@ -216,6 +219,12 @@ class AcceleratedMLP:
 
     def reset_gradients(self, level=0):  # ANU/AcceleratedMLP.cpp:113-129
         check(lib().nerf_mlp_reset_gradients(self._m._h, level))
+
+    def relu_bits(self, level, layer):
+        """(device pointer, words per row) of the ReLU bit plane of hidden layer `layer` cached by the last forward of `level`."""
+        p, w = C.c_uint64(), C.c_int()
+        check(lib().nerf_mlp_relu_bits(self._m._h, level, layer, C.byref(p), C.byref(w)))
+        return p.value, w.value
 
 
 class AcceleratedMipNeRF:

@@ -5,6 +5,8 @@
 // allocation here, so the step is a single 128-bit vectorised elementwise pass: 28 B/param of HBM
 // traffic (read p,g,m,v; write p,m,v).  `grad_scale` lets the data-parallel path fold a gradient
 // rescale into the same pass.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace nerf {
@@ -19,20 +21,27 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   else p -= lr * mh / (sqrtf(vh) + 1e-8f);               // SN/TrainState.cs:34
 }
 
+// DP: gs = 1 / *gs_dev (global sum of loss multipliers, allreduced with the gradient) and the normalised gradient
+// is written back, so the buffers the host sees after the step hold the global mean gradient.
+template <bool DP>
 __global__ void __launch_bounds__(256)
-k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-       float lr, float b1, float b2, float inv1, float inv2, int eps_mode, float gs) {
+k_adam(float* __restrict__ p, typename std::conditional<DP, float*, const float*>::type __restrict__ g, float* __restrict__ m,
+       float* __restrict__ v, long n, float lr, float b1, float b2, float inv1, float inv2, int eps_mode, float gs,
+       const float* __restrict__ gs_dev) {
+  if (DP) gs = 1.0f / *gs_dev;
   const long n4 = n >> 2;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    gg.x *= gs; gg.y *= gs; gg.z *= gs; gg.w *= gs;
+    if (DP) reinterpret_cast<float4*>(const_cast<float*>(g))[i] = gg;
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    adam_one(pp.x, gg.x * gs, mm.x, vv.x, lr, b1, b2, inv1, inv2, eps_mode);
-    adam_one(pp.y, gg.y * gs, mm.y, vv.y, lr, b1, b2, inv1, inv2, eps_mode);
-    adam_one(pp.z, gg.z * gs, mm.z, vv.z, lr, b1, b2, inv1, inv2, eps_mode);
-    adam_one(pp.w, gg.w * gs, mm.w, vv.w, lr, b1, b2, inv1, inv2, eps_mode);
+    adam_one(pp.x, gg.x, mm.x, vv.x, lr, b1, b2, inv1, inv2, eps_mode);
+    adam_one(pp.y, gg.y, mm.y, vv.y, lr, b1, b2, inv1, inv2, eps_mode);
+    adam_one(pp.z, gg.z, mm.z, vv.z, lr, b1, b2, inv1, inv2, eps_mode);
+    adam_one(pp.w, gg.w, mm.w, vv.w, lr, b1, b2, inv1, inv2, eps_mode);
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -42,7 +51,9 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
   if (blockIdx.x == 0 && threadIdx.x < n - tail0) {
     const long i = tail0 + threadIdx.x;
     float pp = p[i], mm = m[i], vv = v[i];
-    adam_one(pp, g[i] * gs, mm, vv, lr, b1, b2, inv1, inv2, eps_mode);
+    const float gi = g[i] * gs;
+    if (DP) const_cast<float*>(g)[i] = gi;
+    adam_one(pp, gi, mm, vv, lr, b1, b2, inv1, inv2, eps_mode);
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
@@ -128,7 +139,18 @@ int launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, 
   // 148 SMs x 8 resident 256-thread blocks, capped by the work available
   const long want = cdiv(n >> 2, 256);
   const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-  k_adam<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, inv1, inv2, eps_mode, grad_scale);
+  k_adam<false><<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, inv1, inv2, eps_mode, grad_scale, nullptr);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_adam_dp(float* p, float* g, float* m, float* v, long n, float lr, float b1, float b2, float inv1, float inv2,
+                   int eps_mode, const float* lm_sum_dev, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) { set_error("adam (data-parallel): buffers must be 16-byte aligned"); return 100001; }
+  const long want = cdiv(n >> 2, 256);
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  k_adam<true><<<grid, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, inv1, inv2, eps_mode, 1.0f, lm_sum_dev);
   NERF_CHECK_LAUNCH();
   return 0;
 }

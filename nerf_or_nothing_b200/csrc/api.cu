@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <vector>
 
 #include "../../include/nerfb200.h"
@@ -137,10 +138,14 @@ struct nerf_mipnerf {
     long last_rows = 0;
   };
   std::vector<Level> lv;
-  float* scalars = nullptr;         // device: [0] = sum(loss_mults), [1..NL] = per-level loss
+  // device: [0] = sum(loss_mults), [1..NL] = per-level loss.  These are the floats right after the n_params gradients
+  // in the SAME allocation, so that the data-parallel step moves gradient + normaliser + losses in one allreduce.
+  float* scalars = nullptr;
   float* scalars_pinned = nullptr;  // host mirror
+  float* red_scratch = nullptr;     // partials + ticket of the multi-block deterministic reductions
   float* user_u = nullptr;          // explicit sampling uniforms [NL, user_u_rays, S+1]
   int user_u_rays = 0;
+  bool grads_unnormalised = false;  // data parallel, between get_gradient and the allreduce / Adam
   uint32_t step = 0;
   uint32_t ray_offset = 0;  // global index of this rank's first ray (Philox counter)
   void* comm = nullptr;
@@ -165,6 +170,8 @@ struct nerf_gradcalc {
 };
 
 namespace {
+
+constexpr int kGradTail = 16;  // floats behind the gradients: [0] sum(loss_mults), [1..n_levels] per-level loss (n_levels <= 4)
 
 struct ProfActivate {  // routes ProfScope hooks to this handle's profiler for the duration of a call
   Profiler* prev;
@@ -195,17 +202,20 @@ int validate(const nerf_config& c) {
 }
 
 // forward of all levels for rays [c0, c0+rc) of the current batch
+// for_training = false (render): deterministic sampling (SN/MipNerfModel.cs:36-97 evaluates with randomized = false),
+// explicit uniforms ignored, no activation caches
 int forward_chunk(nerf_mipnerf* h, int c0, int rc, bool for_training = true) {
   const nerf_config& c = h->cfg;
   const int S = h->S;
+  const int randomized = for_training ? c.randomized : 0;
   for (int l = 0; l < h->NL; l++) {
     auto& L = h->lv[l];
     SampleRng rng;
-    rng.u = h->user_u ? h->user_u + ((size_t)l * h->user_u_rays + c0) * (S + 1) : nullptr;
+    rng.u = (h->user_u && for_training) ? h->user_u + ((size_t)l * h->user_u_rays + c0) * (S + 1) : nullptr;
     rng.seed = c.seed; rng.step = h->step; rng.level = (uint32_t)l; rng.ray0 = h->ray_offset + (uint32_t)c0;
     { ProfScope ps(PC_SAMPLE, h->st);
-    if (l == 0) NERF_TRY(launch_sample_t_vals(h->nears + c0, h->fars + c0, rng, rc, S, c.randomized, L.t, h->st));
-    else NERF_TRY(launch_resample_t_vals(h->lv[l - 1].t, h->lv[l - 1].weights, rng, rc, S, c.resample_padding, c.randomized, L.t, h->st)); }
+    if (l == 0) NERF_TRY(launch_sample_t_vals(h->nears + c0, h->fars + c0, rng, rc, S, randomized, L.t, h->st));
+    else NERF_TRY(launch_resample_t_vals(h->lv[l - 1].t, h->lv[l - 1].weights, rng, rc, S, c.resample_padding, randomized, L.t, h->st)); }
     { ProfScope ps(PC_ENCODE, h->st);
     NERF_TRY(launch_cast_encode_fused(L.t, h->origins + (size_t)c0 * 3, h->dirs + (size_t)c0 * 3, h->radii + c0, rc, S,
                                       c.deg_point, c.deg_view, h->mlp->encode_targets(l), h->st)); }
@@ -244,10 +254,14 @@ int gradient_core(nerf_mipnerf* h, int n_rays, nerf_output_gradient_cb cb, void*
   if (cb && n_rays > h->Rc) { set_error("the host-callback path needs n_rays (%d) <= chunk_rays (%d)", n_rays, h->Rc); return NERF_ERR_INVALID; }
   NERF_CUDA(cudaSetDevice(c.device));
   ProfActivate pa(h);
-  NERF_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)h->shape.n_params * sizeof(float), h->st));
-  NERF_CUDA(cudaMemsetAsync(h->scalars, 0, (size_t)(1 + h->NL) * sizeof(float), h->st));
-  { ProfScope ps(PC_MISC, h->st); NERF_TRY(launch_sum(h->lm, n_rays, h->scalars, h->st)); }  // sum(loss_mults) as a float (A-D13)
-  if (h->comm) NERF_NCCL(g_nccl.AllReduce(h->scalars, h->scalars, 1, kNcclFloat32, kNcclSum, h->comm, h->st));
+  // gradients + the scalars behind them in one memset
+  NERF_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->shape.n_params + kGradTail) * sizeof(float), h->st));
+  { ProfScope ps(PC_MISC, h->st); NERF_TRY(launch_sum(h->lm, n_rays, h->scalars, h->red_scratch, h->st)); }  // sum(loss_mults) as a float (A-D13)
+  // Data parallel: NO collective here.  The rank-local gradient is accumulated un-normalised (lm_sum = 1) and the global
+  // 1 / sum(loss_mults) is applied after the single allreduce of [gradient | sum(lm) | loss numerators] (finish_step).
+  const bool dp = h->comm != nullptr;
+  if (dp && cb) { set_error("the host-callback path is single-GPU (the callback sees a rank-local loss_mult_sum)"); return NERF_ERR_STATE; }
+  h->grads_unnormalised = dp;
   NERF_TRY(h->mlp->prepare(h->params, h->st));
   std::vector<float*> g(h->NL);
   for (int c0 = 0; c0 < n_rays; c0 += h->Rc) {
@@ -266,8 +280,9 @@ int gradient_core(nerf_mipnerf* h, int n_rays, nerf_output_gradient_cb cb, void*
       for (int l = 0; l < h->NL; l++) {
         const float mult = l < h->NL - 1 ? c.coarse_loss_mult : 1.0f;  // .cu:356
         ProfScope ps(PC_LOSS, h->st);
-        NERF_TRY(launch_output_gradient(h->lv[l].comp_rgb + (size_t)c0 * 3, h->pixels + (size_t)c0 * 3, h->lm + c0, rc, 0.f,
-                                        h->scalars, mult, h->lv[l].g + (size_t)c0 * 3, h->scalars + 1 + l, h->st));
+        NERF_TRY(launch_output_gradient(h->lv[l].comp_rgb + (size_t)c0 * 3, h->pixels + (size_t)c0 * 3, h->lm + c0, rc, 1.0f,
+                                        dp ? nullptr : h->scalars, mult, h->lv[l].g + (size_t)c0 * 3, h->scalars + 1 + l,
+                                        h->red_scratch, h->st));
         g[l] = h->lv[l].g;
       }
     }
@@ -322,8 +337,10 @@ int read_loss(nerf_mipnerf* h, float* loss_per_level, float* total) {
   NERF_CUDA(cudaMemcpyAsync(h->scalars_pinned, h->scalars, (size_t)(1 + h->NL) * sizeof(float), cudaMemcpyDeviceToHost, h->st));
   NERF_CUDA(cudaStreamSynchronize(h->st));
   float tot = 0.f;
+  // data parallel: the tail holds allreduced NUMERATORS sum(lm |rgb - pix|^2) and the global sum(lm)
+  const float div = h->comm ? h->scalars_pinned[0] : 1.0f;
   for (int l = 0; l < h->NL; l++) {
-    const float v = h->scalars_pinned[1 + l];
+    const float v = h->scalars_pinned[1 + l] / div;
     if (loss_per_level) loss_per_level[l] = v;
     tot += (l < h->NL - 1 ? h->cfg.coarse_loss_mult : 1.0f) * v;  // SN/Program.cs:81
   }
@@ -349,6 +366,7 @@ void nerf_default_config(nerf_config* c) {
   c->precision = NERF_PRECISION_FP32; c->device = 0; c->chunk_rays = 0;
   c->density_bias = 0.f; c->rgb_padding = 0.f; c->coarse_loss_mult = 0.1f; c->resample_padding = 0.01f;
   c->seed = 7;
+  c->engine_flags = 0;
 }
 
 int nerf_device_count(int* n) {
@@ -382,7 +400,10 @@ int nerf_mipnerf_create(const nerf_config* cfg, nerf_mipnerf** out) {
   if (cudaStreamCreate(&h->st) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(NERF_ERR_NO_DEVICE); }
   const long P = h->shape.n_params;
   if ((s = dalloc(h, &h->params, P))) return fail(s);
-  if ((s = dalloc(h, &h->grads, P))) return fail(s);
+  if ((s = dalloc(h, &h->grads, P + kGradTail))) return fail(s);
+  h->scalars = h->grads + P;
+  if ((s = dalloc(h, &h->red_scratch, NERF_RED_SCRATCH_FLOATS))) return fail(s);
+  if (cudaMemset(h->red_scratch, 0, NERF_RED_SCRATCH_FLOATS * sizeof(float)) != cudaSuccess) { set_error("cudaMemset failed"); return fail(NERF_ERR_NO_DEVICE); }
   for (auto& l : h->shape.layers) { h->param_ptrs.push_back(h->params + l.w_off); h->grad_ptrs.push_back(h->grads + l.w_off); h->sizes.push_back(l.out * (l.in_a + l.in_b)); }
   for (auto& l : h->shape.layers) { h->param_ptrs.push_back(h->params + l.b_off); h->grad_ptrs.push_back(h->grads + l.b_off); h->sizes.push_back(l.out); }
   const size_t R = (size_t)h->Rmax, Mc = (size_t)h->Rc * h->S;
@@ -390,7 +411,6 @@ int nerf_mipnerf_create(const nerf_config* cfg, nerf_mipnerf** out) {
   if ((s = dalloc(h, &h->pixels_own, 3 * R))) return fail(s);
   if (cudaMallocHost(&h->rays_pinned, 13 * R * sizeof(float)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(NERF_ERR_NO_DEVICE); }
   if (cudaMallocHost(&h->scalars_pinned, 16 * sizeof(float)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(NERF_ERR_NO_DEVICE); }
-  if ((s = dalloc(h, &h->scalars, 16))) return fail(s);
   h->lv.resize(h->NL);
   for (auto& L : h->lv) {
     if ((s = dalloc(h, &L.t, (size_t)h->Rc * (h->S + 1)))) return fail(s);
@@ -404,7 +424,7 @@ int nerf_mipnerf_create(const nerf_config* cfg, nerf_mipnerf** out) {
     if ((s = dalloc(h, &L.acc, R))) return fail(s);
     if ((s = dalloc(h, &L.g, R * 3))) return fail(s);
   }
-  h->mlp = cfg->precision == NERF_PRECISION_FP32 ? make_simt_mlp() : make_tc_mlp(cfg->precision == NERF_PRECISION_FP32_TC);
+  h->mlp = cfg->precision == NERF_PRECISION_FP32 ? make_simt_mlp() : make_tc_mlp(cfg->precision == NERF_PRECISION_FP32_TC, cfg->engine_flags);
   if (!h->mlp) { set_error("precision mode %d is not available in this build", cfg->precision); return fail(NERF_ERR_INVALID); }
   if ((s = h->mlp->init(h->shape, (long)Mc, h->NL))) return fail(s);
   // deterministic init (A-D7)
@@ -425,7 +445,7 @@ int nerf_mipnerf_create(const nerf_config* cfg, nerf_mipnerf** out) {
     cudaFree(d_woff); cudaFree(d_o); cudaFree(d_in);
     if (cudaGetLastError() != cudaSuccess) { set_error("parameter init failed"); return fail(NERF_ERR_NO_DEVICE); }
   }
-  cudaMemsetAsync(h->grads, 0, P * sizeof(float), h->st);
+  cudaMemsetAsync(h->grads, 0, (P + kGradTail) * sizeof(float), h->st);
   cudaStreamSynchronize(h->st);
   *out = h;
   return 0;
@@ -678,6 +698,13 @@ int nerf_mlp_get_gradient(nerf_mipnerf* h, const float* color_grad, const float*
   if (grad_dev_ptrs) memcpy(grad_dev_ptrs, h->grad_ptrs.data(), h->grad_ptrs.size() * sizeof(float*));
   return 0;
 }
+int nerf_mlp_relu_bits(nerf_mipnerf* h, int level, int layer, uint64_t* bits_dev, int* words_per_row) {
+  if (!h || !bits_dev || !words_per_row || level < 0 || level >= h->NL) { set_error("mlp_relu_bits: bad arguments"); return NERF_ERR_INVALID; }
+  const uint32_t* b = nullptr;
+  NERF_TRY(h->mlp->relu_bits(level, layer, &b, words_per_row));
+  *bits_dev = (uint64_t)(uintptr_t)b;
+  return 0;
+}
 int nerf_mlp_reset_gradients(nerf_mipnerf* h, int level) {
   (void)level;  // one gradient buffer summed over levels (A-D4/D5)
   if (!h) { set_error("null handle"); return NERF_ERR_INVALID; }
@@ -766,7 +793,7 @@ int nerf_gradcalc_get_output_gradient(nerf_gradcalc* g, uint64_t comp_rgb_dev, c
   float* out = g->grad + (size_t)level * g->batch * 3;
   const float mult = level < g->n_levels - 1 ? g->coarse_mult : 1.0f;
   NERF_TRY(launch_output_gradient((const float*)(uintptr_t)comp_rgb_dev, g->pixels, (const float*)(uintptr_t)loss_mults_dev, n,
-                                  loss_mult_sum, nullptr, mult, out, nullptr, 0));
+                                  loss_mult_sum, nullptr, mult, out, nullptr, nullptr, 0));
   NERF_CUDA(cudaDeviceSynchronize());
   if (grad_dev) *grad_dev = (uint64_t)(uintptr_t)out;
   return 0;
@@ -790,9 +817,19 @@ int nerf_retrieve_output(uint64_t dev, int n_float3, float* host_out) {
 static int finish_step(nerf_mipnerf* h, nerf_adam* a, float lr, float* loss_out) {
   if (a->n != h->shape.n_params) { set_error("optimizer size %ld != model parameters %ld", a->n, h->shape.n_params); return NERF_ERR_INVALID; }
   ProfActivate pa(h);
-  if (h->comm) { ProfScope ps(PC_COMM, h->st); NERF_NCCL(g_nccl.AllReduce(h->grads, h->grads, (size_t)h->shape.n_params, kNcclFloat32, kNcclSum, h->comm, h->st)); }
+  // the step's ONE collective: [gradient | sum(loss_mults) | per-level loss numerators], fp32 sum
+  if (h->comm) { ProfScope ps(PC_COMM, h->st); NERF_NCCL(g_nccl.AllReduce(h->grads, h->grads, (size_t)h->shape.n_params + 1 + h->NL, kNcclFloat32, kNcclSum, h->comm, h->st)); }
   a->iteration++;
-  { ProfScope ps(PC_ADAM, h->st); NERF_TRY(adam_step_flat(a, h->params, h->grads, a->n, 0, lr, 1.0f, h->st)); }
+  { ProfScope ps(PC_ADAM, h->st);
+    if (h->grads_unnormalised) {  // the global 1 / sum(lm) rides in the Adam pass, which writes the normalised gradient back
+      const float inv1 = 1.0f / (1.0f - powf(nerf_adam::beta1, (float)a->iteration));
+      const float inv2 = 1.0f / (1.0f - powf(nerf_adam::beta2, (float)a->iteration));
+      NERF_TRY(launch_adam_dp(h->params, h->grads, a->m, a->v, a->n, lr, nerf_adam::beta1, nerf_adam::beta2, inv1, inv2, a->eps_mode,
+                              h->scalars, h->st));
+      h->grads_unnormalised = false;
+    } else {
+      NERF_TRY(adam_step_flat(a, h->params, h->grads, a->n, 0, lr, 1.0f, h->st));
+    } }
   if (loss_out) {
     float per[8];
     NERF_TRY(read_loss(h, per, loss_out));
@@ -973,12 +1010,17 @@ float nerf_learning_rate_decay(int step, float lr_init, float lr_final, int max_
 namespace {
 struct CkptHeader {
   char magic[8];        // "NERFB200"
-  uint32_t version;     // 1
+  uint32_t version;     // 2 (1: the same without seed / precision — still readable)
   uint32_t n_tensors;
   int64_t n_params;
   int32_t adam_iteration;  // -1: no optimizer state stored
   uint32_t step;           // Philox step counter of the model
   int32_t shape[7];        // depth, width, depth_cond, width_cond, skip, deg_point, deg_view
+};
+struct CkptHeaderV2 {  // follows CkptHeader when version >= 2: what a bitwise-identical resume also depends on
+  uint64_t seed;       // sampling RNG key (cfg.seed)
+  int32_t precision;   // NERF_PRECISION_* the state was trained in
+  int32_t reserved;
 };
 }  // namespace
 
@@ -989,7 +1031,8 @@ int nerf_checkpoint_save(nerf_mipnerf* h, nerf_adam* a, const char* path) {
   NERF_CUDA(cudaSetDevice(h->cfg.device));
   NERF_CUDA(cudaStreamSynchronize(h->st));
   const long n = h->shape.n_params;
-  std::vector<float> buf((size_t)n * (a ? 3 : 1));
+  std::vector<float> buf;
+  try { buf.resize((size_t)n * (a ? 3 : 1)); } catch (const std::exception& e) { set_error("checkpoint_save: %s", e.what()); return NERF_ERR_INVALID; }
   NERF_CUDA(cudaMemcpy(buf.data(), h->params, (size_t)n * 4, cudaMemcpyDeviceToHost));
   if (a) {
     NERF_CUDA(cudaMemcpy(buf.data() + n, a->m, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -998,14 +1041,18 @@ int nerf_checkpoint_save(nerf_mipnerf* h, nerf_adam* a, const char* path) {
   CkptHeader hd;
   memset(&hd, 0, sizeof(hd));
   memcpy(hd.magic, "NERFB200", 8);
-  hd.version = 1; hd.n_tensors = (uint32_t)h->sizes.size(); hd.n_params = n;
+  hd.version = 2; hd.n_tensors = (uint32_t)h->sizes.size(); hd.n_params = n;
   hd.adam_iteration = a ? a->iteration : -1; hd.step = h->step;
   const nerf_config& c = h->cfg;
   const int32_t shp[7] = {c.net_depth, c.net_width, c.net_depth_condition, c.net_width_condition, c.skip_layer, c.deg_point, c.deg_view};
   memcpy(hd.shape, shp, sizeof(shp));
   FILE* f = fopen(path, "wb");
   if (!f) { set_error("checkpoint_save: cannot open %s", path); return NERF_ERR_INVALID; }
+  CkptHeaderV2 h2;
+  memset(&h2, 0, sizeof(h2));
+  h2.seed = c.seed; h2.precision = c.precision;
   bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+  ok = ok && fwrite(&h2, sizeof(h2), 1, f) == 1;
   ok = ok && fwrite(h->sizes.data(), sizeof(int), h->sizes.size(), f) == h->sizes.size();
   ok = ok && fwrite(buf.data(), sizeof(float), buf.size(), f) == buf.size();
   ok = (fclose(f) == 0) && ok;
@@ -1015,35 +1062,58 @@ int nerf_checkpoint_save(nerf_mipnerf* h, nerf_adam* a, const char* path) {
 
 int nerf_checkpoint_load(nerf_mipnerf* h, nerf_adam* a, const char* path) {
   if (!h || !path) { set_error("checkpoint_load: null argument"); return NERF_ERR_INVALID; }
-  FILE* f = fopen(path, "rb");
-  if (!f) { set_error("checkpoint_load: cannot open %s", path); return NERF_ERR_INVALID; }
-  CkptHeader hd;
-  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "NERFB200", 8) != 0 || hd.version != 1) {
-    fclose(f); set_error("checkpoint_load: %s is not a version-1 checkpoint", path); return NERF_ERR_INVALID;
-  }
-  const nerf_config& c = h->cfg;
-  const int32_t shp[7] = {c.net_depth, c.net_width, c.net_depth_condition, c.net_width_condition, c.skip_layer, c.deg_point, c.deg_view};
-  std::vector<int> sizes(hd.n_tensors);
-  if (hd.n_params != h->shape.n_params || hd.n_tensors != h->sizes.size() || memcmp(hd.shape, shp, sizeof(shp)) != 0 ||
-      fread(sizes.data(), sizeof(int), sizes.size(), f) != sizes.size() || sizes != h->sizes) {
-    fclose(f); set_error("checkpoint_load: %s was written for a different network shape", path); return NERF_ERR_INVALID;
-  }
-  const long n = h->shape.n_params;
-  const bool has_opt = hd.adam_iteration >= 0;
-  if (a && !has_opt) { fclose(f); set_error("checkpoint_load: %s holds no optimizer state", path); return NERF_ERR_INVALID; }
-  if (a && a->n != n) { fclose(f); set_error("checkpoint_load: optimizer size %ld != %ld", a->n, n); return NERF_ERR_INVALID; }
-  std::vector<float> buf((size_t)n * (has_opt ? 3 : 1));
-  const size_t got = fread(buf.data(), sizeof(float), buf.size(), f);
-  fclose(f);
-  if (got != buf.size()) { set_error("checkpoint_load: %s is truncated", path); return NERF_ERR_INVALID; }
-  NERF_CUDA(cudaSetDevice(h->cfg.device));
-  NERF_CUDA(cudaStreamSynchronize(h->st));
-  NERF_CUDA(cudaMemcpy(h->params, buf.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-  h->step = hd.step;
-  if (a) {
-    NERF_CUDA(cudaMemcpy(a->m, buf.data() + n, (size_t)n * 4, cudaMemcpyHostToDevice));
-    NERF_CUDA(cudaMemcpy(a->v, buf.data() + 2 * n, (size_t)n * 4, cudaMemcpyHostToDevice));
-    a->iteration = hd.adam_iteration;
+  struct File {  // closed on every exit path
+    FILE* f = nullptr;
+    ~File() { if (f) fclose(f); }
+  } file;
+  file.f = fopen(path, "rb");
+  if (!file.f) { set_error("checkpoint_load: cannot open %s", path); return NERF_ERR_INVALID; }
+  FILE* f = file.f;
+  try {
+    CkptHeader hd;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "NERFB200", 8) != 0 || (hd.version != 1 && hd.version != 2)) {
+      set_error("checkpoint_load: %s is not a version-1/2 checkpoint", path); return NERF_ERR_INVALID;
+    }
+    const nerf_config& c = h->cfg;
+    CkptHeaderV2 h2;
+    memset(&h2, 0, sizeof(h2));
+    h2.seed = c.seed; h2.precision = c.precision;
+    if (hd.version >= 2 && fread(&h2, sizeof(h2), 1, f) != 1) { set_error("checkpoint_load: %s is truncated", path); return NERF_ERR_INVALID; }
+    const int32_t shp[7] = {c.net_depth, c.net_width, c.net_depth_condition, c.net_width_condition, c.skip_layer, c.deg_point, c.deg_view};
+    // compare the header with the model BEFORE sizing anything from it: a corrupt or foreign file must not drive an allocation
+    if (hd.n_params != h->shape.n_params || hd.n_tensors != h->sizes.size() || memcmp(hd.shape, shp, sizeof(shp)) != 0) {
+      set_error("checkpoint_load: %s was written for a different network shape", path); return NERF_ERR_INVALID;
+    }
+    std::vector<int> sizes(h->sizes.size());
+    if (fread(sizes.data(), sizeof(int), sizes.size(), f) != sizes.size() || sizes != h->sizes) {
+      set_error("checkpoint_load: %s was written for a different network shape", path); return NERF_ERR_INVALID;
+    }
+    const long n = h->shape.n_params;
+    const bool has_opt = hd.adam_iteration >= 0;
+    if (a && !has_opt) { set_error("checkpoint_load: %s holds no optimizer state", path); return NERF_ERR_INVALID; }
+    if (a && a->n != n) { set_error("checkpoint_load: optimizer size %ld != %ld", a->n, n); return NERF_ERR_INVALID; }
+    // resuming TRAINING (optimizer state requested) is only bitwise identical with the same sampling seed and precision
+    if (a && (h2.seed != c.seed || h2.precision != c.precision)) {
+      set_error("checkpoint_load: %s was trained with seed %llu / precision %d, this model has seed %llu / precision %d "
+                "(pass a NULL optimizer to load the parameters only)", path, (unsigned long long)h2.seed, h2.precision,
+                (unsigned long long)c.seed, c.precision);
+      return NERF_ERR_INVALID;
+    }
+    std::vector<float> buf((size_t)n * (has_opt ? 3 : 1));
+    const size_t got = fread(buf.data(), sizeof(float), buf.size(), f);
+    if (got != buf.size()) { set_error("checkpoint_load: %s is truncated", path); return NERF_ERR_INVALID; }
+    NERF_CUDA(cudaSetDevice(h->cfg.device));
+    NERF_CUDA(cudaStreamSynchronize(h->st));
+    NERF_CUDA(cudaMemcpy(h->params, buf.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    h->step = hd.step;
+    if (a) {
+      NERF_CUDA(cudaMemcpy(a->m, buf.data() + n, (size_t)n * 4, cudaMemcpyHostToDevice));
+      NERF_CUDA(cudaMemcpy(a->v, buf.data() + 2 * n, (size_t)n * 4, cudaMemcpyHostToDevice));
+      a->iteration = hd.adam_iteration;
+    }
+  } catch (const std::exception& e) {  // nothing may unwind through the extern "C" boundary
+    set_error("checkpoint_load: %s", e.what());
+    return NERF_ERR_INVALID;
   }
   return 0;
 }
@@ -1069,7 +1139,11 @@ int nerf_mipnerf_comm_init(nerf_mipnerf* h, const void* id, int rank, int world)
 int nerf_mipnerf_allreduce_gradients(nerf_mipnerf* h) {
   if (!h || !h->comm) { set_error("allreduce: no communicator attached"); return NERF_ERR_STATE; }
   NERF_CUDA(cudaSetDevice(h->cfg.device));
-  NERF_NCCL(g_nccl.AllReduce(h->grads, h->grads, (size_t)h->shape.n_params, kNcclFloat32, kNcclSum, h->comm, h->st));
+  NERF_NCCL(g_nccl.AllReduce(h->grads, h->grads, (size_t)h->shape.n_params + 1 + h->NL, kNcclFloat32, kNcclSum, h->comm, h->st));
+  if (h->grads_unnormalised) {  // GetGradient + explicit allreduce + nerf_adam_step: normalise here
+    NERF_TRY(launch_scale_by_inv(h->grads, h->shape.n_params, h->scalars, h->st));
+    h->grads_unnormalised = false;
+  }
   return 0;
 }
 int nerf_mipnerf_comm_destroy(nerf_mipnerf* h) {
@@ -1082,6 +1156,12 @@ int nerf_mipnerf_comm_destroy(nerf_mipnerf* h) {
 // ---- per-stage entry points (default stream, synchronous) ------------------------------------------
 #define STAGE_BEGIN() do { int n_ = 0; if (cudaGetDeviceCount(&n_) != cudaSuccess || n_ <= 0) { cudaGetLastError(); set_error("no CUDA device available: libnerfb200 has no CPU path"); return NERF_ERR_NO_DEVICE; } } while (0)
 #define STAGE_END() do { NERF_CUDA(cudaStreamSynchronize(0)); return 0; } while (0)
+namespace {
+struct DevScratch {  // device allocation of a per-stage entry point, released on every exit path (cudaFree synchronises)
+  void* p = nullptr;
+  ~DevScratch() { if (p) cudaFree(p); }
+};
+}  // namespace
 
 int nerf_get_sample_t_vals(const float* nears, const float* fars, const float* u, int R, int S, int randomized, float* t) {
   STAGE_BEGIN();
@@ -1114,12 +1194,12 @@ int nerf_apply_layer(const float* in_a, const float* in_b, const float* W, const
     NERF_TRY(launch_dense_fwd(in_a, k_a, k_a, in_b, k_b, in_b ? k_b : 0, W, b, out, z, M, n, (Act)act, 0));
   } else {
     if (in_b && k_b > 0) { set_error("apply_layer: conjoined inputs need n > 4"); return NERF_ERR_INVALID; }
+    DevScratch own;  // freed on every exit path
     float* zz = z;
-    if (!zz) NERF_CUDA(cudaMalloc(&zz, (size_t)M * n * sizeof(float)));
+    if (!zz) { NERF_CUDA(cudaMalloc(&own.p, (size_t)M * n * sizeof(float))); zz = (float*)own.p; }
     NERF_TRY(launch_thin_fwd(in_a, k_a, W, b, zz, M, n, k_a, 0));
     if (out) NERF_TRY(launch_apply_act(zz, out, M * n, (Act)act, 0));
     NERF_CUDA(cudaStreamSynchronize(0));
-    if (!z) cudaFree(zz);
   }
   STAGE_END();
 }
@@ -1128,24 +1208,26 @@ int nerf_backpropagate_layer(const float* in_a, const float* in_b, const float* 
   STAGE_BEGIN();
   if (act < 0 || act > 3 || M <= 0 || n <= 0 || k_a <= 0) { set_error("backpropagate_layer: bad arguments"); return NERF_ERR_INVALID; }
   const int kb = in_b ? k_b : 0;
-  float *dZ = nullptr, *ws = nullptr;
-  NERF_CUDA(cudaMalloc(&dZ, (size_t)M * n * sizeof(float)));
+  if (n <= 4 && kb) { set_error("backpropagate_layer: conjoined inputs need n > 4"); return NERF_ERR_INVALID; }  // before any allocation
+  DevScratch dz_own, ws_own;  // freed on every exit path
+  NERF_CUDA(cudaMalloc(&dz_own.p, (size_t)M * n * sizeof(float)));
+  float* dZ = (float*)dz_own.p;
+  float* ws = nullptr;
   NERF_TRY(launch_act_grad(dY, Z, dZ, M * n, (Act)act, 0));  // dZ = dY * act'(Z)  (.cu:97-99)
   if (n > 4) {
     size_t wsz = dense_wgrad_workspace(M, n, k_a);
     if (kb) { const size_t w2 = dense_wgrad_workspace(M, n, kb); wsz = w2 > wsz ? w2 : wsz; }
-    NERF_CUDA(cudaMalloc(&ws, wsz * sizeof(float)));
+    NERF_CUDA(cudaMalloc(&ws_own.p, wsz * sizeof(float)));
+    ws = (float*)ws_own.p;
     NERF_TRY(launch_dense_wgrad(dZ, in_a, k_a, k_a, in_b, kb, kb, dW, db, M, n, ws, 0));
     if (in_a_grads) NERF_TRY(launch_dense_dgrad(dZ, W, k_a + kb, in_a_grads, M, n, k_a, nullptr, nullptr, nullptr, true, 0));
   } else {
-    if (kb) { set_error("backpropagate_layer: conjoined inputs need n > 4"); return NERF_ERR_INVALID; }
-    NERF_CUDA(cudaMalloc(&ws, thin_wgrad_workspace(M, n, k_a) * sizeof(float)));
+    NERF_CUDA(cudaMalloc(&ws_own.p, thin_wgrad_workspace(M, n, k_a) * sizeof(float)));
+    ws = (float*)ws_own.p;
     NERF_TRY(launch_thin_wgrad(dZ, in_a, k_a, dW, db, M, n, k_a, ws, 0));
     if (in_a_grads) NERF_TRY(launch_thin_dgrad(dZ, W, in_a_grads, M, n, k_a, nullptr, true, 0));
   }
-  NERF_CUDA(cudaStreamSynchronize(0));
-  cudaFree(dZ); cudaFree(ws);
-  STAGE_END();
+  STAGE_END();  // synchronises the stream; the scratch buffers are released when they go out of scope after it
 }
 int nerf_volumetric_rendering(const float* rgb, const float* density, const float* t, const float* dirs, float* comp, float* depth,
                               float* acc, float* weights, int R, int S, int white) {
@@ -1155,7 +1237,7 @@ int nerf_volumetric_rendering(const float* rgb, const float* density, const floa
 }
 int nerf_get_output_gradient(const float* comp, const float* pix, const float* lm, float* g, float lm_sum, float level_mult, int R) {
   STAGE_BEGIN();
-  NERF_TRY(launch_output_gradient(comp, pix, lm, R, lm_sum, nullptr, level_mult, g, nullptr, 0));
+  NERF_TRY(launch_output_gradient(comp, pix, lm, R, lm_sum, nullptr, level_mult, g, nullptr, nullptr, 0));
   STAGE_END();
 }
 int nerf_volumetric_rendering_gradient(const float* g, const float* rgb, const float* density, const float* t, const float* dirs,

@@ -40,6 +40,12 @@ long launch_count();
 
 inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// Per-DEVICE one-time kernel setup.  The dynamic-shared-memory opt-in (cudaFuncAttributeMaxDynamicSharedMemorySize) is a
+// property of (kernel, device), so a process that drives several GPUs must set it on each of them; the SM count is
+// per device too.  Both are memoised per (kernel, current device); returns 0 or the cudaError_t of the first failure.
+int ensure_kernel_smem(const void* kernel, int dyn_smem_bytes);
+int device_sm_count();  // of the current device (memoised)
+
 // Optional in-stream kernel timing (CUDA events around each launch group on the launching stream) so that
 // bench.py can report per-kernel durations measured live inside the timed region.  Off by default.
 enum ProfCat {
@@ -48,7 +54,7 @@ enum ProfCat {
 };
 const char* prof_name(int cat);
 struct Profiler;
-extern Profiler* g_prof;  // set by the API layer around a step; nullptr = profiling off
+extern thread_local Profiler* g_prof;  // set by the API layer around a call on the calling thread; nullptr = profiling off
 void prof_begin(int cat, cudaStream_t st);
 void prof_end(cudaStream_t st);
 struct ProfScope {

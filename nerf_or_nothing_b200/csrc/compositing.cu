@@ -226,15 +226,49 @@ k_composite_bwd(const float* __restrict__ g, const float* __restrict__ rgb, cons
   }
 }
 
-// g = 2*lm/lm_sum*(rgb-pix)*level_mult; optional loss = sum(lm |rgb-pix|^2)/lm_sum.  One block, fixed order.
+// Deterministic grid-wide sum for the two tiny per-ray reductions below: every block leaves its partial in
+// scratch[blockIdx.x]; the block that arrives last (atomic ticket in scratch[kRedBlocks]) adds the partials in index
+// order, so the result does not depend on which block that was.  Returns true on lane 0 of the finishing warp.
+constexpr int kRedBlocks = 64;
+__device__ __forceinline__ bool grid_sum_fixed_order(float block_part, float* scratch, float& total) {
+  __shared__ bool last;
+  if (gridDim.x == 1) { total = block_part; return threadIdx.x == 0; }
+  unsigned* ticket = reinterpret_cast<unsigned*>(scratch + kRedBlocks);
+  if (threadIdx.x == 0) {
+    scratch[blockIdx.x] = block_part;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x >= 32) return false;
+  __threadfence();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) s += __ldcg(scratch + i);
+  total = warp_sum(s);
+  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on the stream
+  return threadIdx.x == 0;
+}
+__device__ __forceinline__ float block_sum_1024(float part, float* red) {  // valid on thread 0
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  float v = 0.f;
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// g = 2*lm/lm_sum*(rgb-pix)*level_mult; optional loss = sum(lm |rgb-pix|^2)/lm_sum, summed in a fixed order.
 __global__ void __launch_bounds__(1024)
 k_output_gradient(const float* __restrict__ comp_rgb, const float* __restrict__ pixels, const float* __restrict__ lm,
                   int R, float lm_sum, const float* __restrict__ lm_sum_dev, float level_mult, float* __restrict__ g,
-                  float* __restrict__ loss_out) {
+                  float* __restrict__ loss_out, float* __restrict__ scratch) {
   __shared__ float red[32];
   if (lm_sum_dev) lm_sum = *lm_sum_dev;
   float part = 0.f;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
     const float l = lm[r];
     float e2 = 0.f;
 #pragma unroll
@@ -246,28 +280,25 @@ k_output_gradient(const float* __restrict__ comp_rgb, const float* __restrict__ 
     part += l * e2;
   }
   if (!loss_out) return;
-  part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) *loss_out += v / lm_sum;  // accumulates over ray chunks; caller zeroes per step
-  }
+  const float v = block_sum_1024(part, red);
+  float total;
+  if (grid_sum_fixed_order(v, scratch, total)) *loss_out += total / lm_sum;  // accumulates over ray chunks; caller zeroes per step
 }
 
-__global__ void __launch_bounds__(1024) k_sum(const float* __restrict__ x, int n, float* __restrict__ out) {
+__global__ void __launch_bounds__(1024) k_sum(const float* __restrict__ x, int n, float* __restrict__ out, float* __restrict__ scratch) {
   __shared__ float red[32];
   float part = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) part += x[i];
-  part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = red[threadIdx.x];
-    v = warp_sum(v);
-    if (threadIdx.x == 0) *out = v;
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) part += x[i];
+  const float v = block_sum_1024(part, red);
+  float total;
+  if (grid_sum_fixed_order(v, scratch, total)) *out = total;
+}
+
+// grads[i] *= 1 / *lm_sum_dev  (data-parallel GetGradient path: normalise the allreduced un-normalised sum)
+__global__ void k_scale_by_inv(float* __restrict__ g, long n, const float* __restrict__ lm_sum_dev) {
+  const float s = 1.0f / *lm_sum_dev;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] *= s;
 }
 
 template <bool RAW>
@@ -331,15 +362,32 @@ int launch_composite_bwd(const float* g, const float* rgb, const float* density,
   return 0;
 }
 
+// one block per 4096 rays (a single block — the original summation order — up to 4096 rays), at most kRedBlocks
+static unsigned red_grid(int n, const float* scratch) {
+  if (!scratch) return 1u;
+  const long b = cdiv(n, 4096);
+  return (unsigned)(b < 1 ? 1 : (b > kRedBlocks ? kRedBlocks : b));
+}
+
 int launch_output_gradient(const float* comp_rgb, const float* pixels, const float* loss_mults, int R, float lm_sum,
-                           const float* lm_sum_dev, float level_mult, float* g, float* loss_out, cudaStream_t st) {
-  k_output_gradient<<<1, 1024, 0, st>>>(comp_rgb, pixels, loss_mults, R, lm_sum, lm_sum_dev, level_mult, g, loss_out);
+                           const float* lm_sum_dev, float level_mult, float* g, float* loss_out, float* scratch, cudaStream_t st) {
+  // without a loss to reduce the rays are independent: any grid; with one, multi-block needs the scratch
+  const unsigned grid = loss_out ? red_grid(R, scratch) : (unsigned)(cdiv(R, 1024) > 1024 ? 1024 : cdiv(R, 1024));
+  k_output_gradient<<<grid, 1024, 0, st>>>(comp_rgb, pixels, loss_mults, R, lm_sum, lm_sum_dev, level_mult, g, loss_out, scratch);
   NERF_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_sum(const float* x, int n, float* out, cudaStream_t st) {
-  k_sum<<<1, 1024, 0, st>>>(x, n, out);
+int launch_sum(const float* x, int n, float* out, float* scratch, cudaStream_t st) {
+  k_sum<<<red_grid(n, scratch), 1024, 0, st>>>(x, n, out, scratch);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_scale_by_inv(float* g, long n, const float* lm_sum_dev, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long want = cdiv(n, 256);
+  k_scale_by_inv<<<(unsigned)(want > 148 * 8 ? 148 * 8 : want), 256, 0, st>>>(g, n, lm_sum_dev);
   NERF_CHECK_LAUNCH();
   return 0;
 }

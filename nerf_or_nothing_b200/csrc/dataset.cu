@@ -32,7 +32,8 @@ __global__ void k_gather_batch(const float4* __restrict__ rec, long n, const lon
   const float4 a = __ldg(rec + j * 4), b = __ldg(rec + j * 4 + 1), c = __ldg(rec + j * 4 + 2), e = __ldg(rec + j * 4 + 3);
   o[i * 3] = a.x; o[i * 3 + 1] = a.y; o[i * 3 + 2] = a.z;
   d[i * 3] = a.w; d[i * 3 + 1] = b.x; d[i * 3 + 2] = b.y;
-  // b.z b.w c.x = viewdir: the kernels normalise `direction` themselves (SURVEY A-D7), kept in the record for layout parity
+  // b.z b.w c.x = viewdir: loaded and dropped exactly as the reference does (SN/BinDataset.cs:44); the direction PE encodes the
+  // UN-normalised `direction` (SURVEY A-D10), so the field only stays in the record for layout parity
   radii[i] = c.y; nears[i] = c.z; fars[i] = c.w; lm[i] = e.x;
   pix[i * 3] = e.y; pix[i * 3 + 1] = e.z; pix[i * 3 + 2] = e.w;
 }

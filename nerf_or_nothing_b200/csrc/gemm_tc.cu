@@ -722,6 +722,62 @@ k_reduce_partials_tc(const float* __restrict__ ws, int splits, long stride, int 
   }
 }
 
+// The same reduction for MANY splits (the thin heads write ~600 partial rows of a few hundred floats): 16 z-groups per
+// column quad instead of 4, so a thread's chain of dependent loads is 16x shorter than its split count; the groups meet in
+// shared memory in a fixed pairwise tree (deterministic).
+__global__ void __launch_bounds__(1024)
+k_reduce_partials_wide(const float* __restrict__ ws, int splits, long stride, int rows, int cols, int ldw, float* __restrict__ out, int ldo,
+                       int coff, const float* __restrict__ ws2, int n2, long stride2, float* __restrict__ out2) {
+  __shared__ float4 red[16][64];
+  const int q = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int c4 = (cols + 3) >> 2;
+  const long n1 = (long)rows * c4;
+  const long idx = (long)blockIdx.x * 64 + q;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = 0, j = 0;
+  if (idx < n1) {
+    i = (int)(idx / c4); j = (int)(idx % c4) * 4;
+    const float* src = ws + (long)i * ldw + j;
+    const bool vec = (ldw & 3) == 0 && (stride & 3) == 0;
+#pragma unroll 4
+    for (int z = g; z < splits; z += 16) {
+      const float* p = src + (long)z * stride;
+      if (vec) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      } else {
+        s.x += p[0];
+        if (j + 1 < cols) s.y += p[1];
+        if (j + 2 < cols) s.z += p[2];
+        if (j + 3 < cols) s.w += p[3];
+      }
+    }
+  } else if (idx - n1 < n2) {
+    const int jb = (int)(idx - n1);
+    for (int z = g; z < splits; z += 16) s.x += ws2[(long)z * stride2 + jb];
+  }
+  red[g][q] = s;
+  __syncthreads();
+  for (int w = 8; w > 0; w >>= 1) {  // pairwise tree over the groups: g += g + w
+    if (g < w) {
+      const float4 a = red[g][q], b = red[g + w][q];
+      red[g][q] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    __syncthreads();
+  }
+  if (g != 0) return;
+  const float4 t = red[0][q];
+  if (idx < n1) {
+    float* o = out + (long)i * ldo + coff + j;
+    o[0] += t.x;
+    if (j + 1 < cols) o[1] += t.y;
+    if (j + 2 < cols) o[2] += t.z;
+    if (j + 3 < cols) o[3] += t.w;
+  } else if (idx - n1 < n2) {
+    out2[idx - n1] += t.x;
+  }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -835,24 +891,12 @@ static int persist_stages(int BN) {
 }
 int tc_launch(const TcParams& p_in, bool mn_major, dim3 grid, cudaStream_t st) {
   TcParams p = p_in;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
   if (p.BN % 16 || p.BN < 16 || p.BN > 256 || p.n_stages < 1 || p.n_stages > kMaxStages) { set_error("tc_launch: bad BN=%d stages=%d", p.BN, p.n_stages); return 100001; }
   if (mn_major && p.BN % 64) { set_error("tc_launch: MN-major needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
   if (!mn_major && p.BN % 64) { set_error("tc_launch: K-major epilogue needs BN %% 64 == 0 (got %d)", p.BN); return 100001; }
   if (!mn_major) {
-    static std::once_flag once2;
-    static cudaError_t e2 = cudaSuccess;
-    static int sms = 148;
-    std::call_once(once2, [] {
-      e2 = cudaFuncSetAttribute(k_tc_gemm_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (kConstFloats * 4 + 256));
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    });
-    if (e2 != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e2)); return (int)e2; }
+    NERF_TRY(ensure_kernel_smem((const void*)k_tc_gemm_persist, 227 * 1024 - (kConstFloats * 4 + 256)));  // per device
+    const int sms = device_sm_count();
     if (p.n_valid % 32 || p.n_valid > 512) { set_error("tc_launch: n_valid=%d must be a multiple of 32, <= 512", p.n_valid); return 100001; }
     p.n_stages = persist_stages(p.BN);
     const size_t smem_p = (size_t)p.n_stages * (kABytes + p.BN * 128) + 4 * 16384 + 1024;
@@ -866,6 +910,7 @@ int tc_launch(const TcParams& p_in, bool mn_major, dim3 grid, cudaStream_t st) {
   int stages = (220 * 1024 - 1024 - 8192) / stage_bytes;
   p.n_stages = stages > kMaxStages ? kMaxStages : (stages < 1 ? 1 : stages);
   const size_t smem = (size_t)p.n_stages * stage_bytes + 8192 + 1024;
+  NERF_TRY(ensure_kernel_smem((const void*)k_tc_wgrad, 220 * 1024));
   k_tc_wgrad<<<grid, kThreads, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
@@ -924,8 +969,12 @@ int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int
 int launch_reduce_partials2(const float* ws, int splits, long split_stride, int rows, int cols, int ldw, float* out, int ldo, int coff,
                             const float* ws2, int n2, long stride2, float* out2, cudaStream_t st) {
   const long n = (long)rows * ((cols + 3) / 4) + (ws2 ? n2 : 0);
-  k_reduce_partials_tc<<<(unsigned)cdiv(n, 64), 256, 0, st>>>(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff, ws2, ws2 ? n2 : 0,
-                                                               stride2, out2);
+  if (splits >= 64)
+    k_reduce_partials_wide<<<(unsigned)cdiv(n, 64), 1024, 0, st>>>(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff, ws2,
+                                                                   ws2 ? n2 : 0, stride2, out2);
+  else
+    k_reduce_partials_tc<<<(unsigned)cdiv(n, 64), 256, 0, st>>>(ws, splits, split_stride, rows, cols, ldw, out, ldo, coff, ws2, ws2 ? n2 : 0,
+                                                                 stride2, out2);
   NERF_CHECK_LAUNCH();
   return 0;
 }

@@ -52,10 +52,14 @@ int launch_composite_bwd(const float* g, const float* rgb, const float* density,
                          float* d_rgb, float* d_density, cudaStream_t st);
 // g = 2*lm/lm_sum*(rgb-pix)*level_mult (.cu:347-361).  lm_sum_dev (device scalar) overrides lm_sum when set.
 // loss_out (optional, device scalar): sum(lm*|rgb-pix|^2)/lm_sum (SN/Program.cs:64).
+// scratch (optional): NERF_RED_SCRATCH_FLOATS zero-initialised floats; with it the reductions run on several blocks
+// for large batches and are still summed in a fixed order (bitwise reproducible).
+#define NERF_RED_SCRATCH_FLOATS 72
 int launch_output_gradient(const float* comp_rgb, const float* pixels, const float* loss_mults, int R,
                            float lm_sum, const float* lm_sum_dev, float level_mult, float* g, float* loss_out,
-                           cudaStream_t st);
-int launch_sum(const float* x, int n, float* out, cudaStream_t st);  // deterministic single-block sum
+                           float* scratch, cudaStream_t st);
+int launch_sum(const float* x, int n, float* out, float* scratch, cudaStream_t st);  // deterministic sum
+int launch_scale_by_inv(float* g, long n, const float* lm_sum_dev, cudaStream_t st);  // g *= 1 / *lm_sum_dev
 
 // dataset.cu — resident dataset (64-byte records, SN/BinDataset.cs:40-49), on-device batch draw + gather, image error
 int launch_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, int R, long* idx, cudaStream_t st);
@@ -66,6 +70,10 @@ int launch_sq_err(const float* a, const float* b, long n, double* out, cudaStrea
 // ---- adam.cu (B.6) ------------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float inv1,
                 float inv2, int eps_mode, float grad_scale, cudaStream_t st);
+// data-parallel form: the gradient buffer holds the allreduced UN-normalised sum; the pass multiplies by
+// 1 / *lm_sum_dev (the allreduced sum of loss multipliers), writes the normalised gradient back and steps.
+int launch_adam_dp(float* p, float* g, float* m, float* v, long n, float lr, float b1, float b2, float inv1,
+                   float inv2, int eps_mode, const float* lm_sum_dev, cudaStream_t st);
 
 // ---- gemm_simt.cu: strict-fp32 CUDA-core MLP layers ---------------------------------------------
 enum Act { ACT_RELU = 0, ACT_SIGMOID = 1, ACT_SOFTPLUS = 2, ACT_NONE = 3 };

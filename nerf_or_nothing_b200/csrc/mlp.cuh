@@ -57,10 +57,17 @@ class MlpEngine {
   // accumulates dL/dparams into grads from dL/d raw heads
   virtual int backward(int level, long M, const float* params, float* grads, const float* d_raw_density,
                        const float* d_raw_rgb, cudaStream_t st) = 0;
+  // parity hook: ReLU masks of hidden layer i (trunk 0..D-1, then condition layers) of `level`'s last training forward,
+  // one bit per unit: bit j of word c of row m <=> Y[m, 32 c + j] > 0.  Only engines that keep bit planes have them.
+  virtual int relu_bits(int level, int i, const uint32_t** bits, int* words_per_row) {
+    (void)level; (void)i; (void)bits; (void)words_per_row;
+    set_error("this precision mode keeps no ReLU bit planes");
+    return 100003;
+  }
   virtual size_t bytes_allocated() const = 0;
 };
 
 MlpEngine* make_simt_mlp();
-MlpEngine* make_tc_mlp(bool split3);  // defined in mlp_tc.cu
+MlpEngine* make_tc_mlp(bool split3, unsigned engine_flags);  // defined in mlp_tc.cu; flags = nerf_config.engine_flags
 
 }  // namespace nerf

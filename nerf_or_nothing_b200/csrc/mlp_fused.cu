@@ -16,7 +16,6 @@
 // the condition layer.  The N=1 density head and N=3 rgb head are FMAs on the epilogue registers.
 #include <cuda.h>
 
-#include <mutex>
 
 #include "gemm_tc.cuh"
 #include "sm100.cuh"
@@ -442,20 +441,10 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
     return 100001;
   }
   const bool train = act_out != nullptr;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  static int sms = 148;
   const size_t smem = (size_t)(train ? kWStages - 1 : kWStages) * kWStageBytes + 2 * kEncBytes + (train ? 8 * kStageSlot : 0) +
                       (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  });
-  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
+  NERF_TRY(ensure_kernel_smem(train ? (const void*)k_mlp_fused_fwd<1> : (const void*)k_mlp_fused_fwd<0>, 226 * 1024));  // per device
+  const int sms = device_sm_count();
   if (smem > 226 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
   FusedParams p;
   memset(&p, 0, sizeof(p));
@@ -497,16 +486,8 @@ int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, cons
                            int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                            __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, cudaStream_t st) {
   if (W != 256 || Wc != 128 || D > kMaxSteps || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  static int sms = 148;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(k_mlp_fused_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  });
-  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return (int)attr_err; }
+  NERF_TRY(ensure_kernel_smem((const void*)k_mlp_fused_fwd<2>, 226 * 1024));
+  const int sms = device_sm_count();
   const size_t smem = (size_t)(kWStages - 1) * kWStageBytes + 2 * kEncBytes + 8 * kStageSlot + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 226 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
   FusedParams p;

@@ -10,9 +10,9 @@
 //             splits the sample dimension over CTAs and reduces the fp32 partials in a fixed order.
 // The N=1 / N=3 heads stay on CUDA cores (too thin for a UMMA tile) but read the same planes.
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 
+#include "../../include/nerfb200.h"
 #include "gemm_tc.cuh"
 #include "mlp.cuh"
 
@@ -28,7 +28,7 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 class TcMlp : public MlpEngine {
  public:
-  explicit TcMlp(bool split3) : split_(split3) {}
+  TcMlp(bool split3, unsigned flags) : split_(split3), flags_(flags) {}
   ~TcMlp() override {
     for (void* p : owned_) cudaFree(p);
   }
@@ -85,7 +85,7 @@ class TcMlp : public MlpEngine {
       bytes_ += ws * sizeof(float);
     }
     pending_.ws = nullptr;
-    defer_reduce_ = getenv("NERF_NO_DEFERRED_REDUCE") == nullptr;
+    defer_reduce_ = !(flags_ & NERF_FLAG_NO_DEFERRED_REDUCE);
     return 0;
   }
 
@@ -127,7 +127,7 @@ class TcMlp : public MlpEngine {
   }
 
   int forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
-    if (can_fuse_forward() && getenv("NERF_NO_FUSED_TRAIN_FORWARD") == nullptr)
+    if (can_fuse_forward() && !(flags_ & NERF_FLAG_NO_FUSED_TRAIN_FORWARD))
       return fused_forward(level, M, params, raw_density, raw_rgb, true, st);
     Level& lv = levels_[level];
     const int D = s_.D, C = s_.C;
@@ -175,7 +175,7 @@ class TcMlp : public MlpEngine {
   // tensor memory (mlp_fused.cu) instead of one GEMM launch per layer with the activations written to HBM.
   bool can_fuse_forward() const {
     return s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 12 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
-           getenv("NERF_NO_FUSED_FORWARD") == nullptr;
+           !(flags_ & NERF_FLAG_NO_FUSED_FORWARD);
   }
 
   int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
@@ -233,7 +233,7 @@ class TcMlp : public MlpEngine {
       return launch_mlp_fused_forward_split(lv.enc_pos.hi, lv.enc_pos.lo, pos_pitch_, lv.enc_dir.hi, lv.enc_dir.lo, dir_pitch_, wpl.data(),
                                             wlo.data(), kpad.data(), in_b.data(), D, s_.W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                             head_rgb_off, bias_off.data(), raw_density, raw_rgb, train ? act_out.data() : nullptr,
-                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, st);
+                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, quarters(), st);
     }
     return launch_mlp_fused_forward(lv.enc_pos.hi, pos_pitch_, lv.enc_dir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
@@ -270,8 +270,8 @@ class TcMlp : public MlpEngine {
     // The trunk's dgrad chain is one fused kernel in both tensor-core modes.  In the fp32-accurate mode it moves half the
     // bytes of the per-layer launches (each dZ is written once instead of written and re-read) and, since the next layer's
     // first k-blocks run under the second-half epilogue, measures 3.24 ms against their 3.60 ms per step at configs[1].
-    // NERF_NO_FUSED_DGRAD=1 selects the per-layer launches (parity tests compare the two).
-    if (can_fuse_forward() && getenv("NERF_NO_FUSED_DGRAD") == nullptr)
+    // NERF_FLAG_NO_FUSED_DGRAD selects the per-layer launches (parity tests compare the two).
+    if (can_fuse_forward() && !(flags_ & NERF_FLAG_NO_FUSED_DGRAD))
       return backward_fused_chain(level, M, params, grads, d_raw_density, *cur, st);
     for (int i = C - 1; i >= 0; i--) {
       const int l = D + 1 + i;
@@ -340,7 +340,8 @@ class TcMlp : public MlpEngine {
         std::vector<__nv_bfloat16*> dz_lo(D);
         for (int j = 0; j < D; j++) { wt_lo[j] = wtp_[j == 0 ? D + 1 : D - j].lo; dz_lo[j] = dzs_[j].lo; }
         NERF_TRY(launch_mlp_fused_dgrad_split(dz_cond.hi, dz_cond.lo, dz_cond.pitch, wt.data(), wt_lo.data(), wt_pitch.data(), D, W, s_.Wc, M,
-                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), st));
+                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(),
+                                              quarters(), st));
       } else {
         NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                         d_raw_density, dz_out.data(), masks.data(), st));
@@ -363,6 +364,13 @@ class TcMlp : public MlpEngine {
       ProfScope ps(PC_MLP_WGRAD, st);
       NERF_TRY(gemm_wgrad(dzs_[D - 1 - i], in, L.in_a, L.in_b ? &lv.enc_pos : nullptr, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
     }
+    return 0;
+  }
+
+  int relu_bits(int level, int i, const uint32_t** bits, int* words_per_row) override {
+    if (level < 0 || level >= (int)levels_.size() || i < 0 || i >= s_.D + s_.C) { set_error("relu_bits: bad level / layer"); return 100001; }
+    *bits = levels_[level].bits[i];
+    *words_per_row = (i < s_.D ? s_.W : s_.Wc) / 32;
     return 0;
   }
 
@@ -528,7 +536,10 @@ class TcMlp : public MlpEngine {
     return 0;
   }
 
+  bool quarters() const { return (flags_ & NERF_FLAG_QUARTER_SCHEDULE) != 0; }
+
   bool split_;
+  unsigned flags_ = 0;
   MlpShape s_;
   long max_rows_ = 0;
   int pos_pitch_ = 0, dir_pitch_ = 0;
@@ -549,6 +560,6 @@ class TcMlp : public MlpEngine {
 
 }  // namespace
 
-MlpEngine* make_tc_mlp(bool split3) { return new TcMlp(split3); }
+MlpEngine* make_tc_mlp(bool split3, unsigned engine_flags) { return new TcMlp(split3, engine_flags); }
 
 }  // namespace nerf

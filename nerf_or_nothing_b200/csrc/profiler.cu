@@ -1,12 +1,15 @@
 // profiler.cu — in-stream CUDA-event timing of launch groups (see common.cuh).  Used by bench.py to measure
 // each kernel family's duration live inside the timed region; never enabled by default.
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "profiler.cuh"
 
 namespace nerf {
 
-Profiler* g_prof = nullptr;
+thread_local Profiler* g_prof = nullptr;
 
 static const char* kNames[PC_COUNT] = {
     "sample_t_vals", "cast_rays+encode", "mlp_fwd_gemm", "mlp_fwd_heads", "composite_fwd", "loss_gradient",
@@ -65,6 +68,44 @@ void prof_end(cudaStream_t st) {
   cudaEventRecord(p->open.e1, st);
   p->open.launches = launch_count() - p->open.launches;
   p->spans.push_back(p->open);
+}
+
+// ---- per-device kernel setup (declared in common.cuh)
+namespace {
+std::mutex g_dev_mu;
+std::map<std::pair<const void*, int>, std::pair<int, cudaError_t>> g_smem_set;  // (kernel, device) -> (bytes granted, status)
+std::map<int, int> g_sms;
+}  // namespace
+
+int ensure_kernel_smem(const void* kernel, int dyn_smem_bytes) {
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  auto key = std::make_pair(kernel, dev);
+  auto it = g_smem_set.find(key);
+  if (it == g_smem_set.end() || (it->second.second == cudaSuccess && it->second.first < dyn_smem_bytes)) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem_bytes);
+    g_smem_set[key] = std::make_pair(dyn_smem_bytes, e);
+    it = g_smem_set.find(key);
+  }
+  if (it->second.second != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed on device %d: %s", dyn_smem_bytes, dev,
+              cudaGetErrorString(it->second.second));
+    return (int)it->second.second;
+  }
+  return 0;
+}
+
+int device_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  auto it = g_sms.find(dev);
+  if (it != g_sms.end()) return it->second;
+  int sms = 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  g_sms[dev] = sms;
+  return sms;
 }
 
 }  // namespace nerf

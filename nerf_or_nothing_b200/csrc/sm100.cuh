@@ -131,7 +131,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---------------------------------------------------------------- A operand in tensor memory (".ts" MMAs)
 // For kind::f16 with M = 128 the A tile lives at lane = row, two consecutive K elements per 32-bit column (low half =
-// even k), 8 columns per K = 16 step; written with tcgen05.st.32x32b (validated on B200 by scratch/ts_mma_probe.cu).
+// even k), 8 columns per K = 16 step; written with tcgen05.st.32x32b (validated on B200 by scripts/ts_mma_probe.cu).
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {

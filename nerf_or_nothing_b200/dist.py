@@ -1,5 +1,5 @@
 """Data-parallel plumbing: one process per GPU, rays sharded across ranks, replicated parameters, ONE
-exchange per step (NCCL allreduce of the flat 2.19 MB gradient inside libnerfb200).  torch.distributed is used only for
+exchange per step (NCCL allreduce of the flat 2.19 MB gradient + sum(lossMult) + loss numerators inside libnerfb200).  torch.distributed is used only for
 rendezvous: shipping the NCCL unique id from rank 0 and for barriers / max-over-ranks timing in bench.py.
 The reference has no multi-GPU code at all (single `cudaSetDevice(0)`, ANU/AcceleratedMipNeRF.cpp:10)."""
 from __future__ import annotations
@@ -51,15 +51,18 @@ def attach(model, device=None):
     return rank, world
 
 
-def global_loss_scale(local_loss_mult_sum: float) -> float:
-    """Factor that turns a gradient normalised by the LOCAL sum(lossMult) into the global one (what the library does
-    on the device with a 4-byte allreduce before the backward pass)."""
-    import torch
-    import torch.distributed as dist
-
-    t = torch.tensor([local_loss_mult_sum], dtype=torch.float64)
-    dist.all_reduce(t)
-    return float(local_loss_mult_sum / t.item())
+def allreduce_step_buffer(grads_local_mean: np.ndarray, local_loss_mult_sum: float, local_losses):
+    """Host restatement of the library's ONE collective per step (include/nerfb200.h, nerf_mipnerf_comm_init): every rank
+    contributes [un-normalised gradient | sum(lossMult) | per-level loss numerators]; after a single sum-allreduce the
+    global 1 / sum(lossMult) turns the first part into the global mean gradient and the tail into the global losses.
+    `grads_local_mean` / `local_losses` are normalised by the LOCAL sum(lossMult) (what a single-process step returns)."""
+    g = np.asarray(grads_local_mean, np.float64)
+    losses = np.asarray(local_losses, np.float64).reshape(-1)
+    buf = np.concatenate([g * local_loss_mult_sum, [local_loss_mult_sum], losses * local_loss_mult_sum])
+    buf = allreduce_numpy(buf)
+    n = g.shape[0]
+    inv = 1.0 / buf[n]
+    return buf[:n] * inv, buf[n + 1:] * inv
 
 
 def allreduce_numpy(x: np.ndarray) -> np.ndarray:

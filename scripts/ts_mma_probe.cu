@@ -1,7 +1,7 @@
 // ts_mma_probe.cu — experiment (not product): does tcgen05.mma with the A operand in TENSOR MEMORY behave as assumed?
 // Assumption under test: for kind::f16, M=128, A[128 x K] lives in TMEM with lane = row and each 32-bit column holding
 // two consecutive K elements (low half = even k), K=16 per MMA = 8 columns; written by tcgen05.st.32x32b.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I nerf_or_nothing_b200/csrc scratch/ts_mma_probe.cu -o scratch/ts_mma_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I nerf_or_nothing_b200/csrc scripts/ts_mma_probe.cu -o scripts/ts_mma_probe
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 

@@ -68,7 +68,7 @@ def rel_err(a, b):
 def configs_pair(**kw):
     """Matching (nerf_config, orc_config) for the same hyper-parameters."""
     ncfg = nb.default_config(**kw)
-    okw = {k: v for k, v in kw.items() if k not in ("n_rays", "precision", "device", "chunk_rays", "seed")}
+    okw = {k: v for k, v in kw.items() if k not in ("n_rays", "precision", "device", "chunk_rays", "seed", "engine_flags")}
     ocfg = orc.default_config(**okw)
     return ncfg, ocfg
 

@@ -6,7 +6,7 @@ accumulator quarters: overwritten only after they were loaded, loaded only after
 
     python tests/protocol_model.py                       # shipped schedule vs the quarter schedule of the draft patch
 
-It answers two questions without a GPU: (1) is the protocol of `scratch/next_round/fused_split_quarters.patch` deadlock- and hazard-free over
+It answers two questions without a GPU: (1) is the protocol of `k_mlp_fused_split_q` (mlp_fused_split.cu) deadlock- and hazard-free over
 several tiles of the forward (8 trunk layers, skip at 4, condition layer) and of the dgrad chain, with exactly the parity
 expressions of the code; (2) what period per layer does each schedule give under the cycle costs measured with the
 in-kernel clock64 stamps (N=128 MMA 73 cycles -> 3.5 k per half of 48; one 32-column epilogue pass 1.45 k).

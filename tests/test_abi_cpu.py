@@ -36,7 +36,7 @@ def test_config_struct_layout_and_defaults():
     assert (c.deg_point, c.deg_view) == (16, 4)
     assert abs(c.coarse_loss_mult - 0.1) < 1e-7 and abs(c.resample_padding - 0.01) < 1e-7
     assert c.density_bias == 0.0 and c.rgb_padding == 0.0 and c.white_bkgd == 1
-    assert c.seed == 7 and ctypes.sizeof(c) == 96
+    assert c.seed == 7 and c.engine_flags == 0 and ctypes.sizeof(c) == 104
 
 
 def test_header_cites_reference_for_every_group():

@@ -1,7 +1,7 @@
 """CPU, world_size = 2 over gloo: the data-parallel host logic (ray sharding, id broadcast, global normaliser,
 gradient allreduce) with the CPU oracle standing in for the device step.  The property the multi-GPU path relies on:
-sum over ranks of per-shard gradients, each scaled to the GLOBAL sum(lossMult), equals the single-process gradient of
-the whole batch — and therefore every rank applies the identical Adam step."""
+sum over ranks of the UN-normalised per-shard gradients divided by the allreduced sum(lossMult) — one collective —
+equals the single-process gradient (and loss) of the whole batch, so every rank applies the identical Adam step."""
 import os
 import socket
 import sys
@@ -48,10 +48,11 @@ def _worker(rank, world, port, out_dir):
     srays, spix = nd.shard_batch(rays, pix, rank, world)
     assert spix.shape[0] == hi - lo
     o = orc.train_gradient(cfg, params, srays, spix, u[:, lo:hi], prec="f64")
-    scale = nd.global_loss_scale(float(srays["loss_mults"].astype(np.float64).sum()))
-    g = nd.allreduce_numpy(o["grads"] * scale)
+    # the library's protocol: ONE allreduce of [un-normalised gradient | sum(lm) | loss numerators] (nerfb200.h, comm_init)
+    g, losses = nd.allreduce_step_buffer(o["grads"], float(srays["loss_mults"].astype(np.float64).sum()), o["loss"])
     full = orc.train_gradient(cfg, params, rays, pix, u, prec="f64")
     err = np.abs(g - full["grads"]).max() / np.abs(full["grads"]).max()
+    err = max(err, float(np.abs(losses - np.asarray(full["loss"], np.float64)).max() / np.abs(full["loss"]).max()))
     p1, _, _ = orc.adam_step(params, g, np.zeros_like(g), np.zeros_like(g), 1e-3, 1, 0, prec="f64")
     np.save(os.path.join(out_dir, f"p{rank}.npy"), p1)
     np.save(os.path.join(out_dir, f"e{rank}.npy"), np.array([err, lo, hi]))

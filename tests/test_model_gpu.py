@@ -172,13 +172,20 @@ def test_chunked_equals_unchunked_and_deterministic():
 
 
 def test_render_matches_oracle_forward():
-    R = 200  # > chunk: exercises the chunk loop; Philox path (no explicit uniforms), non-randomized too
+    """Evaluation is deterministic (SN/MipNerfModel.cs:36-97 renders with randomized = false): a handle configured for
+    jittered TRAINING still renders the midpoint samples, twice the same bits, without touching its training RNG state."""
+    R = 200  # > chunk: exercises the chunk loop
     for randomized in (1, 0):
         m, ncfg, ocfg = _model(64, randomized=randomized, **SMALL)
         S = ncfg.n_samples
         rays, pix, _ = batch(R, S)
-        u = np.stack([orc.sampling_uniforms(7, 0, lv, 0, R, S + 1) for lv in range(2)])  # seed 7, step 0 = library default
+        u = np.zeros((2, R, S + 1), np.float32)  # ignored: the oracle evaluates with randomized = 0
+        m.set_sampling_uniforms(np.full((2, 64, S + 1), 0.75, np.float32))  # explicit training uniforms must not leak into a render
         rgb, depth, acc = m.render(rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+        again = m.render(rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+        for x, y in zip((rgb, depth, acc), again):
+            np.testing.assert_array_equal(x, y)
+        ocfg.randomized = 0
         o = orc.train_gradient(ocfg, orc.init_params(ocfg, 7), rays, pix, u, with_backward=False, prec="f64")
         np.testing.assert_allclose(rgb, o["comp_rgb"][1], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(acc, o["acc"][1], rtol=1e-4, atol=1e-5)

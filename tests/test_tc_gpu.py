@@ -70,7 +70,8 @@ def _stable_inputs(ocfg, params, M, P, Dd, margin, seed):
 
 
 @pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
-@pytest.mark.parametrize("cfgkw,R", [(NET, 64), (NET, 3), (SMALL, 5)], ids=["8x256-M4096", "8x256-M192", "small-M160"])
+@pytest.mark.parametrize("cfgkw,R", [(NET, 64), (NET, 3), (SMALL, 5), (NET, 300)],
+                         ids=["8x256-M4096", "8x256-M192", "small-M160", "8x256-M19200"])  # M19200: 75 head partials -> wide reduction
 def test_tc_mlp_backward(precision, cfgkw, R):
     """dgrad / wgrad GEMMs (MN-major operands, split reduction) against the fp64 oracle.
     fp32_tc: <= 1e-4 of each tensor's scale on ReLU-stable samples (margin 2e-4 >> the 3e-6 forward error).
@@ -142,25 +143,32 @@ def test_tc_whole_step_and_training(precision):
         assert abs(losses[0] - losses[1]) <= 1e-2 * losses[1], (step, losses)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
+LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO_FUSED_DGRAD
+# engine schedules that must agree with the layer-by-layer kernels: the shipped one and, in the fp32-accurate mode, the
+# quarter-granular variant of the fused kernels (nerf_config.engine_flags)
+SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("fp32_tc", nb.FLAG_QUARTER_SCHEDULE)]
+SCHED_IDS = ["bf16", "fp32_tc", "fp32_tc-quarters"]
+
+
+@pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
 @pytest.mark.parametrize("R", [200, 1], ids=["R200-chunked", "R1"])
-def test_fused_forward_render(R, precision, monkeypatch):
+def test_fused_forward_render(R, precision, flags):
     """Rendering runs the whole MLP as ONE kernel with TMEM-resident activations (mlp_fused.cu / mlp_fused_split.cu).
     It must agree with the fp64 oracle within the mode's tolerance and with the layer-by-layer chain (same operands,
     same roundings between layers) far tighter; ragged last tile (R*S not a multiple of the tile rows) and the tile loop
-    included."""
-    m, ncfg, ocfg = _model(64, precision, **NET)
+    included.  Rendering is deterministic (no jitter) whatever cfg.randomized says."""
+    m, ncfg, ocfg = _model(64, precision, engine_flags=flags, **NET)
+    m2, _, _ = _model(64, precision, engine_flags=nb.FLAG_NO_FUSED_FORWARD, **NET)
     S = ncfg.n_samples
     rays, pix, _ = batch(R, S)
     params = _params_with_biases(ocfg)
     m.set_params(params)
-    u = np.stack([orc.sampling_uniforms(7, 0, lv, 0, R, S + 1) for lv in range(2)])
+    m2.set_params(params)
+    u = np.zeros((2, R, S + 1), np.float32)
     args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
-    monkeypatch.delenv("NERF_NO_FUSED_FORWARD", raising=False)
     rgb, depth, acc = m.render(*args)
-    monkeypatch.setenv("NERF_NO_FUSED_FORWARD", "1")
-    rgb2, depth2, acc2 = m.render(*args)
-    monkeypatch.delenv("NERF_NO_FUSED_FORWARD")
+    rgb2, depth2, acc2 = m2.render(*args)
+    ocfg.randomized = 0
     o = orc.train_gradient(ocfg, params, rays, pix, u, with_backward=False, prec="f64")
     print(f"{precision}: fused vs layered rgb {np.abs(rgb - rgb2).max():.2e}  fused vs f64: rgb {np.abs(rgb - o['comp_rgb'][1]).max():.2e} "
           f"acc {np.abs(acc - o['acc'][1]).max():.2e}")
@@ -173,79 +181,63 @@ def test_fused_forward_render(R, precision, monkeypatch):
     np.testing.assert_allclose(acc, acc2, atol=0.1 * tol)
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
-def test_fused_training_forward_matches_layered(precision, monkeypatch):
+def _gradient_step(m, params, rays, pix, u):
+    m.set_params(params)
+    m.set_pixels(pix)
+    m.set_sampling_uniforms(u)
+    m.GetGradient(rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"])
+    return m.get_gradients().copy(), m.get_loss()[1]
+
+
+@pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
+def test_fused_training_forward_matches_layered(precision, flags):
     """The training forward is the same fused kernel with the activation planes and ReLU bit planes written out for the
     backward pass: a whole gradient step through it must equal the step through the layer-by-layer forward."""
     R = 24
-    m, ncfg, ocfg = _model(R, precision, **NET)
-    S = ncfg.n_samples
-    rays, pix, u = batch(R, S)
-    m.set_params(_params_with_biases(ocfg))
-    m.set_pixels(pix)
-    m.set_sampling_uniforms(u)
-    args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"])
-    monkeypatch.delenv("NERF_NO_FUSED_TRAIN_FORWARD", raising=False)
-    m.GetGradient(*args)
-    g1, l1 = m.get_gradients().copy(), m.get_loss()[1]
-    monkeypatch.setenv("NERF_NO_FUSED_TRAIN_FORWARD", "1")
-    m.GetGradient(*args)
-    g2, l2 = m.get_gradients().copy(), m.get_loss()[1]
-    monkeypatch.delenv("NERF_NO_FUSED_TRAIN_FORWARD")
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
+    m2, _, _ = _model(R, precision, engine_flags=flags | nb.FLAG_NO_FUSED_TRAIN_FORWARD, **NET)
+    rays, pix, u = batch(R, ncfg.n_samples)
+    params = _params_with_biases(ocfg)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
     print(f"{precision}: loss {l1:.8f} vs {l2:.8f}; grad max-norm err {rel_err(g1, g2):.2e}")
     assert abs(l1 - l2) <= 1e-6 * abs(l2)
     # accumulation order differs between the two forwards, so a few ReLU masks near zero flip (see the whole-step test)
     assert rel_err(g1, g2) <= 1e-3
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
-def test_fused_dgrad_chain_matches_layered(precision, monkeypatch):
+@pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
+def test_fused_dgrad_chain_matches_layered(precision, flags):
     """The backward dgrad chain of the trunk is one kernel (dZ resident in tensor memory between layers, each layer's dZ
     written once for the wgrad GEMMs).  Same operands, the same ReLU bit masks and the same roundings between layers as
     the per-layer dgrad launches, so the parameter gradients agree to accumulation-order noise."""
     R = 24
-    m, ncfg, ocfg = _model(R, precision, **NET)
-    S = ncfg.n_samples
-    rays, pix, u = batch(R, S)
-    m.set_params(_params_with_biases(ocfg))
-    m.set_pixels(pix)
-    m.set_sampling_uniforms(u)
-    args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"], rays["loss_mults"])
-    monkeypatch.delenv("NERF_NO_FUSED_DGRAD", raising=False)
-    m.GetGradient(*args)
-    g1 = m.get_gradients().copy()
-    monkeypatch.setenv("NERF_NO_FUSED_DGRAD", "1")
-    m.GetGradient(*args)
-    g2 = m.get_gradients().copy()
-    monkeypatch.delenv("NERF_NO_FUSED_DGRAD")
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
+    m2, _, _ = _model(R, precision, engine_flags=flags | nb.FLAG_NO_FUSED_DGRAD, **NET)
+    rays, pix, u = batch(R, ncfg.n_samples)
+    params = _params_with_biases(ocfg)
+    g1, _ = _gradient_step(m, params, rays, pix, u)
+    g2, _ = _gradient_step(m2, params, rays, pix, u)
     print(f"{precision}: fused vs layered dgrad chain: grad max-norm err {rel_err(g1, g2):.2e}")
     assert np.isfinite(g1).all()
     assert rel_err(g1, g2) <= 1e-5
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
-def test_fused_kernels_many_tiles_per_cta(precision, monkeypatch):
+@pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
+def test_fused_kernels_many_tiles_per_cta(precision, flags):
     """More row tiles than CTAs (700 rays x 64 samples = 350 tiles / 175 tile pairs on 148 SMs, ragged tail): every CTA of
     the persistent fused kernels walks several tiles, so the mbarrier phase bookkeeping across tiles is exercised.  Render
     and a whole gradient step must match the layer-by-layer kernels."""
     R = 700
-    m, ncfg, ocfg = _model(R, precision, **NET)
-    S = ncfg.n_samples
-    rays, pix, u = batch(R, S)
-    m.set_params(_params_with_biases(ocfg))
-    m.set_pixels(pix)
-    m.set_sampling_uniforms(u)
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
+    m2, _, _ = _model(R, precision, engine_flags=LAYERED, **NET)
+    rays, pix, u = batch(R, ncfg.n_samples)
+    params = _params_with_biases(ocfg)
     rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
-    for var in ("NERF_NO_FUSED_FORWARD", "NERF_NO_FUSED_TRAIN_FORWARD", "NERF_NO_FUSED_DGRAD"):
-        monkeypatch.delenv(var, raising=False)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
     rgb1, _, acc1 = m.render(*rargs)
-    m.GetGradient(*rargs, rays["loss_mults"])
-    g1, l1 = m.get_gradients().copy(), m.get_loss()[1]
-    for var in ("NERF_NO_FUSED_FORWARD", "NERF_NO_FUSED_TRAIN_FORWARD", "NERF_NO_FUSED_DGRAD"):
-        monkeypatch.setenv(var, "1")
-    rgb2, _, acc2 = m.render(*rargs)
-    m.GetGradient(*rargs, rays["loss_mults"])
-    g2, l2 = m.get_gradients().copy(), m.get_loss()[1]
+    rgb2, _, acc2 = m2.render(*rargs)
     print(f"{precision}: render rgb diff {np.abs(rgb1 - rgb2).max():.2e}, loss {l1:.8f} vs {l2:.8f}, grad err {rel_err(g1, g2):.2e}")
     tol = TOL[precision]
     assert np.isfinite(rgb1).all() and np.isfinite(g1).all()
@@ -255,12 +247,12 @@ def test_fused_kernels_many_tiles_per_cta(precision, monkeypatch):
     assert rel_err(g1, g2) <= 2e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
-def test_tc_step_is_bitwise_reproducible(precision):
+@pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
+def test_tc_step_is_bitwise_reproducible(precision, flags):
     """No atomics anywhere on the tensor-core path (wgrad partials and head partials are reduced in a fixed order): the same
     batch gives bit-identical gradients, loss and rendered pixels on every run."""
     R = 48
-    m, ncfg, ocfg = _model(R, precision, **NET)
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
     S = ncfg.n_samples
     rays, pix, u = batch(R, S)
     m.set_pixels(pix)

@@ -17,17 +17,26 @@ def layer_views(cfg, shapes, params):
     return Ws, bs
 
 
-def mlp(cfg, shapes, params, enc_pos, enc_dir):
+def mlp(cfg, shapes, params, enc_pos, enc_dir, masks=None, masks_out=None):
+    """masks (optional): one bool tensor per hidden layer; the layer then computes z * mask instead of relu(z) — the
+    network as a path that took exactly those ReLU branches (what a gradient under imposed masks needs).
+    masks_out (optional list): receives z > 0 of every hidden layer."""
     Ws, bs = layer_views(cfg, shapes, params)
     D, Cn = cfg.net_depth, cfg.net_depth_condition
+
+    def act(z, i):
+        if masks_out is not None:
+            masks_out.append(z.detach() > 0)
+        return torch.relu(z) if masks is None else z * masks[i].reshape(z.shape).to(z.dtype)
+
     h = enc_pos
     for i in range(D):
         x = torch.cat([h, enc_pos], -1) if (cfg.skip_layer > 0 and i % cfg.skip_layer == 0 and i > 0) else h
-        h = torch.relu(x @ Ws[i].T + bs[i])
+        h = act(x @ Ws[i].T + bs[i], i)
     raw_density = (h @ Ws[D].T + bs[D])[..., 0]
     c = torch.cat([h, enc_dir], -1)
     for i in range(Cn):
-        c = torch.relu(c @ Ws[D + 1 + i].T + bs[D + 1 + i])
+        c = act(c @ Ws[D + 1 + i].T + bs[D + 1 + i], D + i)
     raw_rgb = c @ Ws[D + Cn + 1].T + bs[D + Cn + 1]
     return raw_density, raw_rgb
 
@@ -73,8 +82,9 @@ def render(rgb, density, t, d, white=True):
     return comp, acc, w
 
 
-def total_loss(cfg, shapes, params, rays, pixels, t_levels):
-    """t_levels: list of [R,S+1] tensors (treated as constants: no gradient through sampling)."""
+def total_loss(cfg, shapes, params, rays, pixels, t_levels, masks_levels=None, masks_out=None):
+    """t_levels: list of [R,S+1] tensors (treated as constants: no gradient through sampling).
+    masks_levels / masks_out: per level, the `masks` / `masks_out` of mlp()."""
     o, d = rays["origins"], rays["directions"]
     lm = rays["loss_mults"]
     loss = 0.0
@@ -83,7 +93,10 @@ def total_loss(cfg, shapes, params, rays, pixels, t_levels):
         mean, cov = cast_rays(t, o, d, rays["radii"])
         ep = ipe(mean, cov, cfg.deg_point)
         ed = dir_enc(d, cfg.deg_view)[:, None, :].expand(-1, ep.shape[1], -1)
-        rd, rr = mlp(cfg, shapes, params, ep, ed)
+        mo = [] if masks_out is not None else None
+        rd, rr = mlp(cfg, shapes, params, ep, ed, None if masks_levels is None else masks_levels[lv], mo)
+        if masks_out is not None:
+            masks_out.append(mo)
         density = torch.nn.functional.softplus(rd + cfg.density_bias)
         rgb = torch.sigmoid(rr) * (1 + 2 * cfg.rgb_padding) - cfg.rgb_padding
         comp, acc, w = render(rgb, density, t, d, bool(cfg.white_bkgd))
