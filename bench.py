@@ -344,7 +344,7 @@ def measure_train(job, args, precision, R, host_batches, dev_batches, want_e2e=T
 
     torch = job.torch
     S, pool = N_SAMPLES, len(dev_batches)
-    cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[precision], device=job.local, **model_kw())
+    cfg = nb.default_config(n_rays=R, precision=nb.PRECISIONS[precision], device=job.local, engine_flags=args.engine_flags, **model_kw())
     model = nb.AcceleratedMipNeRF(cfg)
     opt = nb.AcceleratedAdamOptimizer(model.GetLayerSizes(), device=job.local)
     if job.world > 1:
@@ -434,7 +434,7 @@ def measure_render(job, args, precision, steps=None):
     total, chunk = 640000, 16384
     lo, hi = nd.shard_range(total, job.rank, job.world)
     n = hi - lo
-    cfg = nb.default_config(n_rays=chunk, precision=nb.PRECISIONS[precision], device=job.local, **model_kw())
+    cfg = nb.default_config(n_rays=chunk, precision=nb.PRECISIONS[precision], device=job.local, engine_flags=args.engine_flags, **model_kw())
     model = nb.AcceleratedMipNeRF(cfg)
     rays, _ = synthetic_rays(n, width=800, height=800, n_views=1, seed=7 + job.rank)
     hb = [rays[k] for k in ("origins", "directions", "radii", "nears", "fars")]
@@ -737,6 +737,7 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU (weak scaling)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="configs[2] strong scaling: total rays per step, split evenly over the ranks (overrides --rays)")
+    ap.add_argument("--engine-flags", type=int, default=0, help="nerf_config.engine_flags (NERF_FLAG_*): A/B runs of alternative schedules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the headline configuration (no modes / render / compositing sub-records)")
     ap.add_argument("--profiler-run", action="store_true", help="under ncu only: do not raise --warmup to 3 (the line printed is not a bench value)")

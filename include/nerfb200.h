@@ -292,6 +292,12 @@ int nerf_mipnerf_train_step_dataset(nerf_mipnerf* h, nerf_adam* a, nerf_dataset*
 /* mse and MseToPsnr (SN/MipHelpers.cs:672) of two float arrays (host pointers unless on_device). */
 int nerf_image_error(const float* a, const float* b, long n_floats, int on_device, double* mse,
                      double* psnr);
+/* ComputeSsim / ComputeSsimAverage (SN/MipHelpers.cs:688-737): 2-D normalised Gaussian window (filter_size x filter_size,
+ * odd, <= 15; reference defaults 11, 1.5, k1 = 0.01, k2 = 0.03), ZERO-padded borders (VectorImage.Convolve, :903-927),
+ * variances AND covariance clamped at 0 (:705-712), mean over pixels and the 3 channels.  Images are [height, width, 3]
+ * floats; ssim_map (may be NULL) receives the per-pixel, per-channel map. */
+int nerf_image_ssim(const float* a, const float* b, int width, int height, float max_val, int filter_size,
+                    float filter_sigma, float k1, float k2, int on_device, double* ssim_mean, float* ssim_map);
 /* LearningRateDecay (SN/MipHelpers.cs:758-773). */
 float nerf_learning_rate_decay(int step, float lr_init, float lr_final, int max_steps,
                                int lr_delay_steps, float lr_delay_mult);

@@ -122,6 +122,7 @@ _SIGNATURES = {
     "nerf_dataset_gather": [_VP, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP],
     "nerf_mipnerf_train_step_dataset": [_VP, _VP, _VP, _I, C.c_uint64, _F, C.POINTER(_F)],
     "nerf_image_error": [_VP, _VP, _L, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "nerf_image_ssim": [_VP, _VP, _I, _I, _F, _I, _F, _F, _F, _I, C.POINTER(C.c_double), _VP],
     "nerf_learning_rate_decay": [_I, _F, _F, _I, _I, _F],
     "nerf_checkpoint_save": [_VP, _VP, C.c_char_p],
     "nerf_checkpoint_load": [_VP, _VP, C.c_char_p],
@@ -456,6 +457,20 @@ def image_error(a, b):
     mse, psnr = C.c_double(), C.c_double()
     check(lib().nerf_image_error(_hp(a), _hp(b), a.size, 0, C.byref(mse), C.byref(psnr)))
     return mse.value, psnr.value
+
+
+def image_ssim(a, b, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03, want_map=False):
+    """ComputeSsimAverage (SN/MipHelpers.cs:728-737) of two [H, W, 3] images, computed on the device.
+    Returns the mean SSIM, or (mean, map [H, W, 3]) with want_map."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    if a.shape != b.shape or a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("image_ssim: two [H, W, 3] images expected")
+    mean = C.c_double()
+    m = np.empty_like(a) if want_map else None
+    check(lib().nerf_image_ssim(_hp(a), _hp(b), a.shape[1], a.shape[0], max_val, filter_size, filter_sigma, k1, k2, 0,
+                                C.byref(mean), _hp(m) if want_map else None))
+    return (mean.value, m) if want_map else mean.value
 
 
 def comm_unique_id() -> bytes:

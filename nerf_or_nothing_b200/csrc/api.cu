@@ -969,6 +969,7 @@ int nerf_mipnerf_train_step_dataset(nerf_mipnerf* h, nerf_adam* a, nerf_dataset*
   return finish_step(h, a, lr, loss_out);
 }
 
+#define STAGE_BEGIN_() do { int n_ = 0; if (cudaGetDeviceCount(&n_) != cudaSuccess || n_ <= 0) { cudaGetLastError(); set_error("no CUDA device available: libnerfb200 has no CPU path"); return NERF_ERR_NO_DEVICE; } } while (0)
 // ---- image metrics ----------------------------------------------------------------------------
 // mse over n floats and psnr = -10/ln(10) * ln(mse) (SN/MipHelpers.cs:672); on_device: a/b are device pointers
 int nerf_image_error(const float* a, const float* b, long n, int on_device, double* mse, double* psnr) {
@@ -990,6 +991,39 @@ int nerf_image_error(const float* a, const float* b, long n, int on_device, doub
   const double m = sq / (double)n;
   if (mse) *mse = m;
   if (psnr) *psnr = -10.0 / log(10.0) * log(m);
+  return 0;
+}
+
+// ComputeSsimAverage / ComputeSsim (SN/MipHelpers.cs:688-737): images [height, width, 3]; ssim_map (optional) gets the
+// per-pixel, per-channel map.  on_device: a / b / ssim_map are device pointers.
+int nerf_image_ssim(const float* a, const float* b, int width, int height, float max_val, int filter_size, float filter_sigma,
+                    float k1, float k2, int on_device, double* ssim_mean, float* ssim_map) {
+  if (!a || !b || width <= 0 || height <= 0) { set_error("image_ssim: bad arguments"); return NERF_ERR_INVALID; }
+  STAGE_BEGIN_();
+  struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+  } da, db, dmap, dsum;
+  const size_t n = (size_t)width * height * 3;
+  const long nb = ssim_blocks(width, height);
+  NERF_CUDA(cudaMalloc(&dsum.p, (size_t)nb * sizeof(double)));
+  if (!on_device) {
+    NERF_CUDA(cudaMalloc(&da.p, n * 4));
+    NERF_CUDA(cudaMalloc(&db.p, n * 4));
+    NERF_CUDA(cudaMemcpy(da.p, a, n * 4, cudaMemcpyHostToDevice));
+    NERF_CUDA(cudaMemcpy(db.p, b, n * 4, cudaMemcpyHostToDevice));
+    if (ssim_map) NERF_CUDA(cudaMalloc(&dmap.p, n * 4));
+  }
+  float* map_dev = on_device ? ssim_map : (float*)dmap.p;
+  NERF_TRY(launch_ssim(on_device ? a : (const float*)da.p, on_device ? b : (const float*)db.p, width, height, max_val, filter_size,
+                       filter_sigma, k1, k2, map_dev, (double*)dsum.p, nullptr));
+  std::vector<double> sums;
+  try { sums.resize((size_t)nb); } catch (const std::exception& e) { set_error("image_ssim: %s", e.what()); return NERF_ERR_INVALID; }
+  NERF_CUDA(cudaMemcpy(sums.data(), dsum.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!on_device && ssim_map) NERF_CUDA(cudaMemcpy(ssim_map, dmap.p, n * 4, cudaMemcpyDeviceToHost));
+  double t = 0.0;
+  for (long i = 0; i < nb; i++) t += sums[(size_t)i];  // block order: bitwise reproducible
+  if (ssim_mean) *ssim_mean = t / (double)n;
   return 0;
 }
 

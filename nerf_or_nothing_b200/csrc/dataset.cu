@@ -5,6 +5,8 @@
 // live in HBM once; a step draws its record indices on the device from the counter-based Philox stream and gathers them
 // straight into the structure-of-arrays batch the kernels read — no per-step host traffic at all.
 // Record (16 floats, SN/BinDataset.cs:40-49): origin(3) direction(3) viewdir(3) radius near far lossmult rgb(3).
+#include <cmath>
+
 #include "kernels.cuh"
 
 namespace nerf {
@@ -57,7 +59,96 @@ __global__ void k_sq_err(const float* __restrict__ a, const float* __restrict__ 
   }
 }
 
+// ---- SSIM (SN/MipHelpers.cs:688-757 ComputeSsim / ComputeSsimAverage; VectorImage.Convolve :903-927) -----------------
+// The reference convolves five whole images (a, b, a^2, b^2, ab) with a normalised size x size Gaussian over a ZERO-padded
+// border, one scalar triple loop per image.  Here a block owns a 16 x 16 pixel tile: both images' (16 + size - 1)^2 halo
+// tiles are staged once in shared memory, each thread accumulates the five windowed sums of its pixel and channel in the
+// reference's tap order (kx outer, ky inner), and the SSIM map value is formed in registers.  Image layout: [height,
+// width, 3] floats — pixel (x, y) of the reference's VectorImage[x, y] at (y * width + x) * 3 (the filter is symmetric, so
+// the result does not depend on which axis is called x).
+constexpr int kSsimTile = 16, kSsimMaxFilter = 15;
+struct SsimFilter { float w[kSsimMaxFilter * kSsimMaxFilter]; };
+
+__global__ void __launch_bounds__(kSsimTile * kSsimTile)
+k_ssim(const float* __restrict__ a, const float* __restrict__ b, int W, int H, int fs, SsimFilter filt, float c1, float c2,
+       float* __restrict__ map_out, double* __restrict__ block_sums) {
+  extern __shared__ float tile[];  // [2][span][span][3]
+  const int pad = fs / 2, span = kSsimTile + fs - 1;
+  const int x0 = blockIdx.x * kSsimTile - pad, y0 = blockIdx.y * kSsimTile - pad;
+  float* ta = tile;
+  float* tb = tile + span * span * 3;
+  for (int i = threadIdx.x; i < span * span; i += blockDim.x) {
+    const int ty = i / span, tx = i % span, x = x0 + tx, y = y0 + ty;
+    const bool in = x >= 0 && x < W && y >= 0 && y < H;  // zero padding (MipHelpers.cs:909-911)
+    const long g = ((long)y * W + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ta[i * 3 + c] = in ? a[g + c] : 0.f; tb[i * 3 + c] = in ? b[g + c] : 0.f; }
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % kSsimTile, ly = threadIdx.x / kSsimTile;
+  const int x = blockIdx.x * kSsimTile + lx, y = blockIdx.y * kSsimTile + ly;
+  double part = 0.0;
+  if (x < W && y < H) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float m0 = 0.f, m1 = 0.f, s00 = 0.f, s11 = 0.f, s01 = 0.f;
+      for (int kx = 0; kx < fs; kx++)
+        for (int ky = 0; ky < fs; ky++) {  // MipHelpers.cs:917-923
+          const float w = filt.w[kx * fs + ky];
+          const float va = ta[((ly + ky) * span + lx + kx) * 3 + c], vb = tb[((ly + ky) * span + lx + kx) * 3 + c];
+          m0 = __fadd_rn(m0, __fmul_rn(va, w)); m1 = __fadd_rn(m1, __fmul_rn(vb, w));
+          s00 = __fadd_rn(s00, __fmul_rn(__fmul_rn(va, va), w)); s11 = __fadd_rn(s11, __fmul_rn(__fmul_rn(vb, vb), w));
+          s01 = __fadd_rn(s01, __fmul_rn(__fmul_rn(va, vb), w));
+        }
+      const float mu00 = __fmul_rn(m0, m0), mu11 = __fmul_rn(m1, m1), mu01 = __fmul_rn(m0, m1);
+      const float g00 = fmaxf(__fsub_rn(s00, mu00), 0.f), g11 = fmaxf(__fsub_rn(s11, mu11), 0.f), g01 = fmaxf(__fsub_rn(s01, mu01), 0.f);  // :705-712
+      const float num = __fmul_rn(__fadd_rn(__fmul_rn(mu01, 2.f), c1), __fadd_rn(__fmul_rn(g01, 2.f), c2));  // :723
+      const float den = __fmul_rn(__fadd_rn(__fadd_rn(mu00, mu11), c1), __fadd_rn(__fadd_rn(g00, g11), c2));  // :724
+      const float v = __fdiv_rn(num, den);
+      if (map_out) map_out[((long)y * W + x) * 3 + c] = v;
+      part += (double)v;
+    }
+  }
+  // fixed-order block sum (fp64), one partial per block; the host adds the partials in block order
+  __shared__ double red[kSsimTile * kSsimTile / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kSsimTile * kSsimTile / 32; w++) t += red[w];
+    block_sums[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
 }  // namespace
+
+// mean SSIM over pixels and channels; block_sums: >= ssim_blocks(W, H) doubles of device scratch
+long ssim_blocks(int W, int H) { return cdiv(W, kSsimTile) * cdiv(H, kSsimTile); }
+int launch_ssim(const float* a, const float* b, int W, int H, float max_val, int filter_size, float filter_sigma, float k1, float k2,
+                float* map_out, double* block_sums, cudaStream_t st) {
+  if (filter_size < 1 || filter_size > kSsimMaxFilter || !(filter_size & 1)) { set_error("ssim: filter size must be odd and <= %d", kSsimMaxFilter); return 100001; }
+  SsimFilter f;
+  {  // CreateGaussianFilter (MipHelpers.cs:739-756), fp32 like the original
+    const int hs = filter_size / 2;
+    float sum = 0.f;
+    for (int i = 0; i < filter_size; i++)
+      for (int j = 0; j < filter_size; j++) {
+        const float x = (float)(i - hs), y = (float)(j - hs);
+        f.w[i * filter_size + j] = expf(-(x * x + y * y) / (2 * filter_sigma * filter_sigma));
+        sum += f.w[i * filter_size + j];
+      }
+    for (int i = 0; i < filter_size * filter_size; i++) f.w[i] /= sum;
+  }
+  const float c1 = powf(k1 * max_val, 2.f), c2 = powf(k2 * max_val, 2.f);  // :714-715
+  const int span = kSsimTile + filter_size - 1;
+  const size_t smem = (size_t)2 * span * span * 3 * sizeof(float);
+  k_ssim<<<dim3((unsigned)cdiv(W, kSsimTile), (unsigned)cdiv(H, kSsimTile)), kSsimTile * kSsimTile, smem, st>>>(a, b, W, H, filter_size, f, c1, c2,
+                                                                                                                 map_out, block_sums);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
 
 int launch_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, int R, long* idx, cudaStream_t st) {
   k_draw_indices<<<(unsigned)cdiv(R, 256), 256, 0, st>>>(seed, slot0, step, n, R, idx);

@@ -6,75 +6,13 @@
 // block stages a [32 samples x 6*deg] tile in shared memory and streams it out with 128-bit stores.
 // The fused kernel goes straight from t-values to encodings and can emit the bf16 hi/lo planes the
 // tcgen05 MLP consumes, so mean/cov never touch HBM.
+#include "encode_rows.cuh"
 #include "kernels.cuh"
 
 namespace nerf {
 namespace {
 
-struct Gauss { float mx, my, mz, cx, cy, cz; };
-
-// B.1 in the reference's operation order (.cu:298-316), with explicitly rounded (never FMA-contracted)
-// ops: IPE multiplies the mean by up to 2^15, so a 1-ulp difference in the mean would show up as ~1e-2 rad
-// in the highest frequency.  With this the Gaussian is bit-identical to the CPU oracle's for the same t.
-__device__ __forceinline__ Gauss frustum_to_gaussian(float t0, float t1, float radius, float3 o, float3 d) {
-#define M_(a, b) __fmul_rn(a, b)
-#define A_(a, b) __fadd_rn(a, b)
-#define S_(a, b) __fsub_rn(a, b)
-#define D_(a, b) __fdiv_rn(a, b)
-  const float mu = D_(A_(t0, t1), 2.f), hw = D_(S_(t1, t0), 2.f);
-  const float mu2 = M_(mu, mu), hw2 = M_(hw, hw);
-  const float den = A_(M_(3.f, mu2), hw2);
-  const float t_mean = A_(mu, D_(M_(M_(2.f, mu), hw2), den));                                         // .cu:306
-  const float t_var = S_(D_(hw2, 3.f), D_(M_(D_(4.f, 15.f), M_(M_(hw2, hw2), S_(M_(12.f, mu2), hw2))), M_(den, den)));  // .cu:307
-  const float r_var = M_(M_(radius, radius),
-                         S_(A_(D_(mu2, 4.f), M_(D_(5.f, 12.f), hw2)), D_(M_(D_(4.f, 15.f), M_(hw2, hw2)), den)));       // .cu:308
-  const float ddx = M_(d.x, d.x), ddy = M_(d.y, d.y), ddz = M_(d.z, d.z);
-  const float dmag = fmaxf(1e-10f, A_(A_(ddx, ddy), ddz));                                            // .cu:311
-  Gauss g;
-  g.mx = A_(M_(d.x, t_mean), o.x); g.my = A_(M_(d.y, t_mean), o.y); g.mz = A_(M_(d.z, t_mean), o.z);  // .cu:310
-  g.cx = A_(M_(t_var, ddx), M_(r_var, S_(1.f, D_(ddx, dmag))));                                       // .cu:313-316
-  g.cy = A_(M_(t_var, ddy), M_(r_var, S_(1.f, D_(ddy, dmag))));
-  g.cz = A_(M_(t_var, ddz), M_(r_var, S_(1.f, D_(ddz, dmag))));
-#undef M_
-#undef A_
-#undef S_
-#undef D_
-  return g;
-}
-
-// exp(-.5*var*4^f) * {sin,cos}(mean*2^f)  (.cu:185-186,196-204).
-// The argument mean*2^f reaches 2^15*|x| ~ 2e5 rad, where sincosf falls into its slow Payne-Hanek path.  Instead the
-// mean is converted ONCE per axis to half-turns v = mean/pi as a float-float (vh + vl, ~2^-48 relative); scaling by
-// 2^f is exact, sincospif reduces its argument exactly, and the tiny tail vl*2^f enters through a second-order
-// rotation.  Result: ~2 ulp of the correctly rounded sin/cos of the reference's exact argument, at a fixed cost.
-struct HalfTurns { float hi, lo; };
-__device__ __forceinline__ HalfTurns to_half_turns(float mean) {
-  const float kInvPiHi = 0.31830987334251404f, kInvPiLo = 1.2841276486597053e-08f;
-  HalfTurns v;
-  v.hi = __fmul_rn(mean, kInvPiHi);
-  v.lo = __fmaf_rn(mean, kInvPiHi, -v.hi) + mean * kInvPiLo;
-  return v;
-}
-// `fast`: the output is rounded to a single bf16 plane (2^-9 relative), so after the same exact reduction to [-1, 1]
-// half-turns the SFU sin/cos (absolute error < 5e-7 on [-pi, pi]) replace sincospif's polynomials.
-__device__ __forceinline__ void ipe_pair(HalfTurns v, float var, float scale, float& s, float& c, bool fast = false) {
-  const float x = __fmul_rn(0.5f, __fmul_rn(__fmul_rn(var, scale), scale));  // .5*var*4^f, the reference's rounding
-  if (x > 87.f) { s = 0.f; c = 0.f; return; }                               // exp(-x) < 1.2e-38: below fp32 normals
-  const float e = exp2f(-1.4426950216293335f * x);
-  float s0, c0;
-  if (fast) {
-    float a = v.hi * scale;            // exact
-    a = a - 2.f * rintf(0.5f * a);     // exact: a mod 2 in [-1, 1]
-    s0 = __sinf(3.1415927410125732f * a);
-    c0 = __cosf(3.1415927410125732f * a);
-  } else {
-    sincospif(v.hi * scale, &s0, &c0);  // exact scaling; sin/cos(pi * a)
-  }
-  const float d = 3.1415927410125732f * (v.lo * scale);
-  const float q = fmaf(-0.5f * d, d, 1.0f);
-  s = e * fmaf(d, c0, s0 * q);
-  c = e * fmaf(-d, s0, c0 * q);
-}
+using namespace enc;
 
 __global__ void k_cast_rays(const float* __restrict__ t, const float* __restrict__ o, const float* __restrict__ d,
                             const float* __restrict__ radii, int R, int S, float* __restrict__ means,

@@ -66,6 +66,10 @@ int launch_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, in
 int launch_gather_batch(const float* records, long n, const long* idx, uint64_t seed, uint32_t slot0, uint32_t step, int R, float* o,
                         float* d, float* radii, float* nears, float* fars, float* lm, float* pix, cudaStream_t st);
 int launch_sq_err(const float* a, const float* b, long n, double* out, cudaStream_t st);
+// SSIM map + per-block sums (SN/MipHelpers.cs:688-757); images [H, W, 3]; block_sums: ssim_blocks(W, H) doubles
+long ssim_blocks(int W, int H);
+int launch_ssim(const float* a, const float* b, int W, int H, float max_val, int filter_size, float filter_sigma, float k1, float k2,
+                float* map_out, double* block_sums, cudaStream_t st);
 
 // ---- adam.cu (B.6) ------------------------------------------------------------------------------
 int launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float inv1,

@@ -102,6 +102,65 @@ void orc_init_params(const orc_config* c, uint64_t seed, float* params) {
     for (int j = 0; j < out[l]; j++) params[off++] = 0.0f;
 }
 
+/* ComputeSsim (SN/MipHelpers.cs:688-727) with VectorImage.Convolve (:903-927) and CreateGaussianFilter (:739-756), float
+ * arithmetic in the original's order: five zero-padded "same" convolutions of a, b, a*a, b*b, a*b with the normalised
+ * fs x fs Gaussian (taps kx outer, ky inner), variances and the covariance clamped at 0, map = num / den.  Images are
+ * [H, W, 3]; pixel (x, y) of VectorImage[x, y] at (y * W + x) * 3.  The mean (ComputeSsimAverage :728-737) is returned in
+ * double precision over the float map (the original accumulates 3*W*H terms in a float). */
+static void orc_convolve_(const float* img, int W, int H, const float* filt, int fs, float* out) {
+  const int pad = fs / 2, PW = W + 2 * pad, PH = H + 2 * pad;
+  float* p = (float*)calloc((size_t)PW * PH * 3, sizeof(float));
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++)
+      for (int c = 0; c < 3; c++) p[((size_t)(y + pad) * PW + x + pad) * 3 + c] = img[((size_t)y * W + x) * 3 + c];
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++)
+      for (int c = 0; c < 3; c++) {
+        float sum = 0.0f;
+        for (int kx = 0; kx < fs; kx++)
+          for (int ky = 0; ky < fs; ky++) sum += p[((size_t)(y + ky) * PW + x + kx) * 3 + c] * filt[kx * fs + ky];
+        out[((size_t)y * W + x) * 3 + c] = sum;
+      }
+  free(p);
+}
+double orc_ssim(const float* a, const float* b, int W, int H, float max_val, int fs, float sigma, float k1, float k2,
+                float* map) {
+  const size_t n = (size_t)W * H * 3;
+  float* filt = (float*)malloc((size_t)fs * fs * sizeof(float));
+  const int hs = fs / 2;
+  float fsum = 0.0f;
+  for (int i = 0; i < fs; i++)
+    for (int j = 0; j < fs; j++) {
+      const float x = (float)(i - hs), y = (float)(j - hs);
+      filt[i * fs + j] = expf(-(x * x + y * y) / (2 * sigma * sigma));
+      fsum += filt[i * fs + j];
+    }
+  for (int i = 0; i < fs * fs; i++) filt[i] /= fsum;
+  float *mu0 = malloc(n * 4), *mu1 = malloc(n * 4), *s00 = malloc(n * 4), *s11 = malloc(n * 4), *s01 = malloc(n * 4), *tmp = malloc(n * 4);
+  orc_convolve_(a, W, H, filt, fs, mu0);
+  orc_convolve_(b, W, H, filt, fs, mu1);
+  for (size_t i = 0; i < n; i++) tmp[i] = a[i] * a[i];
+  orc_convolve_(tmp, W, H, filt, fs, s00);
+  for (size_t i = 0; i < n; i++) tmp[i] = b[i] * b[i];
+  orc_convolve_(tmp, W, H, filt, fs, s11);
+  for (size_t i = 0; i < n; i++) tmp[i] = a[i] * b[i];
+  orc_convolve_(tmp, W, H, filt, fs, s01);
+  const float c1 = powf(k1 * max_val, 2.0f), c2 = powf(k2 * max_val, 2.0f);
+  double total = 0.0;
+  for (size_t i = 0; i < n; i++) {
+    const float mu00 = mu0[i] * mu0[i], mu11 = mu1[i] * mu1[i], mu01 = mu0[i] * mu1[i];
+    const float g00 = fmaxf(s00[i] - mu00, 0.0f), g11 = fmaxf(s11[i] - mu11, 0.0f), g01 = fmaxf(s01[i] - mu01, 0.0f);
+    const float num = (mu01 * 2 + c1) * (g01 * 2 + c2);
+    const float den = (mu00 + mu11 + c1) * (g00 + g11 + c2);
+    const float v = num / den;
+    if (map) map[i] = v;
+    total += (double)v;
+  }
+  free(filt); free(mu0); free(mu1); free(s00); free(s11); free(s01); free(tmp);
+  return total / (double)n;
+}
+
 /* SN/MipHelpers.cs:758-773, float arithmetic. */
 float orc_learning_rate_decay(int step, float lr_init, float lr_final, int max_steps,
                               int lr_delay_steps, float lr_delay_mult) {

@@ -138,6 +138,18 @@ def learning_rate_decay(step, lr_init=5e-4, lr_final=5e-6, max_steps=1000000, lr
     return float(lib().orc_learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult))
 
 
+def ssim(a, b, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03):
+    """(mean, map) of ComputeSsim / ComputeSsimAverage (SN/MipHelpers.cs:688-737); images [H, W, 3] float32."""
+    a, b = _arr(a, np.float32), _arr(b, np.float32)
+    H, W = a.shape[:2]
+    m = np.empty_like(a)
+    fn = lib().orc_ssim
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    mean = fn(_p(a), _p(b), W, H, max_val, filter_size, filter_sigma, k1, k2, _p(m))
+    return float(mean), m
+
+
 # ---------------------------------------------------------------- per-stage functions
 
 

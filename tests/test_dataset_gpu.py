@@ -124,6 +124,23 @@ def test_checkpoint_resume_is_bitwise_identical(tmp_path):
         m2.load_checkpoint(tmp_path / "junk.ckpt")
 
 
+def test_ssim_matches_oracle():
+    """nerf_image_ssim (SN/MipHelpers.cs:688-737) against the CPU restatement: same taps in the same order in fp32, so the
+    map agrees to rounding noise; sizes that are not multiples of the 16 x 16 tile, a different window, and the mean of an
+    800 x 800 image (the render size of configs[3])."""
+    rng = np.random.default_rng(3)
+    for (H, W, fs, sigma) in ((37, 53, 11, 1.5), (64, 48, 7, 1.0), (800, 800, 11, 1.5)):
+        a = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+        b = np.clip(a + rng.normal(0, 0.05, a.shape), 0, 1).astype(np.float32)
+        mean, m = nb.image_ssim(a, b, filter_size=fs, filter_sigma=sigma, want_map=True)
+        omean, om = orc.ssim(a, b, filter_size=fs, filter_sigma=sigma)
+        print(f"ssim {H}x{W} window {fs}: {mean:.6f} (oracle {omean:.6f}), map max abs diff {np.abs(m - om).max():.2e}")
+        np.testing.assert_allclose(m, om, atol=2e-6)
+        assert abs(mean - omean) <= 1e-7
+    assert abs(nb.image_ssim(a, a) - 1.0) <= 1e-5
+    assert nb.image_ssim(a, b) == nb.image_ssim(a, b)  # block partials are added in block order
+
+
 def test_image_error_and_psnr():
     rng = np.random.default_rng(0)
     a = rng.random((100, 120, 3), dtype=np.float32)

@@ -235,3 +235,35 @@ def test_train_gradient_deterministic_across_threads():
         orc.set_threads(n)
     np.testing.assert_array_equal(a["comp_rgb"], b["comp_rgb"])  # per-ray work is order-free
     assert np.abs(a["grads"] - b["grads"]).max() <= 1e-5 * np.abs(a["grads"]).max()
+
+
+def test_ssim_oracle_against_scipy_and_identities():
+    """SN/MipHelpers.cs:688-757.  Independent check of the restatement: the same definition written with scipy's
+    correlate2d (zero-padded `same` window of the normalised 11x11 Gaussian) in fp64; identities: SSIM(a, a) = 1,
+    symmetric in its arguments, < 1 and decreasing with added noise."""
+    from scipy.signal import correlate2d
+
+    rng = np.random.default_rng(0)
+    H, W = 37, 53  # not multiples of anything: borders and odd sizes
+    a = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.05, a.shape), 0, 1).astype(np.float32)
+    mean, m = orc.ssim(a, b)
+    x = np.arange(11) - 5
+    filt = np.exp(-(x[:, None] ** 2 + x[None, :] ** 2) / (2 * 1.5 ** 2))
+    filt /= filt.sum()
+
+    def conv(img):
+        return np.stack([correlate2d(img[..., c].astype(np.float64), filt, mode="same", boundary="fill") for c in range(3)], -1)
+
+    mu0, mu1 = conv(a), conv(b)
+    s00 = np.maximum(conv(a.astype(np.float64) ** 2) - mu0 ** 2, 0)
+    s11 = np.maximum(conv(b.astype(np.float64) ** 2) - mu1 ** 2, 0)
+    s01 = np.maximum(conv(a.astype(np.float64) * b) - mu0 * mu1, 0)
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    ref = ((2 * mu0 * mu1 + c1) * (2 * s01 + c2)) / ((mu0 ** 2 + mu1 ** 2 + c1) * (s00 + s11 + c2))
+    np.testing.assert_allclose(m, ref, atol=2e-4)  # fp32 window sums vs fp64
+    assert abs(mean - ref.mean()) <= 2e-5
+    assert abs(orc.ssim(a, a)[0] - 1.0) <= 1e-5
+    assert abs(orc.ssim(b, a)[0] - mean) <= 1e-7
+    worse = np.clip(a + rng.normal(0, 0.2, a.shape), 0, 1).astype(np.float32)
+    assert orc.ssim(a, worse)[0] < mean < 1.0

@@ -56,7 +56,7 @@ def cast_rays(t, o, d, radii):
 
 
 def ipe(mean, cov, deg):
-    sc = 2.0 ** torch.arange(deg, dtype=mean.dtype)
+    sc = 2.0 ** torch.arange(deg, dtype=mean.dtype, device=mean.device)
     y = mean[..., None, :] * sc[:, None]
     yv = cov[..., None, :] * (sc**2)[:, None]
     e = torch.exp(-0.5 * yv)
