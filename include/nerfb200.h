@@ -68,12 +68,13 @@ typedef struct nerf_config {
   uint32_t engine_flags;   /* NERF_FLAG_*: A/B switches of the tensor-core engine (0 = the shipped schedule) */
 } nerf_config;
 
-/* engine_flags: bits 0-3 select the slower, simpler path the default replaced (parity tests compare the two); bit 4 an alternative schedule. */
+/* engine_flags: each bit selects the slower, simpler path the default replaced — parity tests compare the two. */
 #define NERF_FLAG_NO_FUSED_FORWARD 1u       /* render / forward-only: one GEMM launch per layer instead of the fused kernel */
 #define NERF_FLAG_NO_FUSED_TRAIN_FORWARD 2u /* training forward: per-layer launches */
 #define NERF_FLAG_NO_FUSED_DGRAD 4u         /* backward: per-layer dgrad launches instead of the fused chain */
 #define NERF_FLAG_NO_DEFERRED_REDUCE 8u     /* wgrad partial tiles reduced by a launch of their own */
-#define NERF_FLAG_QUARTER_SCHEDULE 16u      /* fp32-accurate fused kernels: quarter-granular accumulators, two-phase k order */
+#define NERF_FLAG_NO_FUSED_ENCODE 16u       /* cast_rays + IPE + direction PE as a kernel of their own (planes through HBM) instead of
+                                              * the encoder warps inside the fused MLP kernels */
 
 typedef struct nerf_mipnerf nerf_mipnerf;   /* AcceleratedMipNeRF + its embedded AcceleratedMLP */
 typedef struct nerf_adam nerf_adam;         /* AcceleratedAdamOptimizer */

@@ -216,11 +216,19 @@ int forward_chunk(nerf_mipnerf* h, int c0, int rc, bool for_training = true) {
     { ProfScope ps(PC_SAMPLE, h->st);
     if (l == 0) NERF_TRY(launch_sample_t_vals(h->nears + c0, h->fars + c0, rng, rc, S, randomized, L.t, h->st));
     else NERF_TRY(launch_resample_t_vals(h->lv[l - 1].t, h->lv[l - 1].weights, rng, rc, S, c.resample_padding, randomized, L.t, h->st)); }
-    { ProfScope ps(PC_ENCODE, h->st);
-    NERF_TRY(launch_cast_encode_fused(L.t, h->origins + (size_t)c0 * 3, h->dirs + (size_t)c0 * 3, h->radii + c0, rc, S,
-                                      c.deg_point, c.deg_view, h->mlp->encode_targets(l), h->st)); }
-    if (for_training) NERF_TRY(h->mlp->forward(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
-    else NERF_TRY(h->mlp->forward_only(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
+    // cast_rays + encode_input_data (.cu:292-317, 187-221): inside the fused MLP kernel where the engine can (no kernel of
+    // their own, no HBM round trip of the encodings), else one fused encode kernel into the engine's planes
+    RaySource rs;
+    rs.t = L.t; rs.o = h->origins + (size_t)c0 * 3; rs.d = h->dirs + (size_t)c0 * 3; rs.radii = h->radii + c0;
+    rs.R = rc; rs.S = S; rs.deg_point = c.deg_point; rs.deg_view = c.deg_view;
+    int handled = 0;
+    NERF_TRY(h->mlp->forward_from_rays(l, rs, (long)rc * S, h->params, L.raw_density, L.raw_rgb, for_training, h->st, &handled));
+    if (!handled) {
+      { ProfScope ps(PC_ENCODE, h->st);
+      NERF_TRY(launch_cast_encode_fused(L.t, rs.o, rs.d, rs.radii, rc, S, c.deg_point, c.deg_view, h->mlp->encode_targets(l), h->st)); }
+      if (for_training) NERF_TRY(h->mlp->forward(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
+      else NERF_TRY(h->mlp->forward_only(l, (long)rc * S, h->params, L.raw_density, L.raw_rgb, h->st));
+    }
     L.last_rows = (long)rc * S;
     { ProfScope ps(PC_COMPOSITE_FWD, h->st);
     NERF_TRY(launch_composite_fwd(L.raw_rgb, L.raw_density, L.t, h->dirs + (size_t)c0 * 3, rc, S, c.white_bkgd,

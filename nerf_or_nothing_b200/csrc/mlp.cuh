@@ -6,6 +6,7 @@
 #pragma once
 #include <vector>
 
+#include "encode_rows.cuh"
 #include "kernels.cuh"
 
 namespace nerf {
@@ -50,6 +51,15 @@ class MlpEngine {
   virtual int prepare(const float* params, cudaStream_t st) = 0;
   // raw (pre-activation) heads: raw_density [M], raw_rgb [M,3]; caches activations of `level`
   virtual int forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) = 0;
+  // Forward straight from the level's t-values and rays: an engine whose forward kernel builds the encodings itself sets
+  // *handled = 1 and runs the whole level (training: caches as forward(); else as forward_only()); otherwise it leaves
+  // *handled = 0 and the caller runs the encode kernel into encode_targets() followed by forward() / forward_only().
+  virtual int forward_from_rays(int level, const RaySource& rays, long M, const float* params, float* raw_density, float* raw_rgb,
+                                bool training, cudaStream_t st, int* handled) {
+    (void)level; (void)rays; (void)M; (void)params; (void)raw_density; (void)raw_rgb; (void)training; (void)st;
+    *handled = 0;
+    return 0;
+  }
   // same heads, but no backward pass will follow: an engine may skip the activation caches (rendering)
   virtual int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) {
     return forward(level, M, params, raw_density, raw_rgb, st);

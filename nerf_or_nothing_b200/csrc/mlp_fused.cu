@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 
+#include "encode_rows.cuh"
 #include "gemm_tc.cuh"
 #include "sm100.cuh"
 
@@ -25,7 +26,9 @@ namespace {
 
 using namespace sm100;
 
-constexpr int kThreadsF = 320;
+constexpr int kThreadsF = 320;                    // 8 epilogue warps + TMA producer + MMA issuer
+constexpr int kEncWarps = 2;                      // forward kernels: + 2 encoder warps (cast_rays + IPE + direction PE in-kernel)
+constexpr int kThreadsFE = kThreadsF + 32 * kEncWarps;
 constexpr int kWStages = 6;                       // render; training gives one stage to the activation staging
 constexpr int kWStageBytes = 128 * 128;           // [128 rows (N half) x 64 bf16]
 constexpr int kEncBytes = 2 * 16384 + 16384;      // per tile: position encoding 2 boxes of [128 x 64], direction 1 box
@@ -63,6 +66,13 @@ struct alignas(64) FusedParams {
   uint32_t* bits[kMaxSteps];
   // dgrad chain only: bits[s] is READ (ReLU mask of the step's output); step 0 adds the rank-1 term r1[row] * v1[col]
   const float* r1;      // [M] dL/d raw_density
+  // forward only — in-kernel cast_rays + IPE + direction PE (accelerated_functions.cu:292-317, 187-221; encode_rows.cuh):
+  // enc_mode 0: map_pos / map_dir view planes another kernel wrote (stand-alone AcceleratedMLP::get_output);
+  //          1: the encoder warps write the level's planes [M, 128] / [M, 64] (training: the wgrad GEMMs read them later);
+  //          2: they write a per-CTA, double-buffered scratch [gridDim.x * 2 * 256 rows] that stays in L2 (rendering)
+  int enc_mode;
+  RaySource rs;
+  __nv_bfloat16 *enc_pos, *enc_dir;
 };
 
 namespace {
@@ -148,13 +158,20 @@ __device__ __forceinline__ void dgrad_chunk(const uint32_t (&r)[32], uint32_t ma
 // restages its 32 rows in shared memory and issues its own TMA store).
 // MODE 0: inference forward; 1: training forward; 2: backward dgrad chain (A of step 0 = dZ of the condition layer from
 // shared memory, epilogue = rank-1 density-head term + ReLU mask of the layer below, every step's dZ written out for wgrad).
+// Forward modes run two more warps (10, 11): the ENCODERS.  For pair j they turn the pair's 256 samples (t-values + ray)
+// into the position / direction encoding rows — one thread per row, the arithmetic of encode.cu — and store them through
+// L2 (planes or scratch, see FusedParams::enc_mode); `fence.proxy.async` + enc_ready[j & 1] hands them to the producer,
+// whose TMA loads bring them into shared memory as the A operands of layer 0, the skip layer and the condition layer.
+// They run up to two pairs ahead of the MMAs (enc_free[j & 1] = pair j's loads have landed), so the encode of the next
+// pair is hidden under the current pair's MMAs and no encode kernel runs at all.
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_fused_fwd(const __grid_constant__ FusedParams p) {
   constexpr bool TRAIN = MODE != 0;   // activations / gradients are written out
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kWStages - 1 : kWStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[kWStages], w_empty[kWStages], pos_full, pos_empty, dir_full, dir_empty, acc_full, acc_empty, act_ready, act_lo_ready;
+  __shared__ uint64_t enc_ready[2], enc_free[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,9 +191,10 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
     for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(&pos_full, 1); mbar_init(&pos_empty, 1); mbar_init(&dir_full, 1); mbar_init(&dir_empty, 1);
     mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8); mbar_init(&act_ready, 8); mbar_init(&act_lo_ready, 8);
+    for (int b = 0; b < 2; b++) { mbar_init(&enc_ready[b], kEncWarps); mbar_init(&enc_free[b], 1); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_consts; i += kThreadsF) s_const[i] = __ldg(p.consts + i);
+  for (int i = threadIdx.x; i < p.n_consts; i += blockDim.x) s_const[i] = __ldg(p.consts + i);
   if (warp == 8) {
     tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
@@ -195,7 +213,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
     if (lane == 0) {
       uint32_t wit = 0, pl = 0;
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
-        const int row0 = pair * 256;
+        // rows of this pair's encodings in the tensor the maps view: the sample index, or this CTA's scratch buffer pl & 1
+        const int row0 = (!DGRAD && p.enc_mode == 2) ? (blockIdx.x * 2 + (int)(pl & 1)) * 256 : pair * 256;
+        if (!DGRAD && p.enc_mode) mbar_wait(&enc_ready[pl & 1], (pl >> 1) & 1);  // the encoder warps have written them
         mbar_wait(&pos_empty, (pl & 1) ^ 1);
         mbar_arrive_expect_tx(&pos_full, 2 * 32768);
         for (int t = 0; t < 2; t++) {
@@ -281,9 +301,31 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_mlp_fused_fwd(const __grid_con
         }
         if (s == last_pos_step && leader) umma_commit(&pos_empty);  // the next pair's position encodings may land
       }
-      if (leader) umma_commit(&dir_empty);
+      if (leader) {
+        umma_commit(&dir_empty);
+        // pos_full and dir_full of this pair have been waited for: its encodings have left the scratch buffer pl & 1
+        if (!DGRAD && p.enc_mode) mbar_arrive(&enc_free[pl & 1]);
+      }
     }
     __syncwarp();
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ encoders (forward modes): one thread per sample row
+    if (!DGRAD && p.enc_mode) {
+      const int et = threadIdx.x - 320;  // 0 .. 32 * kEncWarps
+      uint32_t pl = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
+        if (pl >= 2) mbar_wait(&enc_free[pl & 1], ((pl >> 1) & 1) ^ 1);  // pair pl - 2 has been loaded out of this buffer
+        const long out0 = p.enc_mode == 2 ? (long)(blockIdx.x * 2 + (int)(pl & 1)) * 256 : (long)pair * 256;
+        for (int i = et; i < 256; i += 32 * kEncWarps) {
+          const long m = (long)pair * 256 + i;
+          const bool valid = m < p.M;
+          if (valid || p.enc_mode == 2) enc::encode_row_to_planes(p.rs, m, valid, out0 + i, p.enc_pos, nullptr, p.enc_dir, nullptr);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> visible to the TMA loads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&enc_ready[pl & 1]);
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue: tile t = warp / 4, rows 32 (warp % 4) ..
     const int t = warp >> 2;
@@ -435,7 +477,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
                              const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                              float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
-                             cudaStream_t st) {
+                             const RaySource* rays, long enc_scratch_rows, cudaStream_t st) {
   if (W != 256 || Wc != 128 || D + 1 > kMaxSteps || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
     return 100001;
@@ -448,8 +490,24 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   if (smem > 226 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
   FusedParams p;
   memset(&p, 0, sizeof(p));
-  NERF_TRY(tc_make_tmap(&p.map_pos, pos, M, 128, pos_pitch, 128));
-  NERF_TRY(tc_make_tmap(&p.map_dir, dir, M, 64, dir_pitch, 128));
+  const int pairs = (int)cdiv(M, 256);
+  const int grid = pairs < sms ? pairs : sms;
+  // rays != nullptr: the kernel's encoder warps build the encodings from the t-values; `pos` / `dir` are then the level's
+  // planes (training) or, with enc_scratch_rows > 0, a scratch of that many rows (>= grid * 512) that never leaves L2
+  long map_rows = M;
+  if (rays) {
+    p.enc_mode = enc_scratch_rows > 0 ? 2 : 1;
+    p.rs = *rays; p.enc_pos = const_cast<__nv_bfloat16*>(pos); p.enc_dir = const_cast<__nv_bfloat16*>(dir);
+    if (p.enc_mode == 2) {
+      if (enc_scratch_rows < (long)grid * 512) { set_error("fused forward: encoding scratch too small"); return 100001; }
+      map_rows = enc_scratch_rows;
+    }
+    if (rays->deg_point % 4 || rays->deg_point * 6 > 120 || rays->deg_view > 4 || (long)rays->R * rays->S < M) {
+      set_error("fused forward: in-kernel encoding needs deg_point %% 4 == 0, <= 20, deg_view <= 4"); return 100001;
+    }
+  }
+  NERF_TRY(tc_make_tmap(&p.map_pos, pos, map_rows, 128, pos_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_dir, dir, map_rows, 64, dir_pitch, 128));
   for (int s = 0; s <= D; s++) {
     const int N = s < D ? W : Wc;
     NERF_TRY(tc_make_tmap(&p.map_w[s], wplanes[s], N, kpad[s], kpad[s], 128));
@@ -469,10 +527,8 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  const int pairs = (int)cdiv(M, 256);
-  const int grid = pairs < sms ? pairs : sms;
-  if (train) k_mlp_fused_fwd<1><<<grid, kThreadsF, smem, st>>>(p);
-  else k_mlp_fused_fwd<0><<<grid, kThreadsF, smem, st>>>(p);
+  if (train) k_mlp_fused_fwd<1><<<grid, kThreadsFE, smem, st>>>(p);
+  else k_mlp_fused_fwd<0><<<grid, kThreadsFE, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
 }

@@ -17,6 +17,7 @@
 
 #include <cstring>
 
+#include "encode_rows.cuh"
 #include "gemm_tc.cuh"
 #include "sm100.cuh"
 
@@ -26,6 +27,8 @@ namespace {
 using namespace sm100;
 
 constexpr int kThreadsS = 320;            // 8 epilogue warps + TMA producer + MMA issuer
+constexpr int kEncWarpsS = 2;             // forward kernels: + 2 encoder warps (cast_rays + IPE + direction PE in-kernel)
+constexpr int kThreadsSE = kThreadsS + 32 * kEncWarpsS;
 constexpr int kEpiWarps = 8;
 constexpr int kNSInfer = 6, kNSTrain = 5;  // operand ring: 32 KB stages (a weight plane tile [<=256 x 64], or an encoding k-block's hi|lo tiles)
 constexpr int kStageB = 256 * 128;        // 32 KB
@@ -56,6 +59,11 @@ struct alignas(64) SplitParams {
   float* raw_density;
   float* raw_rgb;
   const float* r1;  // dgrad chain: [M] dL/d raw_density (rank-1 term of step 0); bits[] are then READ as ReLU masks
+  // forward only — in-kernel cast_rays + IPE + direction PE (see FusedParams::enc_mode in mlp_fused.cu): 0 = planes written by
+  // another kernel, 1 = the encoder warps write the level's hi/lo planes, 2 = a per-CTA double-buffered scratch (128 rows each)
+  int enc_mode;
+  RaySource rs;
+  __nv_bfloat16 *enc_pos[2], *enc_dir[2];  // [hi, lo]
 };
 
 namespace {
@@ -128,13 +136,16 @@ __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint3
 // MODE 0: inference forward; 1: training forward (activation planes + ReLU bits written); 2: backward dgrad chain (step 0:
 // A = dZ of the condition layer streamed through the ring like an encoding, epilogue = density-head rank-1 term + ReLU
 // mask of the layer below; every step's dZ planes written for the wgrad GEMMs).
+// Forward modes run two more warps (10, 11), the ENCODERS: one thread per sample row turns the tile's t-values + ray into
+// the hi/lo encoding rows (encode_rows.cuh), stored through L2; enc_ready[tile & 1] hands them to the producer's TMA loads,
+// enc_free[tile & 1] (MMA issuer, end of tile) returns the scratch buffer.  They run up to two tiles ahead of the MMAs.
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
+__global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
   constexpr bool TRAIN = MODE != 0;
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready, act_lo_ready;
+  __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready, act_lo_ready, enc_ready[2], enc_free[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float head_part[128][4];  // partial head dot products of the upper-column warps
 
@@ -151,9 +162,10 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
     for (int h = 0; h < 2; h++) { mbar_init(&acc_full[h], 1); mbar_init(&acc_empty[h], kEpiWarps); }
     mbar_init(&act_ready, kEpiWarps);
     mbar_init(&act_lo_ready, kEpiWarps);
+    for (int b = 0; b < 2; b++) { mbar_init(&enc_ready[b], kEncWarpsS); mbar_init(&enc_free[b], 1); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_consts; i += kThreadsS) s_const[i] = __ldg(p.consts + i);
+  for (int i = threadIdx.x; i < p.n_consts; i += blockDim.x) s_const[i] = __ldg(p.consts + i);
   if (warp == kEpiWarps) {
     tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
@@ -172,9 +184,11 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
     // ------------------------------------------------------------------ TMA producer: everything goes through ONE ring of
     // 32 KB stages — the hi|lo tiles [128 x 64] of a weight half-layer k-block, or of an encoding k-block (A operand)
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = tile * 128;
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+        // rows of this tile's encodings in the tensors the maps view: the sample index, or this CTA's scratch buffer tl & 1
+        const int row0 = (!DGRAD && p.enc_mode == 2) ? (blockIdx.x * 2 + (int)(tl & 1)) * 128 : tile * 128;
+        if (!DGRAD && p.enc_mode) mbar_wait(&enc_ready[tl & 1], (tl >> 1) & 1);  // the encoder warps have written them
         for (int s = 0; s < p.n_steps; s++) {
           const SplitParams::Step st = p.steps[s];
           const int n_kb = st.n_act_kb + st.n_enc_kb;
@@ -206,8 +220,8 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
     const uint64_t desc0 = make_smem_desc(0, 16, 1024);
     const uint32_t ring_base = smem_u32(w_ring);
     const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
-    uint32_t it = 0, n_acc[2] = {0, 0}, n_act = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t it = 0, n_acc[2] = {0, 0}, n_act = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
       for (int s = 0; s < p.n_steps; s++) {
         const SplitParams::Step st = p.steps[s];
         const int n_kb = st.n_act_kb + st.n_enc_kb;
@@ -261,8 +275,29 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
           if (leader) umma_commit(&acc_full[h]);
         }
       }
+      // every encoding stage of this tile has been waited for (w_full): its rows have left the scratch buffer tl & 1
+      if (!DGRAD && p.enc_mode && leader) mbar_arrive(&enc_free[tl & 1]);
     }
     __syncwarp();
+  } else if (warp >= kEpiWarps + 2) {
+    // ------------------------------------------------------------------ encoders (forward modes): one thread per sample row
+    if (!DGRAD && p.enc_mode) {
+      const int et = threadIdx.x - kThreadsS;  // 0 .. 32 * kEncWarpsS
+      uint32_t tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+        if (tl >= 2) mbar_wait(&enc_free[tl & 1], ((tl >> 1) & 1) ^ 1);  // tile tl - 2 has been loaded out of this buffer
+        const long out0 = p.enc_mode == 2 ? (long)(blockIdx.x * 2 + (int)(tl & 1)) * 128 : (long)tile * 128;
+        for (int i = et; i < 128; i += 32 * kEncWarpsS) {
+          const long m = (long)tile * 128 + i;
+          const bool valid = m < p.M;
+          if (valid || p.enc_mode == 2)
+            enc::encode_row_to_planes(p.rs, m, valid, out0 + i, p.enc_pos[0], p.enc_pos[1], p.enc_dir[0], p.enc_dir[1]);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> visible to the TMA loads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&enc_ready[tl & 1]);
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue: lane quarter warp % 4, column half warp / 4
     const int qtr = warp & 3, ch = warp >> 2;
@@ -382,304 +417,6 @@ __global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split(const __grid_c
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Quarter-granular variant, selected by NERF_FLAG_QUARTER_SCHEDULE (nerf_config.engine_flags).
-// Same data flow as k_mlp_fused_split, two changes to the order of work inside a layer:
-//   * two-phase k-block order for a layer that consumes ACT (4 activation k-blocks, two N-halves): PHASE A = everything that
-//     needs only K 0..127 of ACT (encoding k-blocks, then k-blocks 0,1; both halves), then wait `act_ready`, PHASE B = k-blocks
-//     2,3.  Phase B never reads ACT columns 0..63, so the first half's outputs go straight into ACT (nothing is parked);
-//   * phase B runs QUARTER-major (N = 64 MMAs on the two resident stages of a half): accumulator quarter q is complete
-//     a quarter of the phase earlier than the next, and the eight epilogue warps work in 32-column passes per quarter.
-// Barriers: acc_full[4] / acc_empty[4] (one per 64-column accumulator quarter), act_lo_ready after quarters 0,1,
-// act_ready after quarter 3.  Quarter 2 is written to ACT only after acc_full[3] (its columns are still being read).
-__device__ __forceinline__ bool q_two_phase(const SplitParams::Step& st) { return st.n_halves == 2 && st.n_act_kb == 4; }
-// i-th (half, k-block) of a step in issue order; phase B items (two_phase only) are i >= 2 * (n_enc + 2)
-__device__ __forceinline__ void q_item(const SplitParams::Step& st, int i, int& h, int& kb) {
-  const int n_kb = st.n_act_kb + st.n_enc_kb;
-  if (!q_two_phase(st)) { h = i / n_kb; kb = i % n_kb; return; }
-  const int a = st.n_enc_kb + 2;  // phase A items per half: encodings first (they do not depend on ACT), then k-blocks 0,1
-  if (i < 2 * a) {
-    h = i / a;
-    const int r = i % a;
-    kb = r < st.n_enc_kb ? 4 + r : r - st.n_enc_kb;
-  } else {
-    const int j = i - 2 * a;
-    h = j >> 1;
-    kb = 2 + (j & 1);
-  }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreadsS, 1) k_mlp_fused_split_q(const __grid_constant__ SplitParams p) {
-  constexpr bool TRAIN = MODE != 0;
-  constexpr bool DGRAD = MODE == 2;
-  constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[4], acc_empty[4], act_ready, act_lo_ready;
-  __shared__ uint32_t tmem_base_smem;
-  __shared__ float head_part[128][4];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* w_ring = smem;
-  uint8_t* stage_buf = smem + NS * kStageB;
-  float* s_const = reinterpret_cast<float*>(stage_buf + (TRAIN ? kEpiWarps * kSlotB : 0));
-  const int n_tiles = (int)((p.M + 127) / 128);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int q = 0; q < 4; q++) { mbar_init(&acc_full[q], 1); mbar_init(&acc_empty[q], kEpiWarps); }
-    mbar_init(&act_ready, kEpiWarps);
-    mbar_init(&act_lo_ready, kEpiWarps);
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < p.n_consts; i += kThreadsS) s_const[i] = __ldg(p.consts + i);
-  if (warp == kEpiWarps) {
-    tmem_alloc<512>(&tmem_base_smem);
-    if (lane == 0) {
-      for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_pos[q]); if (!DGRAD) prefetch_tmap(&p.map_dir[q]); }
-      for (int s = 0; s < p.n_steps; s++)
-        for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_w[s][q]); if (TRAIN) prefetch_tmap(&p.map_act[s][q]); }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t ACT_HI = tmem_base, ACT_LO = tmem_base + 128, ACC = tmem_base + 256;  // accumulator quarter q at + 64 q
-
-  if (warp == kEpiWarps) {
-    // ------------------------------------------------------------------ TMA producer: the ring in ISSUE order
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = tile * 128;
-        for (int s = 0; s < p.n_steps; s++) {
-          const SplitParams::Step st = p.steps[s];
-          const int n_items = st.n_halves * (st.n_act_kb + st.n_enc_kb);
-          for (int i = 0; i < n_items; i++) {
-            int h, kb;
-            q_item(st, i, h, kb);
-            if (kb >= st.n_act_kb) {  // encoding k-block: A_hi | A_lo in their own stage
-              const int ws = it % NS;
-              mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);
-              mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
-              const CUtensorMap* me = st.enc_kind == 2 ? p.map_dir : p.map_pos;
-              const int ecol = (kb - st.n_act_kb) * 64;
-              tma_load_2d(w_ring + (size_t)ws * kStageB, &me[0], ecol, row0, &w_full[ws]);
-              tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &me[1], ecol, row0, &w_full[ws]);
-              it++;
-            }
-            const int ws = it % NS;
-            mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);
-            mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
-            tma_load_2d(w_ring + (size_t)ws * kStageB, &p.map_w[s][0], kb * 64, h * 128, &w_full[ws]);
-            tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &p.map_w[s][1], kb * 64, h * 128, &w_full[ws]);
-            it++;
-          }
-        }
-      }
-    }
-  } else if (warp == kEpiWarps + 1) {
-    // ------------------------------------------------------------------ MMA issuer (uniform warp, one elected lane issues)
-    const bool leader = elect_one();
-    const uint64_t desc0 = make_smem_desc(0, 16, 1024);
-    const uint32_t ring_base = smem_u32(w_ring);
-    const uint32_t idesc128 = make_idesc_bf16(128, 128, false, false), idesc64 = make_idesc_bf16(128, 64, false, false);
-    uint32_t it = 0, n_acc[4] = {0, 0, 0, 0}, n_act = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int s = 0; s < p.n_steps; s++) {
-        const SplitParams::Step st = p.steps[s];
-        const int n_kb = st.n_act_kb + st.n_enc_kb;
-        const bool two = q_two_phase(st);
-        const int n_a = two ? 2 * (st.n_enc_kb + 2) : st.n_halves * n_kb;  // items issued as whole-half (N = 128) MMAs
-        bool act_lo_seen = false, act_hi_seen = false;
-        int cur_h = -1, n_in_half = 0;
-        for (int i = 0; i < n_a; i++) {
-          int h, kb;
-          q_item(st, i, h, kb);
-          if (h != cur_h) {  // first item of this half: both of its accumulator quarters must have been drained
-            cur_h = h; n_in_half = 0;
-            mbar_wait(&acc_empty[2 * h], (n_acc[2 * h] & 1) ^ 1); n_acc[2 * h]++;
-            mbar_wait(&acc_empty[2 * h + 1], (n_acc[2 * h + 1] & 1) ^ 1); n_acc[2 * h + 1]++;
-            tc_fence_after_sync();
-          }
-          const bool from_act = kb < st.n_act_kb;
-          if (from_act && !act_lo_seen) { mbar_wait(&act_lo_ready, n_act & 1); tc_fence_after_sync(); act_lo_seen = true; }
-          if (from_act && kb >= 2 && !act_hi_seen) { mbar_wait(&act_ready, n_act & 1); tc_fence_after_sync(); act_hi_seen = true; }
-          uint32_t a_stage = 0, a_hi = 0;
-          if (!from_act) {
-            a_stage = it % NS;
-            mbar_wait(&w_full[a_stage], (it / NS) & 1);
-            a_hi = ring_base + a_stage * kStageB;
-            it++;
-          }
-          const uint32_t ws = it % NS;
-          mbar_wait(&w_full[ws], (it / NS) & 1);
-          tc_fence_after_sync();
-          const uint32_t acc = ACC + 128 * h;
-          const uint64_t dbh = desc0 + ((ring_base + ws * kStageB) >> 4), dbl = dbh + (16384 >> 4);
-          if (leader) {
-            if (from_act) {
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc128, (n_in_half | k) ? 1u : 0u);
-                umma_bf16_ts(acc, ACT_LO + kb * 32 + k * 8, dbh + 2 * k, idesc128, 1u);
-                umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbl + 2 * k, idesc128, 1u);
-              }
-            } else {
-              const uint64_t dah = desc0 + (a_hi >> 4), dal = dah + (16384 >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                umma_bf16(acc, dah + 2 * k, dbh + 2 * k, idesc128, (n_in_half | k) ? 1u : 0u);
-                umma_bf16(acc, dal + 2 * k, dbh + 2 * k, idesc128, 1u);
-                umma_bf16(acc, dah + 2 * k, dbl + 2 * k, idesc128, 1u);
-              }
-              umma_commit(&w_empty[a_stage]);
-            }
-            umma_commit(&w_empty[ws]);
-          }
-          it++;
-          n_in_half++;
-          if (!two && n_in_half == n_kb && leader) {  // natural order: the half is complete, both quarters at once
-            umma_commit(&acc_full[2 * h]);
-            umma_commit(&acc_full[2 * h + 1]);
-          }
-        }
-        if (two) {
-          // PHASE B: k-blocks 2,3 of each half, quarter-major on the half's two resident stages
-          if (!act_hi_seen) { mbar_wait(&act_ready, n_act & 1); tc_fence_after_sync(); act_hi_seen = true; }
-          for (int h = 0; h < 2; h++) {
-            const uint32_t ws0 = it % NS, ws1 = (it + 1) % NS;
-            mbar_wait(&w_full[ws0], (it / NS) & 1);
-            mbar_wait(&w_full[ws1], ((it + 1) / NS) & 1);
-            tc_fence_after_sync();
-            if (leader) {
-#pragma unroll
-              for (int j = 0; j < 2; j++) {
-                const uint32_t acc = ACC + 128 * h + 64 * j;
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                  const int kb = 2 + b;
-                  const uint64_t dbh = desc0 + ((ring_base + (b ? ws1 : ws0) * kStageB + j * 8192) >> 4), dbl = dbh + (16384 >> 4);
-#pragma unroll
-                  for (int k = 0; k < 4; k++) {
-                    umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc64, 1u);
-                    umma_bf16_ts(acc, ACT_LO + kb * 32 + k * 8, dbh + 2 * k, idesc64, 1u);
-                    umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbl + 2 * k, idesc64, 1u);
-                  }
-                }
-                umma_commit(&acc_full[2 * h + j]);
-              }
-              umma_commit(&w_empty[ws0]);
-              umma_commit(&w_empty[ws1]);
-            }
-            it += 2;
-          }
-        }
-        if (st.n_act_kb > 0) n_act++;
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ epilogue: lane quarter warp % 4; of every 64-column
-    // accumulator quarter this warp takes columns [32 ch, 32 ch + 32), ch = warp / 4
-    const int qtr = warp & 3, ch = warp >> 2;
-    const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    uint8_t* slot = stage_buf + warp * kSlotB;
-    uint8_t* slot_row = slot + lane * 64;
-    const int swz = (lane >> 1) & 3;
-    uint32_t n_full[4] = {0, 0, 0, 0};
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row_w = tile * 128 + qtr * 32;
-      const int row_t = qtr * 32 + lane;
-      const long row = (long)row_w + lane;
-      const bool row_ok = row < p.M;
-      const float r1v = (DGRAD && row_ok) ? __ldg(p.r1 + row) : 0.f;
-      for (int s = 0; s < p.n_steps; s++) {
-        const SplitParams::Step st = p.steps[s];
-        const int nq = 2 * st.n_halves;
-        float head[3] = {0.f, 0.f, 0.f};
-        bool waited3 = false;
-        for (int q = 0; q < nq; q++) {
-          const int col_t = 64 * q + 32 * ch;  // first output column of this thread's pass
-          const float* bias = s_const + st.bias_off + col_t;
-          const float* head_w = s_const + (st.head == 3 ? p.head_rgb_off : p.head_d_off) + col_t;
-          uint32_t mk = 0u;
-          if (DGRAD && row_ok) mk = __ldg(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5));
-          const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + col_t : nullptr;
-          if (!(q == 3 && waited3)) {
-            mbar_wait(&acc_full[q], n_full[q] & 1);
-            n_full[q]++;
-          }
-          tc_fence_after_sync();
-          uint32_t r[32];
-          tmem_ld_32x32(ACC + 64 * q + 32 * ch + lane_off, r);
-          tmem_ld_wait();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[q]);  // this warp's share of the quarter is in registers
-          uint32_t hw[16], lw[16], m = 0u;
-          if (DGRAD) dgrad_split_chunk(r, mk, r1v, v1, hw, lw);
-          else m = split_chunk<MODE == 1>(r, bias, st.head, head_w, head, hw, lw);
-          if (st.produces) {
-            if (q == 2 && !waited3) {  // columns 64..127 of ACT are read by quarter 3's MMAs until they complete
-              mbar_wait(&acc_full[3], n_full[3] & 1);
-              n_full[3]++;
-              tc_fence_after_sync();
-              waited3 = true;
-            }
-            const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
-            tmem_st_16(ACT_HI + out, hw);
-            tmem_st_16(ACT_LO + out, lw);
-            if (q == 1 || q == 3) {
-              tmem_st_wait();
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(q == 1 ? &act_lo_ready : &act_ready);
-            }
-          }
-          if (TRAIN) {  // ship this 32-column pass (both planes) of the warp's 32 rows
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-              *reinterpret_cast<uint4*>(slot_row + ((c ^ swz) << 4)) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
-              *reinterpret_cast<uint4*>(slot_row + 2048 + ((c ^ swz) << 4)) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.map_act[s][0], slot, col_t, row_w);
-              tma_store_2d(&p.map_act[s][1], slot + 2048, col_t, row_w);
-              tma_store_commit();
-            }
-          }
-          if (MODE == 1 && row_ok) p.bits[s][row * (st.n_halves * 4) + (col_t >> 5)] = m;
-        }
-        if (!DGRAD && st.head) {  // the column halves of a row meet in shared memory
-          if (ch == 1) { head_part[row_t][0] = head[0]; head_part[row_t][1] = head[1]; head_part[row_t][2] = head[2]; }
-          named_barrier_sync(1 + qtr, 64);
-          if (ch == 0 && row_ok) {
-            if (st.head == 1) {
-              p.raw_density[row] = head[0] + head_part[row_t][0] + s_const[p.head_d_off + 256];
-            } else {
-#pragma unroll
-              for (int n = 0; n < 3; n++) p.raw_rgb[row * 3 + n] = head[n] + head_part[row_t][n] + s_const[p.head_rgb_off + 3 * 128 + n];
-            }
-          }
-          named_barrier_sync(1 + qtr, 64);
-        }
-      }
-    }
-    if (TRAIN && lane == 0) tma_store_wait_read<0>();
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == kEpiWarps) tmem_dealloc<512>(tmem_base);
-}
-
 }  // namespace
 
 // Host side.  wplanes_hi/lo[s]: weight planes of dense layer s (trunk 0..D-1, then the condition layer), [N, kpad[s]].
@@ -689,24 +426,39 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, bool quarters, cudaStream_t st) {
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, cudaStream_t st) {
   if (W != 256 || Wc != 128 || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
     return 100001;
   }
   const bool train = act_hi != nullptr;
   const size_t smem = (size_t)(train ? kNSTrain : kNSInfer) * kStageB + (train ? kEpiWarps * kSlotB : 0) + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
-  const void* kern = quarters ? (train ? (const void*)k_mlp_fused_split_q<1> : (const void*)k_mlp_fused_split_q<0>)
-                              : (train ? (const void*)k_mlp_fused_split<1> : (const void*)k_mlp_fused_split<0>);
-  NERF_TRY(ensure_kernel_smem(kern, 218 * 1024));  // per device: the opt-in is a (kernel, device) property
+  NERF_TRY(ensure_kernel_smem(train ? (const void*)k_mlp_fused_split<1> : (const void*)k_mlp_fused_split<0>, 218 * 1024));  // per device
   const int sms = device_sm_count();
   if (smem > 218 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
   SplitParams p;
   memset(&p, 0, sizeof(p));
-  NERF_TRY(tc_make_tmap(&p.map_pos[0], pos_hi, M, 128, pos_pitch, 128));
-  NERF_TRY(tc_make_tmap(&p.map_pos[1], pos_lo, M, 128, pos_pitch, 128));
-  NERF_TRY(tc_make_tmap(&p.map_dir[0], dir_hi, M, 64, dir_pitch, 128));
-  NERF_TRY(tc_make_tmap(&p.map_dir[1], dir_lo, M, 64, dir_pitch, 128));
+  const int tiles = (int)cdiv(M, 128);
+  const int grid = tiles < sms ? tiles : sms;
+  // rays != nullptr: the kernel's encoder warps build the encodings (see launch_mlp_fused_forward)
+  long map_rows = M;
+  if (rays) {
+    p.enc_mode = enc_scratch_rows > 0 ? 2 : 1;
+    p.rs = *rays;
+    p.enc_pos[0] = const_cast<__nv_bfloat16*>(pos_hi); p.enc_pos[1] = const_cast<__nv_bfloat16*>(pos_lo);
+    p.enc_dir[0] = const_cast<__nv_bfloat16*>(dir_hi); p.enc_dir[1] = const_cast<__nv_bfloat16*>(dir_lo);
+    if (p.enc_mode == 2) {
+      if (enc_scratch_rows < (long)grid * 256) { set_error("fused forward: encoding scratch too small"); return 100001; }
+      map_rows = enc_scratch_rows;
+    }
+    if (rays->deg_point % 4 || rays->deg_point * 6 > 120 || rays->deg_view > 4 || (long)rays->R * rays->S < M) {
+      set_error("fused forward: in-kernel encoding needs deg_point %% 4 == 0, <= 20, deg_view <= 4"); return 100001;
+    }
+  }
+  NERF_TRY(tc_make_tmap(&p.map_pos[0], pos_hi, map_rows, 128, pos_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_pos[1], pos_lo, map_rows, 128, pos_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_dir[0], dir_hi, map_rows, 64, dir_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_dir[1], dir_lo, map_rows, 64, dir_pitch, 128));
   for (int s = 0; s <= D; s++) {
     const int N = s < D ? W : Wc;
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], w_hi[s], N, kpad[s], kpad[s], 128));
@@ -728,13 +480,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  const int tiles = (int)cdiv(M, 128);
-  const int grid = tiles < sms ? tiles : sms;
-  if (quarters) {
-    if (train) k_mlp_fused_split_q<1><<<grid, kThreadsS, smem, st>>>(p);
-    else k_mlp_fused_split_q<0><<<grid, kThreadsS, smem, st>>>(p);
-  } else if (train) k_mlp_fused_split<1><<<grid, kThreadsS, smem, st>>>(p);
-  else k_mlp_fused_split<0><<<grid, kThreadsS, smem, st>>>(p);
+  if (train) k_mlp_fused_split<1><<<grid, kThreadsSE, smem, st>>>(p);
+  else k_mlp_fused_split<0><<<grid, kThreadsSE, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
 }
@@ -746,9 +493,9 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool quarters, cudaStream_t st) {
+                                 cudaStream_t st) {
   if (W != 256 || Wc != 128 || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
-  NERF_TRY(ensure_kernel_smem(quarters ? (const void*)k_mlp_fused_split_q<2> : (const void*)k_mlp_fused_split<2>, 218 * 1024));
+  NERF_TRY(ensure_kernel_smem((const void*)k_mlp_fused_split<2>, 218 * 1024));
   const int sms = device_sm_count();
   const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 218 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
@@ -772,8 +519,7 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
   const int tiles = (int)cdiv(M, 128);
-  if (quarters) k_mlp_fused_split_q<2><<<tiles < sms ? tiles : sms, kThreadsS, smem, st>>>(p);
-  else k_mlp_fused_split<2><<<tiles < sms ? tiles : sms, kThreadsS, smem, st>>>(p);
+  k_mlp_fused_split<2><<<tiles < sms ? tiles : sms, kThreadsS, smem, st>>>(p);
   NERF_CHECK_LAUNCH();
   return 0;
 }

@@ -128,7 +128,7 @@ class TcMlp : public MlpEngine {
 
   int forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
     if (can_fuse_forward() && !(flags_ & NERF_FLAG_NO_FUSED_TRAIN_FORWARD))
-      return fused_forward(level, M, params, raw_density, raw_rgb, true, st);
+      return fused_forward(level, M, params, raw_density, raw_rgb, true, nullptr, st);
     Level& lv = levels_[level];
     const int D = s_.D, C = s_.C;
     const Plane* h = &lv.enc_pos;
@@ -180,7 +180,24 @@ class TcMlp : public MlpEngine {
 
   int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
     if (!can_fuse_forward()) return forward(level, M, params, raw_density, raw_rgb, st);
-    return fused_forward(level, M, params, raw_density, raw_rgb, false, st);
+    return fused_forward(level, M, params, raw_density, raw_rgb, false, nullptr, st);
+  }
+
+  // cast_rays + IPE + direction PE inside the fused forward kernel (encoder warps, encode_rows.cuh): no encode kernel runs.
+  // Training: the encoder warps write the level's planes (the wgrad GEMMs of layer 0, the skip layer and the condition layer
+  // read them); rendering: a per-CTA double-buffered scratch that stays in L2.
+  int forward_from_rays(int level, const RaySource& rays, long M, const float* params, float* raw_density, float* raw_rgb,
+                        bool training, cudaStream_t st, int* handled) override {
+    *handled = 0;
+    if (!can_fuse_forward() || (flags_ & NERF_FLAG_NO_FUSED_ENCODE) || (training && (flags_ & NERF_FLAG_NO_FUSED_TRAIN_FORWARD))) return 0;
+    if (rays.deg_point % 4 || 6 * rays.deg_point > 120 || rays.deg_view > 4) return 0;
+    if (!training && !scr_pos_.hi) {  // 148 CTAs x 2 buffers x 256 rows (bf16 walks tile pairs): 29 MB with the lo planes
+      scr_rows_ = (long)device_sm_count() * 2 * 256;
+      NERF_TRY(alloc_plane(&scr_pos_, scr_rows_, pos_pitch_));
+      NERF_TRY(alloc_plane(&scr_dir_, scr_rows_, dir_pitch_));
+    }
+    *handled = 1;
+    return fused_forward(level, M, params, raw_density, raw_rgb, training, &rays, st);
   }
 
   // biases of the D trunk layers and the condition layer, then the density head (w[256], b) and the rgb head (w[3][128], b[3]):
@@ -211,8 +228,14 @@ class TcMlp : public MlpEngine {
     return 0;
   }
 
-  int fused_forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, bool train, cudaStream_t st) {
+  int fused_forward(int level, long M, const float* params, float* raw_density, float* raw_rgb, bool train, const RaySource* rays,
+                    cudaStream_t st) {
     Level& lv = levels_[level];
+    // where the encodings are: the level's planes, or (rendering with in-kernel encoding) the L2 scratch
+    const bool scratch = rays && !train;
+    const Plane& epos = scratch ? scr_pos_ : lv.enc_pos;
+    const Plane& edir = scratch ? scr_dir_ : lv.enc_dir;
+    const long scr_rows = scratch ? scr_rows_ : 0;
     const int D = s_.D;
     std::vector<int> bias_off(D + 1), kpad(D + 1), in_b(D + 1);
     std::vector<const __nv_bfloat16*> wpl(D + 1);
@@ -230,14 +253,14 @@ class TcMlp : public MlpEngine {
       std::vector<const __nv_bfloat16*> wlo(D + 1);
       std::vector<__nv_bfloat16*> act_lo(D + 1);
       for (int s = 0; s <= D; s++) { wlo[s] = wp_[s < D ? s : D + 1].lo; act_lo[s] = lv.acts[s].lo; }
-      return launch_mlp_fused_forward_split(lv.enc_pos.hi, lv.enc_pos.lo, pos_pitch_, lv.enc_dir.hi, lv.enc_dir.lo, dir_pitch_, wpl.data(),
+      return launch_mlp_fused_forward_split(epos.hi, epos.lo, pos_pitch_, edir.hi, edir.lo, dir_pitch_, wpl.data(),
                                             wlo.data(), kpad.data(), in_b.data(), D, s_.W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                             head_rgb_off, bias_off.data(), raw_density, raw_rgb, train ? act_out.data() : nullptr,
-                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, quarters(), st);
+                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, st);
     }
-    return launch_mlp_fused_forward(lv.enc_pos.hi, pos_pitch_, lv.enc_dir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
+    return launch_mlp_fused_forward(epos.hi, pos_pitch_, edir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
-                                    train ? act_out.data() : nullptr, train ? lv.bits.data() : nullptr, st);
+                                    train ? act_out.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, st);
   }
 
   int backward(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
@@ -340,8 +363,7 @@ class TcMlp : public MlpEngine {
         std::vector<__nv_bfloat16*> dz_lo(D);
         for (int j = 0; j < D; j++) { wt_lo[j] = wtp_[j == 0 ? D + 1 : D - j].lo; dz_lo[j] = dzs_[j].lo; }
         NERF_TRY(launch_mlp_fused_dgrad_split(dz_cond.hi, dz_cond.lo, dz_cond.pitch, wt.data(), wt_lo.data(), wt_pitch.data(), D, W, s_.Wc, M,
-                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(),
-                                              quarters(), st));
+                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), st));
       } else {
         NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                         d_raw_density, dz_out.data(), masks.data(), st));
@@ -536,14 +558,14 @@ class TcMlp : public MlpEngine {
     return 0;
   }
 
-  bool quarters() const { return (flags_ & NERF_FLAG_QUARTER_SCHEDULE) != 0; }
-
   bool split_;
   unsigned flags_ = 0;
   MlpShape s_;
   long max_rows_ = 0;
   int pos_pitch_ = 0, dir_pitch_ = 0;
   std::vector<Level> levels_;
+  Plane scr_pos_, scr_dir_;  // rendering: encoding scratch of the in-kernel encoder warps (L2-resident)
+  long scr_rows_ = 0;
   Plane dz_[2];
   std::vector<Plane> dzs_;  // bf16 fused dgrad chain: dZ of trunk layer D-1-j, kept for the wgrad GEMMs
   std::vector<Plane> wp_, wtp_;

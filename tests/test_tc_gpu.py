@@ -144,10 +144,10 @@ def test_tc_whole_step_and_training(precision):
 
 
 LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO_FUSED_DGRAD
-# engine schedules that must agree with the layer-by-layer kernels: the shipped one and, in the fp32-accurate mode, the
-# quarter-granular variant of the fused kernels (nerf_config.engine_flags)
-SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("fp32_tc", nb.FLAG_QUARTER_SCHEDULE)]
-SCHED_IDS = ["bf16", "fp32_tc", "fp32_tc-quarters"]
+# engine variants that must agree with the layer-by-layer kernels (nerf_config.engine_flags): the shipped one (cast_rays + IPE
+# + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
+SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encode-kernel", "fp32_tc-encode-kernel"]
 
 
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
@@ -245,6 +245,33 @@ def test_fused_kernels_many_tiles_per_cta(precision, flags):
     np.testing.assert_allclose(acc1, acc2, atol=0.1 * tol)
     assert abs(l1 - l2) <= 1e-5 * abs(l2)
     assert rel_err(g1, g2) <= 2e-3
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
+@pytest.mark.parametrize("R", [700, 37], ids=["R700-many-tiles", "R37-ragged"])
+def test_inkernel_encoding_is_bit_identical_to_the_encode_kernel(precision, R):
+    """accelerated_functions.cu:292-317 + 187-221 inside the fused MLP kernels: the encoder warps run the arithmetic of
+    encode.cu (same device functions, same order), so a render and a whole gradient step must give the SAME BITS as the
+    path that runs k_encode_pos / k_encode_dir first — through the training planes, through the L2 scratch of the render
+    path (more tiles than CTAs: both scratch buffers of every CTA are reused), and on a ragged last tile."""
+    m, ncfg, ocfg = _model(R, precision, **NET)
+    m2, _, _ = _model(R, precision, engine_flags=nb.FLAG_NO_FUSED_ENCODE, **NET)
+    rays, pix, u = batch(R, ncfg.n_samples)
+    params = _params_with_biases(ocfg)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
+    rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    out1, out2 = m.render(*rargs), m2.render(*rargs)
+    assert l1 == l2
+    np.testing.assert_array_equal(g1, g2)
+    for a, b in zip(out1, out2):
+        np.testing.assert_array_equal(a, b)
+    before = m.launch_count()
+    m.render(*rargs)
+    n1 = m.launch_count() - before
+    before = m2.launch_count()
+    m2.render(*rargs)
+    assert m2.launch_count() - before - n1 >= 2 * 2  # no encode launches on the default path (2 kernels x 2 levels per chunk less)
 
 
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
