@@ -106,8 +106,11 @@ __device__ __forceinline__ void store_chunk8(const float (&x)[8], __nv_bfloat16*
 // (3 + 6 * deg_view features, deg_view <= 4, zero padded), each as a bf16 hi plane and — fp32-accurate mode — a lo plane
 // with x ~= hi + lo.  Same operations in the same order as k_encode_pos / k_encode_dir (encode.cu): the planes are
 // bit-identical to what those kernels write.  `valid` = false (row beyond the batch) writes zeros.
-__device__ __forceinline__ void encode_row_to_planes(const RaySource& rs, long m, bool valid, long out_row, __nv_bfloat16* pos_hi,
-                                                     __nv_bfloat16* pos_lo, __nv_bfloat16* dir_hi, __nv_bfloat16* dir_lo) {
+// FAST = single bf16 plane out (encode.cu: `fast`); a template parameter and a rolled frequency loop keep the code small —
+// the encoder shares the instruction cache with the MMA issue and epilogue loops of the fused kernels.
+template <bool FAST>
+__device__ __noinline__ void encode_row_to_planes(const RaySource& rs, long m, bool valid, long out_row, __nv_bfloat16* pos_hi,
+                                                  __nv_bfloat16* pos_lo, __nv_bfloat16* dir_hi, __nv_bfloat16* dir_lo) {
   __nv_bfloat16* ph = pos_hi + out_row * 128;
   __nv_bfloat16* pl = pos_lo ? pos_lo + out_row * 128 : nullptr;
   __nv_bfloat16* dh = dir_hi + out_row * 64;
@@ -126,8 +129,9 @@ __device__ __forceinline__ void encode_row_to_planes(const RaySource& rs, long m
   const Gauss g = frustum_to_gaussian(__ldg(rs.t + (long)r * (rs.S + 1) + s), __ldg(rs.t + (long)r * (rs.S + 1) + s + 1),
                                       __ldg(rs.radii + r), oo, dd);
   const HalfTurns hx = to_half_turns(g.mx), hy = to_half_turns(g.my), hz = to_half_turns(g.mz);
-  const bool fast = pos_lo == nullptr;  // single bf16 plane out (encode.cu: `fast`)
+  constexpr bool fast = FAST;
   // four frequencies = 24 features = three 16-byte chunks per pass
+#pragma unroll 1
   for (int f0 = 0; f0 < 20; f0 += 4) {
     const int c0 = (f0 >> 2) * 3;
     if (f0 >= rs.deg_point) {

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
         for (int i = et; i < 256; i += 32 * kEncWarps) {
           const long m = (long)pair * 256 + i;
           const bool valid = m < p.M;
-          if (valid || p.enc_mode == 2) enc::encode_row_to_planes(p.rs, m, valid, out0 + i, p.enc_pos, nullptr, p.enc_dir, nullptr);
+          if (valid || p.enc_mode == 2) enc::encode_row_to_planes<true>(p.rs, m, valid, out0 + i, p.enc_pos, nullptr, p.enc_dir, nullptr);
         }
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> visible to the TMA loads
         __syncwarp();

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           const long m = (long)tile * 128 + i;
           const bool valid = m < p.M;
           if (valid || p.enc_mode == 2)
-            enc::encode_row_to_planes(p.rs, m, valid, out0 + i, p.enc_pos[0], p.enc_pos[1], p.enc_dir[0], p.enc_dir[1]);
+            enc::encode_row_to_planes<false>(p.rs, m, valid, out0 + i, p.enc_pos[0], p.enc_pos[1], p.enc_dir[0], p.enc_dir[1]);
         }
         asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> visible to the TMA loads
         __syncwarp();

@@ -189,7 +189,8 @@ class TcMlp : public MlpEngine {
   int forward_from_rays(int level, const RaySource& rays, long M, const float* params, float* raw_density, float* raw_rgb,
                         bool training, cudaStream_t st, int* handled) override {
     *handled = 0;
-    if (!can_fuse_forward() || (flags_ & NERF_FLAG_NO_FUSED_ENCODE) || (training && (flags_ & NERF_FLAG_NO_FUSED_TRAIN_FORWARD))) return 0;
+    if (!can_fuse_forward()) return 0;
+    if (training ? (!(flags_ & NERF_FLAG_FUSED_ENCODE_TRAIN) || (flags_ & NERF_FLAG_NO_FUSED_TRAIN_FORWARD)) : (flags_ & NERF_FLAG_NO_FUSED_ENCODE) != 0) return 0;
     if (rays.deg_point % 4 || 6 * rays.deg_point > 120 || rays.deg_view > 4) return 0;
     if (!training && !scr_pos_.hi) {  // 148 CTAs x 2 buffers x 256 rows (bf16 walks tile pairs): 29 MB with the lo planes
       scr_rows_ = (long)device_sm_count() * 2 * 256;

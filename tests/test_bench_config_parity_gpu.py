@@ -25,9 +25,9 @@ pytestmark = pytest.mark.gpu
 R, S = 512, 128
 TOL = {"fp32_tc": 1e-4, "bf16": 2e-2}
 # fraction of ReLU masks that may differ from fp64 (~ forward error / spread of the pre-activations)
-MAX_FLIPS = {"fp32_tc": 2e-5, "bf16": 1e-2}
+MAX_FLIPS = {"fp32_tc": 2e-5, "bf16": 1e-2}  # measured 3.1e-6 / 1.1e-3
 # whole-step gradient against the PLAIN fp64 gradient (masks free): kink-limited, see the module docstring
-RAW_TOL = {"fp32_tc": 1e-3, "bf16": 0.15}
+RAW_TOL = {"fp32_tc": 1e-4, "bf16": 0.15}  # fp32 path: north_star's 1e-4 holds on the plain gradient too at this batch size (1.9e-5 measured)
 
 
 class _IntView:

@@ -146,8 +146,9 @@ def test_tc_whole_step_and_training(precision):
 LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO_FUSED_DGRAD
 # engine variants that must agree with the layer-by-layer kernels (nerf_config.engine_flags): the shipped one (cast_rays + IPE
 # + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
-SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE)]
-SCHED_IDS = ["bf16", "fp32_tc", "bf16-encode-kernel", "fp32_tc-encode-kernel"]
+ENC_ALL = nb.FLAG_FUSED_ENCODE_TRAIN  # encoder warps in the training forward too (rendering has them by default)
+SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel"]
 
 
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
@@ -254,7 +255,7 @@ def test_inkernel_encoding_is_bit_identical_to_the_encode_kernel(precision, R):
     encode.cu (same device functions, same order), so a render and a whole gradient step must give the SAME BITS as the
     path that runs k_encode_pos / k_encode_dir first — through the training planes, through the L2 scratch of the render
     path (more tiles than CTAs: both scratch buffers of every CTA are reused), and on a ragged last tile."""
-    m, ncfg, ocfg = _model(R, precision, **NET)
+    m, ncfg, ocfg = _model(R, precision, engine_flags=nb.FLAG_FUSED_ENCODE_TRAIN, **NET)
     m2, _, _ = _model(R, precision, engine_flags=nb.FLAG_NO_FUSED_ENCODE, **NET)
     rays, pix, u = batch(R, ncfg.n_samples)
     params = _params_with_biases(ocfg)
