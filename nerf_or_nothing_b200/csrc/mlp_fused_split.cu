@@ -16,6 +16,9 @@
 #include <cuda.h>
 
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "encode_rows.cuh"
 #include "gemm_tc.cuh"
@@ -139,8 +142,19 @@ __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint3
 // Forward modes run two more warps (10, 11), the ENCODERS: one thread per sample row turns the tile's t-values + ray into
 // the hi/lo encoding rows (encode_rows.cuh), stored through L2; enc_ready[tile & 1] hands them to the producer's TMA loads,
 // enc_free[tile & 1] (MMA issuer, end of tile) returns the scratch buffer.  They run up to two tiles ahead of the MMAs.
-template <int MODE>
+//
+// CL = 2: the kernel runs as thread-block CLUSTERS of two CTAs that share every weight stage.  Measured (ncu, round 1) the
+// CL = 1 kernels move ~5300 B/cycle through L2 — 2.3 MB of hi+lo weights per 128-row tile against 6144 cycles of MMAs per layer
+// — which is the chip's L2 throughput ceiling (~6300 B/cycle, B300_MICROARCH.md), not the tensor pipe: that is why the
+// training forward and the dgrad chain both sat at 55 % tensor-pipe activity.  Every CTA walks the SAME weight sequence
+// (weights do not depend on the tile), so the two rings run in lock-step slot for slot: rank 0 fetches the W_hi box of a stage,
+// rank 1 the W_lo box, each with `.multicast::cluster` into both CTAs' rings — one L2 read feeds two SMs, weight traffic
+// halves.  A slot is recycled when BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto w_empty, count CL).
+// Encoding stages stay per-CTA (own tile).  Every CTA of the grid walks the same NUMBER of tiles (phantom tiles past the end
+// load zeros and store nothing) so that the rings never diverge.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
+  static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
   constexpr bool TRAIN = MODE != 0;
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
@@ -156,9 +170,12 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
   float* s_const = reinterpret_cast<float*>(stage_buf + (TRAIN ? kEpiWarps * kSlotB : 0));
 
   const int n_tiles = (int)((p.M + 127) / 128);
+  const int tiles_per_cta = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA: rings stay in lock-step
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     for (int h = 0; h < 2; h++) { mbar_init(&acc_full[h], 1); mbar_init(&acc_empty[h], kEpiWarps); }
     mbar_init(&act_ready, kEpiWarps);
     mbar_init(&act_lo_ready, kEpiWarps);
@@ -176,6 +193,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t ACT_HI = tmem_base, ACT_LO = tmem_base + 128, ACC = tmem_base + 256;  // ACC half h at + 128 h
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     // 32 KB stages — the hi|lo tiles [128 x 64] of a weight half-layer k-block, or of an encoding k-block (A operand)
     if (lane == 0) {
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+      for (int tile = blockIdx.x; (int)tl < tiles_per_cta; tile += gridDim.x, tl++) {
         // rows of this tile's encodings in the tensors the maps view: the sample index, or this CTA's scratch buffer tl & 1
         const int row0 = (!DGRAD && p.enc_mode == 2) ? (blockIdx.x * 2 + (int)(tl & 1)) * 128 : tile * 128;
         if (!DGRAD && p.enc_mode) mbar_wait(&enc_ready[tl & 1], (tl >> 1) & 1);  // the encoder warps have written them
@@ -205,10 +223,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
                 it++;
               }
               const int ws = it % NS;  // W_hi | W_lo rows [128 h, 128 h + 128) of this k-block
-              mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);
-              mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
-              tma_load_2d(w_ring + (size_t)ws * kStageB, &p.map_w[s][0], kb * 64, h * 128, &w_full[ws]);
-              tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &p.map_w[s][1], kb * 64, h * 128, &w_full[ws]);
+              mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);   // every CTA of the cluster has consumed this slot
+              mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);  // both boxes land here, whoever fetches them
+              if (CL == 1) {
+                tma_load_2d(w_ring + (size_t)ws * kStageB, &p.map_w[s][0], kb * 64, h * 128, &w_full[ws]);
+                tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &p.map_w[s][1], kb * 64, h * 128, &w_full[ws]);
+              } else {  // this CTA fetches one of the two boxes for the whole cluster
+                tma_load_2d_multicast(w_ring + (size_t)ws * kStageB + cta_rank * 16384, &p.map_w[s][cta_rank], kb * 64, h * 128, &w_full[ws],
+                                      kAllCtas);
+              }
               it++;
             }
         }
@@ -221,7 +244,12 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     const uint32_t ring_base = smem_u32(w_ring);
     const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
     uint32_t it = 0, n_acc[2] = {0, 0}, n_act = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+    // a ring slot is released in EVERY CTA of the cluster: the peer may multicast into this CTA's slot only when both are done
+    auto release = [&](uint64_t* bar) {
+      if (CL == 1) umma_commit(bar);
+      else umma_commit_multicast(bar, kAllCtas);
+    };
+    for (; (int)tl < tiles_per_cta; tl++) {
       for (int s = 0; s < p.n_steps; s++) {
         const SplitParams::Step st = p.steps[s];
         const int n_kb = st.n_act_kb + st.n_enc_kb;
@@ -265,9 +293,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
                   umma_bf16(acc, dal + 2 * k, dbh + 2 * k, idesc, 1u);
                   umma_bf16(acc, dah + 2 * k, dbl + 2 * k, idesc, 1u);
                 }
-                umma_commit(&w_empty[a_stage]);
+                release(&w_empty[a_stage]);
               }
-              umma_commit(&w_empty[ws]);
+              release(&w_empty[ws]);
             }
             it++;
           }
@@ -284,7 +312,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     if (!DGRAD && p.enc_mode) {
       const int et = threadIdx.x - kThreadsS;  // 0 .. 32 * kEncWarpsS
       uint32_t tl = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tl++) {
+      for (int tile = blockIdx.x; (int)tl < tiles_per_cta; tile += gridDim.x, tl++) {
         if (tl >= 2) mbar_wait(&enc_free[tl & 1], ((tl >> 1) & 1) ^ 1);  // tile tl - 2 has been loaded out of this buffer
         const long out0 = p.enc_mode == 2 ? (long)(blockIdx.x * 2 + (int)(tl & 1)) * 128 : (long)tile * 128;
         for (int i = et; i < 128; i += 32 * kEncWarpsS) {
@@ -306,7 +334,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     uint8_t* slot_row = slot + lane * 64;
     const int swz = (lane >> 1) & 3;             // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
     uint32_t n_full[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int ti = 0, tile = blockIdx.x; ti < tiles_per_cta; ti++, tile += gridDim.x) {
       const int row_w = tile * 128 + qtr * 32;
       const int row_t = qtr * 32 + lane;         // row within the tile
       const long row = (long)row_w + lane;
@@ -413,9 +441,56 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
 
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
   if (warp == kEpiWarps) tmem_dealloc<512>(tmem_base);
 }
 
+
+// launch on `grid` CTAs (rounded up to whole clusters); CL = 2 -> thread-block clusters of two CTAs
+template <int MODE>
+int launch_split(const SplitParams& p, int grid, int threads, size_t smem, bool pair, cudaStream_t st) {
+  const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2> : (const void*)k_mlp_fused_split<MODE, 1>;
+  NERF_TRY(ensure_kernel_smem(kern, 218 * 1024));  // per device: the opt-in is a (kernel, device) property
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(pair ? (grid + 1) / 2 * 2 : grid));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = pair ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  if (pair) {
+    // A persistent kernel must be one wave: clusters are placed inside a GPC, so an odd SM left over in a GPC cannot host one.
+    // Size the grid by what the device can hold at once (memoised per kernel and device).
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cache;
+    int dev = 0;
+    NERF_CUDA(cudaGetDevice(&dev));
+    int max_clusters = 0;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = cache.find({kern, dev});
+      if (it == cache.end()) {
+        cudaLaunchConfig_t probe = cfg;
+        probe.gridDim = dim3((unsigned)(device_sm_count() / 2 * 2));
+        int n = 0;
+        NERF_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &probe));
+        it = cache.emplace(std::make_pair(kern, dev), n).first;
+      }
+      max_clusters = it->second;
+    }
+    if (max_clusters < 1) { set_error("fused kernel: no 2-CTA cluster fits on this device"); return 100001; }
+    if ((int)cfg.gridDim.x > 2 * max_clusters) cfg.gridDim = dim3((unsigned)(2 * max_clusters));
+  }
+  SplitParams pp = p;
+  void* args[] = {&pp};
+  NERF_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  count_launch();
+  return 0;
+}
 
 }  // namespace
 
@@ -426,20 +501,19 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, cudaStream_t st) {
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
   if (W != 256 || Wc != 128 || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
     return 100001;
   }
   const bool train = act_hi != nullptr;
   const size_t smem = (size_t)(train ? kNSTrain : kNSInfer) * kStageB + (train ? kEpiWarps * kSlotB : 0) + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
-  NERF_TRY(ensure_kernel_smem(train ? (const void*)k_mlp_fused_split<1> : (const void*)k_mlp_fused_split<0>, 218 * 1024));  // per device
   const int sms = device_sm_count();
   if (smem > 218 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
   SplitParams p;
   memset(&p, 0, sizeof(p));
   const int tiles = (int)cdiv(M, 128);
-  const int grid = tiles < sms ? tiles : sms;
+  const int grid = pair ? ((tiles < sms ? tiles : sms) + 1) / 2 * 2 : (tiles < sms ? tiles : sms);  // whole clusters
   // rays != nullptr: the kernel's encoder warps build the encodings (see launch_mlp_fused_forward)
   long map_rows = M;
   if (rays) {
@@ -480,10 +554,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  if (train) k_mlp_fused_split<1><<<grid, kThreadsSE, smem, st>>>(p);
-  else k_mlp_fused_split<0><<<grid, kThreadsSE, smem, st>>>(p);
-  NERF_CHECK_LAUNCH();
-  return 0;
+  return train ? launch_split<1>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0>(p, grid, kThreadsSE, smem, pair, st);
 }
 
 
@@ -493,9 +564,8 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 cudaStream_t st) {
+                                 bool pair, cudaStream_t st) {
   if (W != 256 || Wc != 128 || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
-  NERF_TRY(ensure_kernel_smem((const void*)k_mlp_fused_split<2>, 218 * 1024));
   const int sms = device_sm_count();
   const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 218 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
@@ -519,9 +589,7 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
   const int tiles = (int)cdiv(M, 128);
-  k_mlp_fused_split<2><<<tiles < sms ? tiles : sms, kThreadsS, smem, st>>>(p);
-  NERF_CHECK_LAUNCH();
-  return 0;
+  return launch_split<2>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
 }
 
 }  // namespace nerf

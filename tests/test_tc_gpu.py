@@ -147,8 +147,9 @@ LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO
 # engine variants that must agree with the layer-by-layer kernels (nerf_config.engine_flags): the shipped one (cast_rays + IPE
 # + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
 ENC_ALL = nb.FLAG_FUSED_ENCODE_TRAIN  # encoder warps in the training forward too (rendering has them by default)
-SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE)]
-SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel"]
+SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE),
+             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast"]
 
 
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
@@ -273,6 +274,26 @@ def test_inkernel_encoding_is_bit_identical_to_the_encode_kernel(precision, R):
     before = m2.launch_count()
     m2.render(*rargs)
     assert m2.launch_count() - before - n1 >= 2 * 2  # no encode launches on the default path (2 kernels x 2 levels per chunk less)
+
+
+@pytest.mark.parametrize("R", [700, 37, 2], ids=["R700-many-tiles", "R37-ragged", "R2-one-tile"])
+def test_weight_multicast_clusters_are_bit_identical_to_single_ctas(R):
+    """fp32-accurate fused kernels as 2-CTA clusters that share every weight stage by TMA multicast (mlp_fused_split.cu): the
+    arithmetic of a tile does not depend on which CTA walks it or on who fetched its weights, so render, loss and gradients
+    must be the same bits as with one CTA per slot — with more tiles than CTAs (rings recycled many times), an odd tile count
+    (a phantom tile keeps the pair's rings in lock-step) and fewer tiles than one cluster."""
+    m, ncfg, ocfg = _model(R, "fp32_tc", **NET)
+    m2, _, _ = _model(R, "fp32_tc", engine_flags=nb.FLAG_NO_WEIGHT_MULTICAST, **NET)
+    rays, pix, u = batch(R, ncfg.n_samples)
+    params = _params_with_biases(ocfg)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
+    rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    out1, out2 = m.render(*rargs), m2.render(*rargs)
+    assert l1 == l2
+    np.testing.assert_array_equal(g1, g2)
+    for a, b in zip(out1, out2):
+        np.testing.assert_array_equal(a, b)
 
 
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
