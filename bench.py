@@ -133,32 +133,34 @@ class ClockSampler:
             self.proc = None
 
     def window(self, t0, t1):
-        """clocks / throttle reasons of the samples taken in [t0, t1] (the sampler keeps running)"""
+        """clocks / board power / throttle reasons of the samples taken in [t0, t1] (the sampler keeps running)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         time.sleep(0.15)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t0 - 0.05 or ts > t1 + 0.05:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower() == "active":
-                    reasons.add(n)
-        if not sm:  # region shorter than the sampling period: take every sample we have
-            for ts, line in self.rows:
+
+        def collect(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for line in rows:
                 f = [x.strip() for x in line.split(",")]
                 try:
                     sm.append(float(f[0])); mx.append(float(f[1]))
                 except Exception:
+                    continue
+                try:
+                    pw.append(float(f[2]))
+                except Exception:
                     pass
+                for n, v in zip(names, f[3:7]):
+                    if v.lower() == "active":
+                        reasons.add(n)
+            return sm, mx, pw, reasons
+
+        sm, mx, pw, reasons = collect([line for ts, line in self.rows if t0 - 0.05 <= ts <= t1 + 0.05])
+        if not sm:  # region shorter than the sampling period: take every sample we have
+            sm, mx, pw, reasons = collect([line for _, line in self.rows])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def peaks():
