@@ -49,7 +49,8 @@ struct alignas(64) FusedParams {
     int16_t n_act_kb;   // k-blocks read from the TMEM-resident activation (0 or width/64)
     int16_t enc_kind;   // 0 none, 1 position encoding, 2 direction encoding (shared-memory A operand)
     int16_t n_enc_kb;   // k-blocks of that encoding
-    int16_t n_halves;   // N / 128
+    int16_t n_halves;   // ceil(N / 128): a 64-wide layer runs as one half whose upper 64 weight rows are the TMA's out-of-bounds zeros
+    int16_t n_cols;     // N: output columns that exist (64, 128 or 256)
     int16_t produces;   // 1: writes the next layer's activation; 0: last (condition) layer
     int16_t head;       // 0 none, 1 density head after this step, 3 rgb head after this step
     int32_t bias_off;   // offset into the staged constants
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
           const float* bias = s_const + st.bias_off + h * 128;
           uint32_t m0, m1, m2, m3;
           uint4 mk = make_uint4(0u, 0u, 0u, 0u);  // DGRAD: ReLU mask words of this thread's 128 columns (requested before the wait)
-          if (DGRAD && row_ok) mk = __ldg(reinterpret_cast<const uint4*>(p.bits[s] + row * (st.n_halves * 4) + h * 4));
+          if (DGRAD && row_ok) mk = __ldg(reinterpret_cast<const uint4*>(p.bits[s] + row * (st.n_cols >> 5) + h * 4));  // dgrad outputs are 128 or 256 wide
           const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + h * 128 : nullptr;
           // one 32-column chunk c of this half: forward = bias + ReLU (+ heads, + mask out); dgrad = (+ r1 v1^T) * mask in
           auto chunk = [&](const uint32_t (&r)[32], int c, const float* hw, uint32_t* out16) -> uint32_t {
@@ -439,12 +440,18 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
               tmem_st_wait();
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&act_ready);
+              if (lane == 0) {
+                if (st.n_halves == 1) mbar_arrive(&act_lo_ready);  // a one-half layer has no parked first instalment
+                mbar_arrive(&act_ready);
+              }
             }
             ship(h * 128 + 64, 1, pk);
           }
-          if (MODE == 1 && row_ok)
-            *reinterpret_cast<uint4*>(p.bits[s] + row * (st.n_halves * 4) + h * 4) = make_uint4(m0, m1, m2, m3);
+          if (MODE == 1 && row_ok) {
+            uint32_t* bw = p.bits[s] + row * (st.n_cols >> 5) + h * 4;
+            if (st.n_cols >= 128) *reinterpret_cast<uint4*>(bw) = make_uint4(m0, m1, m2, m3);
+            else *reinterpret_cast<uint2*>(bw) = make_uint2(m0, m1);  // 64-wide layer: two mask words per row
+          }
         }
         if (DGRAD) continue;
         if (st.head == 1) {
@@ -478,8 +485,8 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                              float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
                              const RaySource* rays, long enc_scratch_rows, cudaStream_t st) {
-  if (W != 256 || Wc != 128 || D + 1 > kMaxSteps || pos_pitch != 128 || dir_pitch != 64) {
-    set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
+  if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxSteps || pos_pitch != 128 || dir_pitch != 64) {
+    set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
   }
   const bool train = act_out != nullptr;
@@ -517,9 +524,10 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
     }
     FusedParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
-    else if (s < D) { stp.n_act_kb = 4; stp.enc_kind = in_b[s] ? 1 : 0; stp.n_enc_kb = in_b[s] ? 2 : 0; }
-    else { stp.n_act_kb = 4; stp.enc_kind = 2; stp.n_enc_kb = 1; }
-    stp.n_halves = (int16_t)(N / 128);
+    else if (s < D) { stp.n_act_kb = (int16_t)(W / 64); stp.enc_kind = in_b[s] ? 1 : 0; stp.n_enc_kb = in_b[s] ? 2 : 0; }
+    else { stp.n_act_kb = (int16_t)(W / 64); stp.enc_kind = 2; stp.n_enc_kb = 1; }
+    stp.n_halves = (int16_t)((N + 127) / 128);
+    stp.n_cols = (int16_t)N;
     stp.produces = s < D ? 1 : 0;
     stp.head = s == D - 1 ? 1 : (s == D ? 3 : 0);
     stp.bias_off = bias_off[s];
@@ -541,22 +549,23 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
 int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, const __nv_bfloat16* const* wt, const int* wt_pitch, int D, int W,
                            int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                            __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, cudaStream_t st) {
-  if (W != 256 || Wc != 128 || D > kMaxSteps || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
+  if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxSteps || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   NERF_TRY(ensure_kernel_smem((const void*)k_mlp_fused_fwd<2>, 226 * 1024));
   const int sms = device_sm_count();
   const size_t smem = (size_t)(kWStages - 1) * kWStageBytes + 2 * kEncBytes + 8 * kStageSlot + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 226 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
   FusedParams p;
   memset(&p, 0, sizeof(p));
-  NERF_TRY(tc_make_tmap(&p.map_pos, dz_cond, M, 128, dz_cond_pitch, 128));  // A of step 0, loaded like the position encoding
+  NERF_TRY(tc_make_tmap(&p.map_pos, dz_cond, M, Wc, dz_cond_pitch, 128));  // A of step 0, loaded like the position encoding
   for (int s = 0; s < D; s++) {
     NERF_TRY(tc_make_tmap(&p.map_w[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_act[s], dz_out[s], M, W, W, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     FusedParams::Step& stp = p.steps[s];
-    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
-    else { stp.n_act_kb = 4; stp.enc_kind = 0; stp.n_enc_kb = 0; }
-    stp.n_halves = 2;
+    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
+    else { stp.n_act_kb = (int16_t)(W / 64); stp.enc_kind = 0; stp.n_enc_kb = 0; }
+    stp.n_halves = (int16_t)(W / 128);
+    stp.n_cols = (int16_t)W;
     stp.produces = s < D - 1 ? 1 : 0;
     stp.head = 0; stp.bias_off = 0;
   }

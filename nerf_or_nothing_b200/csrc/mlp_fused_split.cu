@@ -51,8 +51,10 @@ struct alignas(64) SplitParams {
   CUtensorMap map_act[kMaxStepsS][2];         // training: [hi, lo] activation planes [M, N], box {32, 32} (SWIZZLE_64B)
   uint32_t* bits[kMaxStepsS];                 // training: ReLU bit planes [M, N/32]
   struct Step {
-    int16_t n_act_kb, enc_kind, n_enc_kb, n_halves;  // n_halves = N / 128
+    int16_t n_act_kb, enc_kind, n_enc_kb, n_halves;  // n_halves = ceil(N / 128): a 64-wide layer runs as one half whose upper
+                                                     // 64 weight rows are the TMA's out-of-bounds zeros
     int16_t produces, head;
+    int16_t n_cols;                                  // N: output columns that exist (64, 128 or 256)
     int32_t bias_off;
   } steps[kMaxStepsS];
   int n_steps;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           const uint32_t acc = ACC + 128 * h + lane_off + ch * 64;
           uint32_t m0, m1;
           uint2 mk = make_uint2(0u, 0u);  // DGRAD: ReLU mask words of this thread's 64 columns (requested before the wait)
-          if (DGRAD && row_ok) mk = __ldg(reinterpret_cast<const uint2*>(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5)));
+          if (DGRAD && row_ok && col_t < st.n_cols) mk = __ldg(reinterpret_cast<const uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)));
           const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + col_t : nullptr;
           auto chunk = [&](const uint32_t (&r)[32], int c, uint32_t* hw_, uint32_t* lw_) -> uint32_t {
             if (DGRAD) {
@@ -415,11 +417,14 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
               tmem_st_wait();
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&act_ready);
+              if (lane == 0) {
+                if (st.n_halves == 1) mbar_arrive(&act_lo_ready);  // a one-half layer has no parked first instalment
+                mbar_arrive(&act_ready);
+              }
             }
             ship(col_t + 32, hw, lw);
           }
-          if (MODE == 1 && row_ok) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_halves * 4) + (col_t >> 5)) = make_uint2(m0, m1);
+          if (MODE == 1 && row_ok && col_t < st.n_cols) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)) = make_uint2(m0, m1);
         }
         if (!DGRAD && st.head) {  // the column halves of a row meet in shared memory
           if (ch == 1) { head_part[row_t][0] = head[0]; head_part[row_t][1] = head[1]; head_part[row_t][2] = head[2]; }
@@ -502,8 +507,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
                                    uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
-  if (W != 256 || Wc != 128 || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
-    set_error("fused forward supports width 256 / condition width 128 / position pitch 128 / direction pitch 64");
+  if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
+    set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
   }
   const bool train = act_hi != nullptr;
@@ -544,9 +549,10 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
     }
     SplitParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
-    else if (s < D) { stp.n_act_kb = 4; stp.enc_kind = in_b[s] ? 1 : 0; stp.n_enc_kb = in_b[s] ? 2 : 0; }
-    else { stp.n_act_kb = 4; stp.enc_kind = 2; stp.n_enc_kb = 1; }
-    stp.n_halves = (int16_t)(N / 128);
+    else if (s < D) { stp.n_act_kb = (int16_t)(W / 64); stp.enc_kind = in_b[s] ? 1 : 0; stp.n_enc_kb = in_b[s] ? 2 : 0; }
+    else { stp.n_act_kb = (int16_t)(W / 64); stp.enc_kind = 2; stp.n_enc_kb = 1; }
+    stp.n_halves = (int16_t)((N + 127) / 128);
+    stp.n_cols = (int16_t)N;
     stp.produces = s < D ? 1 : 0;
     stp.head = s == D - 1 ? 1 : (s == D ? 3 : 0);
     stp.bias_off = bias_off[s];
@@ -565,14 +571,14 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
                                  bool pair, cudaStream_t st) {
-  if (W != 256 || Wc != 128 || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports width 256 / condition width 128"); return 100001; }
+  if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
   const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 218 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
   SplitParams p;
   memset(&p, 0, sizeof(p));
-  NERF_TRY(tc_make_tmap(&p.map_pos[0], dz_cond_hi, M, 128, dz_cond_pitch, 128));  // A of step 0, streamed like an encoding
-  NERF_TRY(tc_make_tmap(&p.map_pos[1], dz_cond_lo, M, 128, dz_cond_pitch, 128));
+  NERF_TRY(tc_make_tmap(&p.map_pos[0], dz_cond_hi, M, Wc, dz_cond_pitch, 128));  // A of step 0, streamed like an encoding
+  NERF_TRY(tc_make_tmap(&p.map_pos[1], dz_cond_lo, M, Wc, dz_cond_pitch, 128));
   for (int s = 0; s < D; s++) {
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], wt_hi[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
@@ -580,9 +586,10 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
     NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     SplitParams::Step& stp = p.steps[s];
-    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = 2; }
-    else { stp.n_act_kb = 4; stp.enc_kind = 0; stp.n_enc_kb = 0; }
-    stp.n_halves = 2;
+    if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
+    else { stp.n_act_kb = (int16_t)(W / 64); stp.enc_kind = 0; stp.n_enc_kb = 0; }
+    stp.n_halves = (int16_t)(W / 128);
+    stp.n_cols = (int16_t)W;
     stp.produces = s < D - 1 ? 1 : 0;
     stp.head = 0; stp.bias_off = 0;
   }

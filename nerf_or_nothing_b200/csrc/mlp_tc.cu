@@ -173,9 +173,11 @@ class TcMlp : public MlpEngine {
 
   // Rendering: no backward follows, so in bf16 mode the whole net runs as one kernel with the activations kept in
   // tensor memory (mlp_fused.cu) instead of one GEMM launch per layer with the activations written to HBM.
+  // The fused kernels are written for trunk / condition widths 256 / 128 (the reference network) and 128 / 64 (the narrow end of
+  // the configs[4] sweep), one condition layer, encodings that fit 128 / 64 columns.
   bool can_fuse_forward() const {
-    return s_.W == 256 && s_.Wc == 128 && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 12 && pos_pitch_ == 128 && dir_pitch_ == 64 &&
-           !(flags_ & NERF_FLAG_NO_FUSED_FORWARD);
+    const bool widths = (s_.W == 256 && s_.Wc == 128) || (s_.W == 128 && s_.Wc == 64);
+    return widths && s_.C == 1 && s_.D >= 2 && s_.D + 1 <= 12 && pos_pitch_ == 128 && dir_pitch_ == 64 && !(flags_ & NERF_FLAG_NO_FUSED_FORWARD);
   }
 
   int forward_only(int level, long M, const float* params, float* raw_density, float* raw_rgb, cudaStream_t st) override {
@@ -222,8 +224,9 @@ class TcMlp : public MlpEngine {
     }
     const LayerInfo& Ld = s_.layers[D];
     const LayerInfo& Lr = s_.layers[D + 2];
-    add(head_d_off, Ld.w_off, 256); add(head_d_off + 256, Ld.b_off, 1);
-    add(head_rgb_off, Lr.w_off, 3 * 128); add(head_rgb_off + 384, Lr.b_off, 3);
+    add(head_d_off, Ld.w_off, s_.W); add(head_d_off + 256, Ld.b_off, 1);  // w[W] (zero beyond W), bias in a fixed slot
+    for (int n = 0; n < 3; n++) add(head_rgb_off + n * 128, Lr.w_off + (long)n * s_.Wc, s_.Wc);  // w[3][Wc] in rows of 128
+    add(head_rgb_off + 384, Lr.b_off, 3);
     NERF_TRY(launch_gather_f32(params, fconsts_, jobs, st));
     fconsts_dirty_ = false;
     return 0;

@@ -14,6 +14,9 @@ TOL = {"fp32_tc": 1e-4, "bf16": 2e-2}
 NET = dict(n_samples=64)  # 8x256 + 1x128 view branch, 64+64 samples (BASELINE config 1 shape)
 SMALL = dict(n_samples=32, net_depth=4, net_width=64, net_depth_condition=2, net_width_condition=64, skip_layer=2,
              deg_point=8, deg_view=2)
+# the narrow end of BASELINE.json configs[4] (4x128, condition width 64): runs through the same fused kernels as 8x256
+NARROW = dict(n_samples=64, net_depth=4, net_width=128, net_depth_condition=1, net_width_condition=64, skip_layer=2)
+NETS = {"8x256": NET, "4x128": NARROW}
 
 
 def _model(R, precision, **kw):
@@ -30,7 +33,7 @@ def _params_with_biases(ocfg, seed=5):
 
 
 @pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
-@pytest.mark.parametrize("cfgkw,R", [(NET, 16), (NET, 3), (SMALL, 5)], ids=["8x256-M1024", "8x256-M192", "small-M160"])
+@pytest.mark.parametrize("cfgkw,R", [(NET, 16), (NET, 3), (SMALL, 5), (NARROW, 16)], ids=["8x256-M1024", "8x256-M192", "small-M160", "4x128-M1024"])
 def test_tc_mlp_forward(precision, cfgkw, R):
     m, ncfg, ocfg = _model(R, precision, **cfgkw)
     S = ncfg.n_samples
@@ -70,8 +73,8 @@ def _stable_inputs(ocfg, params, M, P, Dd, margin, seed):
 
 
 @pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
-@pytest.mark.parametrize("cfgkw,R", [(NET, 64), (NET, 3), (SMALL, 5), (NET, 300)],
-                         ids=["8x256-M4096", "8x256-M192", "small-M160", "8x256-M19200"])  # M19200: 75 head partials -> wide reduction
+@pytest.mark.parametrize("cfgkw,R", [(NET, 64), (NET, 3), (SMALL, 5), (NET, 300), (NARROW, 64)],
+                         ids=["8x256-M4096", "8x256-M192", "small-M160", "8x256-M19200", "4x128-M4096"])  # M19200: 75 head partials -> wide reduction
 def test_tc_mlp_backward(precision, cfgkw, R):
     """dgrad / wgrad GEMMs (MN-major operands, split reduction) against the fp64 oracle.
     fp32_tc: <= 1e-4 of each tensor's scale on ReLU-stable samples (margin 2e-4 >> the 3e-6 forward error).
@@ -152,15 +155,16 @@ SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL
 SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast"]
 
 
+@pytest.mark.parametrize("net", list(NETS))
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
 @pytest.mark.parametrize("R", [200, 1], ids=["R200-chunked", "R1"])
-def test_fused_forward_render(R, precision, flags):
+def test_fused_forward_render(R, precision, flags, net):
     """Rendering runs the whole MLP as ONE kernel with TMEM-resident activations (mlp_fused.cu / mlp_fused_split.cu).
     It must agree with the fp64 oracle within the mode's tolerance and with the layer-by-layer chain (same operands,
     same roundings between layers) far tighter; ragged last tile (R*S not a multiple of the tile rows) and the tile loop
     included.  Rendering is deterministic (no jitter) whatever cfg.randomized says."""
-    m, ncfg, ocfg = _model(64, precision, engine_flags=flags, **NET)
-    m2, _, _ = _model(64, precision, engine_flags=nb.FLAG_NO_FUSED_FORWARD, **NET)
+    m, ncfg, ocfg = _model(64, precision, engine_flags=flags, **NETS[net])
+    m2, _, _ = _model(64, precision, engine_flags=nb.FLAG_NO_FUSED_FORWARD, **NETS[net])
     S = ncfg.n_samples
     rays, pix, _ = batch(R, S)
     params = _params_with_biases(ocfg)
@@ -191,13 +195,14 @@ def _gradient_step(m, params, rays, pix, u):
     return m.get_gradients().copy(), m.get_loss()[1]
 
 
+@pytest.mark.parametrize("net", list(NETS))
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
-def test_fused_training_forward_matches_layered(precision, flags):
+def test_fused_training_forward_matches_layered(precision, flags, net):
     """The training forward is the same fused kernel with the activation planes and ReLU bit planes written out for the
     backward pass: a whole gradient step through it must equal the step through the layer-by-layer forward."""
     R = 24
-    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
-    m2, _, _ = _model(R, precision, engine_flags=flags | nb.FLAG_NO_FUSED_TRAIN_FORWARD, **NET)
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NETS[net])
+    m2, _, _ = _model(R, precision, engine_flags=flags | nb.FLAG_NO_FUSED_TRAIN_FORWARD, **NETS[net])
     rays, pix, u = batch(R, ncfg.n_samples)
     params = _params_with_biases(ocfg)
     g1, l1 = _gradient_step(m, params, rays, pix, u)
@@ -208,14 +213,15 @@ def test_fused_training_forward_matches_layered(precision, flags):
     assert rel_err(g1, g2) <= 1e-3
 
 
+@pytest.mark.parametrize("net", list(NETS))
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
-def test_fused_dgrad_chain_matches_layered(precision, flags):
+def test_fused_dgrad_chain_matches_layered(precision, flags, net):
     """The backward dgrad chain of the trunk is one kernel (dZ resident in tensor memory between layers, each layer's dZ
     written once for the wgrad GEMMs).  Same operands, the same ReLU bit masks and the same roundings between layers as
     the per-layer dgrad launches, so the parameter gradients agree to accumulation-order noise."""
     R = 24
-    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
-    m2, _, _ = _model(R, precision, engine_flags=flags | nb.FLAG_NO_FUSED_DGRAD, **NET)
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NETS[net])
+    m2, _, _ = _model(R, precision, engine_flags=flags | nb.FLAG_NO_FUSED_DGRAD, **NETS[net])
     rays, pix, u = batch(R, ncfg.n_samples)
     params = _params_with_biases(ocfg)
     g1, _ = _gradient_step(m, params, rays, pix, u)
@@ -225,14 +231,15 @@ def test_fused_dgrad_chain_matches_layered(precision, flags):
     assert rel_err(g1, g2) <= 1e-5
 
 
+@pytest.mark.parametrize("net", list(NETS))
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
-def test_fused_kernels_many_tiles_per_cta(precision, flags):
+def test_fused_kernels_many_tiles_per_cta(precision, flags, net):
     """More row tiles than CTAs (700 rays x 64 samples = 350 tiles / 175 tile pairs on 148 SMs, ragged tail): every CTA of
     the persistent fused kernels walks several tiles, so the mbarrier phase bookkeeping across tiles is exercised.  Render
     and a whole gradient step must match the layer-by-layer kernels."""
     R = 700
-    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NET)
-    m2, _, _ = _model(R, precision, engine_flags=LAYERED, **NET)
+    m, ncfg, ocfg = _model(R, precision, engine_flags=flags, **NETS[net])
+    m2, _, _ = _model(R, precision, engine_flags=LAYERED, **NETS[net])
     rays, pix, u = batch(R, ncfg.n_samples)
     params = _params_with_biases(ocfg)
     rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
