@@ -528,35 +528,43 @@ k_thin_fwd_planes(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __r
   }
 }
 
-// dX[m, k..k+7] = mask * sum_n dz[m,n] W[n,k]: one thread per 8 consecutive columns, 16-byte plane stores
-__global__ void k_thin_dgrad_planes(const float* __restrict__ dZ, const float* __restrict__ W, long M, int N, int K,
-                                    const uint32_t* __restrict__ mask_bits, int ld_bits, __nv_bfloat16* __restrict__ oh,
-                                    __nv_bfloat16* __restrict__ ol, int ldo) {
-  const int k8 = K >> 3;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * k8) return;
-  const long m = idx / k8;
-  const int k = (int)(idx % k8) * 8;
-  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int n = 0; n < N; n++) {
-    const float g = __ldg(dZ + m * N + n);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + n * K + k));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + n * K + k + 4));
-    v[0] = fmaf(g, w0.x, v[0]); v[1] = fmaf(g, w0.y, v[1]); v[2] = fmaf(g, w0.z, v[2]); v[3] = fmaf(g, w0.w, v[3]);
-    v[4] = fmaf(g, w1.x, v[4]); v[5] = fmaf(g, w1.y, v[5]); v[6] = fmaf(g, w1.z, v[6]); v[7] = fmaf(g, w1.w, v[7]);
-  }
-  if (mask_bits) {
-    const uint32_t bits = __ldg(mask_bits + m * ld_bits + (k >> 5)) >> (k & 31);
+// dX[m, k..k+7] = mask * sum_n dz[m,n] W[n,k].  A thread owns ONE 8-column chunk for the whole launch — its NN x 8 weights
+// live in registers — and walks rows with a grid stride (K/8 consecutive lanes cover a row: 16-byte plane stores, a full 128-byte
+// line per 8 lanes); the head gradients of a row are broadcast loads.  Pure write traffic: 4 B (hi + lo) per element.
+template <int NN>
+__global__ void __launch_bounds__(256)
+k_thin_dgrad_planes(const float* __restrict__ dZ, const float* __restrict__ W, long M, int K, const uint32_t* __restrict__ mask_bits,
+                    int ld_bits, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int ldo) {
+  const int k8 = K >> 3;                      // chunks per row (blockDim.x is a multiple of it)
+  const int k = (threadIdx.x % k8) * 8;
+  const int rows_per_block = blockDim.x / k8;
+  float w[NN][8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+  for (int n = 0; n < NN; n++) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + n * K + k)), w1 = __ldg(reinterpret_cast<const float4*>(W + n * K + k + 4));
+    w[n][0] = w0.x; w[n][1] = w0.y; w[n][2] = w0.z; w[n][3] = w0.w; w[n][4] = w1.x; w[n][5] = w1.y; w[n][6] = w1.z; w[n][7] = w1.w;
   }
-  *reinterpret_cast<uint4*>(oh + m * ldo + k) =
-      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-  if (ol) {
+  for (long m = (long)blockIdx.x * rows_per_block + threadIdx.x / k8; m < M; m += (long)gridDim.x * rows_per_block) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
-    *reinterpret_cast<uint4*>(ol + m * ldo + k) =
+    for (int n = 0; n < NN; n++) {
+      const float g = __ldg(dZ + m * NN + n);
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = fmaf(g, w[n][j], v[j]);
+    }
+    if (mask_bits) {
+      const uint32_t bits = __ldg(mask_bits + m * ld_bits + (k >> 5)) >> (k & 31);
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(oh + m * ldo + k) =
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    if (ol) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+      *reinterpret_cast<uint4*>(ol + m * ldo + k) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
   }
 }
 
@@ -960,8 +968,17 @@ int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int
 
 int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const uint32_t* mask_bits, int ld_bits,
                              __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st) {
-  if (K % 8 || ((uintptr_t)W & 15)) { set_error("thin_dgrad_planes: K=%d / W alignment", K); return 100001; }
-  k_thin_dgrad_planes<<<(unsigned)cdiv(M * (K / 8), 256), 256, 0, st>>>(dZ, W, M, N, K, mask_bits, ld_bits, oh, ol, ldo);
+  if (K % 8 || K > 2048 || N < 1 || N > 4 || ((uintptr_t)W & 15)) { set_error("thin_dgrad_planes: N=%d K=%d / W alignment", N, K); return 100001; }
+  const int rows_per_block = 256 / (K / 8);
+  const unsigned threads = (unsigned)(rows_per_block * (K / 8));  // whole rows per block
+  long blocks = cdiv(M, rows_per_block);
+  if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride over the rows: the weights are loaded once per thread
+  switch (N) {
+    case 1: k_thin_dgrad_planes<1><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
+    case 2: k_thin_dgrad_planes<2><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
+    case 3: k_thin_dgrad_planes<3><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
+    default: k_thin_dgrad_planes<4><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
+  }
   NERF_CHECK_LAUNCH();
   return 0;
 }

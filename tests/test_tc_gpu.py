@@ -187,6 +187,30 @@ def test_fused_forward_render(R, precision, flags, net):
     np.testing.assert_allclose(acc, acc2, atol=0.1 * tol)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
+@pytest.mark.parametrize("S,R", [(32, 21), (128, 5), (256, 3)], ids=["S32", "S128", "S256"])
+def test_fused_kernels_other_sample_counts(precision, S, R):
+    """A 128-row tile is 4 rays at S = 32, one ray at S = 128 (the bench) and half a ray at S = 256: the encoder warps' row ->
+    (ray, sample) mapping, the render and a whole gradient step against the fp64 oracle and the per-layer kernels."""
+    kw = dict(NET, n_samples=S)
+    m, ncfg, ocfg = _model(R, precision, **kw)
+    m2, _, _ = _model(R, precision, engine_flags=LAYERED | nb.FLAG_NO_FUSED_ENCODE, **kw)
+    rays, pix, u = batch(R, S)
+    params = _params_with_biases(ocfg)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
+    rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    rgb1, _, acc1 = m.render(*rargs)
+    rgb2, _, acc2 = m2.render(*rargs)
+    ocfg.randomized = 0
+    o = orc.train_gradient(ocfg, params, rays, pix, np.zeros((2, R, S + 1), np.float32), with_backward=False, prec="f64")
+    tol = TOL[precision]
+    np.testing.assert_allclose(rgb1, o["comp_rgb"][1], atol=tol)
+    np.testing.assert_allclose(acc1, o["acc"][1], atol=tol)
+    np.testing.assert_allclose(rgb1, rgb2, atol=0.1 * tol)
+    assert abs(l1 - l2) <= 1e-5 * abs(l2) and rel_err(g1, g2) <= 2e-3
+
+
 def _gradient_step(m, params, rays, pix, u):
     m.set_params(params)
     m.set_pixels(pix)
