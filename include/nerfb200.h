@@ -140,6 +140,14 @@ int nerf_mipnerf_render(nerf_mipnerf* h, const float* origins3, const float* dir
 int nerf_mipnerf_render_dev(nerf_mipnerf* h, const float* origins3_dev, const float* directions3_dev,
                             const float* radii_dev, const float* nears_dev, const float* fars_dev,
                             long n_rays, float* rgb3_dev, float* depth_dev, float* acc_dev);
+/* One view (or a pixel range of it, row-major y * width + x) from a camera pose: c2w12 = 3 x 4 row-major [R | t] on the host.
+ * The rays are generated on the device chunk by chunk with the arithmetic of Dataset.GenerateRays (SN/Dataset.cs:111-176), so the
+ * only per-view host->device traffic is the pose.  edge_mode 0: the reference's radius at the last column (a pixel differenced
+ * with itself: 0, :151); 1: the left neighbour's difference (mip-NeRF).  Outputs on the host, or device pointers if
+ * outputs_on_device; any may be NULL. */
+int nerf_mipnerf_render_view(nerf_mipnerf* h, const float* c2w12, float focal, int width, int height, float near_,
+                             float far_, int edge_mode, long first_pixel, long n_pixels, float* rgb3, float* depth,
+                             float* acc, int outputs_on_device);
 /* per-level results of the last get_gradient / render chunk (device pointers, library-owned) */
 int nerf_mipnerf_level_outputs(nerf_mipnerf* h, int level, uint64_t* comp_rgb_dev, uint64_t* depth_dev,
                                uint64_t* acc_dev, uint64_t* weights_dev, uint64_t* t_vals_dev);
@@ -281,6 +289,11 @@ typedef struct nerf_dataset nerf_dataset;
 int nerf_dataset_create(const void* records, long n_records, int device, nerf_dataset** out);
 int nerf_dataset_load(const char* path, int device, nerf_dataset** out); /* train_data.bin, SN/Program.cs:23 */
 int nerf_dataset_size(const nerf_dataset* ds, long* n);                  /* SN/BinDataset.cs:15 */
+/* Dataset.GenerateRays (SN/Dataset.cs:111-176) for pixels [first_pixel, first_pixel + n_pixels) of one camera into device
+ * arrays (what nerf_mipnerf_render_view feeds itself with); c2w12 on the host. */
+int nerf_generate_rays(const float* c2w12, float focal, int width, int height, float near_, float far_, int edge_mode,
+                       long first_pixel, long n_pixels, float* origins3_dev, float* directions3_dev, float* radii_dev,
+                       float* nears_dev, float* fars_dev);
 int nerf_dataset_destroy(nerf_dataset* ds);
 /* BinDataset.Next (SN/BinDataset.cs:21-25): batch indices drawn with replacement — here from Philox4x32-10 with
  * counter (first_slot + i, 0, step, 0x0DA7A5E7), key = seed, index = floor(word0 * n / 2^32) — instead of

@@ -179,6 +179,14 @@ inline void SaveCheckpoint(AcceleratedMipNeRF& model, AcceleratedAdamOptimizer* 
 inline void LoadCheckpoint(AcceleratedMipNeRF& model, AcceleratedAdamOptimizer* optimizer, const std::string& path) {
   check(nerf_checkpoint_load(model.handle(), optimizer ? optimizer->handle() : nullptr, path.c_str()));
 }
+// MathHelpers.MseToPsnr / ComputeSsimAverage (ScratchNerf/ScratchNerf/MipHelpers.cs:672, 688-737) of two host images [height, width, 3]
+struct ImageMetrics { double mse, psnr, ssim; };
+inline ImageMetrics CompareImages(const float* a, const float* b, int width, int height, float max_val = 1.0f) {
+  ImageMetrics m{};
+  check(nerf_image_error(a, b, (long)width * height * 3, 0, &m.mse, &m.psnr));
+  check(nerf_image_ssim(a, b, width, height, max_val, 11, 1.5f, 0.01f, 0.03f, 0, &m.ssim, nullptr));
+  return m;
+}
 
 // ANU/OutputRetriever.h:7-11
 struct OutputRetriever {

@@ -78,6 +78,8 @@ _SIGNATURES = {
     "nerf_mipnerf_render": [_VP, _VP, _VP, _VP, _VP, _VP, _L, _VP, _VP, _VP],
     "nerf_mipnerf_render_dev": [_VP, _VP, _VP, _VP, _VP, _VP, _L, _VP, _VP, _VP],
     "nerf_mipnerf_level_outputs": [_VP, _I] + [C.POINTER(C.c_uint64)] * 5,
+    "nerf_mipnerf_render_view": [_VP, _VP, _F, _I, _I, _F, _F, _I, _L, _L, _VP, _VP, _VP, _I],
+    "nerf_generate_rays": [_VP, _F, _I, _I, _F, _F, _I, _L, _L, _VP, _VP, _VP, _VP, _VP],
     "nerf_mipnerf_get_loss": [_VP, C.POINTER(_F), C.POINTER(_F)],
     "nerf_mipnerf_synchronize": [_VP],
     "nerf_mipnerf_launch_count": [_VP, C.POINTER(_L)],
@@ -333,6 +335,16 @@ class AcceleratedMipNeRF:
         check(lib().nerf_mipnerf_render_dev(self._h, *[_dp(x) for x in (origins, directions, radii, nears, fars)], n_rays,
                                             _dp(rgb), _dp(depth), _dp(acc)))
 
+    def render_view(self, c2w, focal, width, height, near=2.0, far=6.0, edge_mode=1, first_pixel=0, n_pixels=None):
+        """Render a view from a 3x4 camera-to-world pose; rays are generated on the device (SN/Dataset.cs:111-176).
+        Returns (rgb [n,3], depth [n], acc [n]) for the pixel range, row-major."""
+        c = _host(np.asarray(c2w, np.float32).reshape(12))
+        n = width * height - first_pixel if n_pixels is None else n_pixels
+        rgb, depth, acc = np.empty((n, 3), np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+        check(lib().nerf_mipnerf_render_view(self._h, _hp(c), focal, width, height, near, far, edge_mode, first_pixel, n,
+                                             _hp(rgb), _hp(depth), _hp(acc), 0))
+        return rgb, depth, acc
+
     def level_outputs(self, level):
         v = [C.c_uint64() for _ in range(5)]
         check(lib().nerf_mipnerf_level_outputs(self._h, level, *[C.byref(x) for x in v]))
@@ -447,6 +459,20 @@ class BinDataset:
         for k in ("radii", "nears", "fars", "loss_mults"):
             out[k] = out[k][:, 0]
         return out
+
+
+def generate_rays(c2w, focal, width, height, near=2.0, far=6.0, edge_mode=1, first_pixel=0, n_pixels=None):
+    """Dataset.GenerateRays (SN/Dataset.cs:111-176) on the device; returns host copies of the SoA ray arrays (parity hook)."""
+    import torch
+    c = _host(np.asarray(c2w, np.float32).reshape(12))
+    n = width * height - first_pixel if n_pixels is None else n_pixels
+    bufs = {k: torch.empty((n, w), dtype=torch.float32, device="cuda") for k, w in (("origins", 3), ("directions", 3), ("radii", 1), ("nears", 1), ("fars", 1))}
+    check(lib().nerf_generate_rays(_hp(c), focal, width, height, near, far, edge_mode, first_pixel, n,
+                                   *[C.c_void_p(bufs[k].data_ptr()) for k in ("origins", "directions", "radii", "nears", "fars")]))
+    out = {k: v.cpu().numpy() for k, v in bufs.items()}
+    for k in ("radii", "nears", "fars"):
+        out[k] = out[k][:, 0]
+    return out
 
 
 def image_error(a, b):

@@ -618,6 +618,39 @@ int nerf_mipnerf_render(nerf_mipnerf* h, const float* o, const float* d, const f
   return 0;
 }
 
+// One view from a camera pose: the rays of every pixel are generated on the device chunk by chunk (Dataset.GenerateRays,
+// SN/Dataset.cs:111-176), so nothing per-ray crosses PCIe on the way in.
+int nerf_mipnerf_render_view(nerf_mipnerf* h, const float* c2w12, float focal, int width, int height, float near, float far, int edge_mode,
+                             long first_pixel, long n_pixels, float* rgb, float* depth, float* acc, int outputs_on_device) {
+  if (!h || !c2w12 || width <= 0 || height <= 0 || !(focal > 0.f) || first_pixel < 0 || n_pixels <= 0 ||
+      first_pixel + n_pixels > (long)width * height) { set_error("render_view: bad arguments"); return NERF_ERR_INVALID; }
+  NERF_CUDA(cudaSetDevice(h->cfg.device));
+  ProfActivate pa(h);
+  NERF_TRY(h->mlp->prepare(h->params, h->st));
+  const int last = h->NL - 1;
+  const size_t R = (size_t)h->Rmax;
+  float* b = h->rays_dev;
+  const cudaMemcpyKind kind = outputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  for (long b0 = 0; b0 < n_pixels; b0 += h->Rc) {
+    const int rc = (int)(n_pixels - b0 < h->Rc ? n_pixels - b0 : h->Rc);
+    { ProfScope ps(PC_MISC, h->st);
+      NERF_TRY(launch_generate_rays(c2w12, focal, width, height, near, far, edge_mode, first_pixel + b0, rc, b, b + 3 * R, b + 6 * R, b + 7 * R,
+                                    b + 8 * R, h->st)); }
+    set_batch_dev(h, b, b + 3 * R, b + 6 * R, b + 7 * R, b + 8 * R, nullptr, nullptr);
+    const uint32_t keep = h->ray_offset;
+    h->ray_offset = keep + (uint32_t)b0;
+    const int s = forward_chunk(h, 0, rc, false);
+    h->ray_offset = keep;
+    NERF_TRY(s);
+    auto& L = h->lv[last];
+    if (rgb) NERF_CUDA(cudaMemcpyAsync(rgb + b0 * 3, L.comp_rgb, (size_t)rc * 12, kind, h->st));
+    if (depth) NERF_CUDA(cudaMemcpyAsync(depth + b0, L.depth, (size_t)rc * 4, kind, h->st));
+    if (acc) NERF_CUDA(cudaMemcpyAsync(acc + b0, L.acc, (size_t)rc * 4, kind, h->st));
+  }
+  if (!outputs_on_device) NERF_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
 int nerf_mipnerf_level_outputs(nerf_mipnerf* h, int level, uint64_t* comp_rgb, uint64_t* depth, uint64_t* acc,
                                uint64_t* weights, uint64_t* t_vals) {
   if (!h || level < 0 || level >= h->NL) { set_error("level_outputs: bad level"); return NERF_ERR_INVALID; }
@@ -911,6 +944,19 @@ int nerf_dataset_load(const char* path, int device, nerf_dataset** out) {  // tr
   fclose(f);
   if ((long)got != n) { set_error("dataset_load: short read from %s", path); return NERF_ERR_INVALID; }  // SN/BinDataset.cs:38-39
   return nerf_dataset_create(buf.data(), n, device, out);
+}
+
+// Dataset.GenerateRays for one camera into caller device arrays (parity hook of nerf_mipnerf_render_view's ray source)
+int nerf_generate_rays(const float* c2w12, float focal, int width, int height, float near, float far, int edge_mode, long first_pixel,
+                       long n_pixels, float* origins3_dev, float* directions3_dev, float* radii_dev, float* nears_dev, float* fars_dev) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); set_error("no CUDA device available: libnerfb200 has no CPU path"); return NERF_ERR_NO_DEVICE; }
+  if (!c2w12 || width <= 0 || height <= 0 || !(focal > 0.f) || first_pixel < 0 || n_pixels <= 0 || first_pixel + n_pixels > (long)width * height ||
+      !origins3_dev || !directions3_dev || !radii_dev || !nears_dev || !fars_dev) { set_error("generate_rays: bad arguments"); return NERF_ERR_INVALID; }
+  NERF_TRY(launch_generate_rays(c2w12, focal, width, height, near, far, edge_mode, first_pixel, n_pixels, origins3_dev, directions3_dev, radii_dev,
+                                nears_dev, fars_dev, 0));
+  NERF_CUDA(cudaStreamSynchronize(0));
+  return 0;
 }
 
 int nerf_dataset_size(const nerf_dataset* ds, long* n) {

@@ -59,6 +59,41 @@ __global__ void k_sq_err(const float* __restrict__ a, const float* __restrict__ 
   }
 }
 
+// ---- Dataset.GenerateRays (SN/Dataset.cs:111-176) for one camera, on the device ---------------------------------------------
+// Pixel p = y * W + x of the view -> camera direction ((x - W/2 + .5)/f, -(y - H/2 + .5)/f, -1), rotated by the camera-to-world
+// rotation (rows dotted left to right, separately rounded like the C#), origin = translation, radius = |d(x) - d(x+1)| * 2 / sqrt(12).
+// At the last column the reference differences a pixel with itself (radius 0, :151); edge_mode 1 uses the left neighbour instead
+// (mip-NeRF's own behaviour, and what nerf_or_nothing_b200/scene.py generates).
+__device__ __forceinline__ float3 view_dir(const float* __restrict__ c, float focal, int W, int H, int x, int y) {
+  const float dx = __fdiv_rn(__fadd_rn(__fsub_rn((float)x, __fmul_rn((float)W, 0.5f)), 0.5f), focal);
+  const float dy = -__fdiv_rn(__fadd_rn(__fsub_rn((float)y, __fmul_rn((float)H, 0.5f)), 0.5f), focal);
+  const float dz = -1.f;
+  float3 d;
+  d.x = __fadd_rn(__fadd_rn(__fmul_rn(c[0], dx), __fmul_rn(c[1], dy)), __fmul_rn(c[2], dz));
+  d.y = __fadd_rn(__fadd_rn(__fmul_rn(c[4], dx), __fmul_rn(c[5], dy)), __fmul_rn(c[6], dz));
+  d.z = __fadd_rn(__fadd_rn(__fmul_rn(c[8], dx), __fmul_rn(c[9], dy)), __fmul_rn(c[10], dz));
+  return d;
+}
+struct Pose { float c[12]; };  // 3 x 4 row-major [R | t]
+__global__ void k_generate_rays(Pose pose, float focal, int W, int H, float near, float far, int edge_mode, long first, long n,
+                                float* __restrict__ o, float* __restrict__ d, float* __restrict__ radii, float* __restrict__ nears,
+                                float* __restrict__ fars) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long p = first + i;
+  const int y = (int)(p / W), x = (int)(p % W);
+  const float3 dd = view_dir(pose.c, focal, W, H, x, y);
+  int nx = x < W - 1 ? x + 1 : x;                       // Dataset.cs:151
+  if (edge_mode == 1 && x == W - 1 && W > 1) nx = x - 1;
+  const float3 dn = view_dir(pose.c, focal, W, H, nx, y);
+  const float ex = __fsub_rn(dd.x, dn.x), ey = __fsub_rn(dd.y, dn.y), ez = __fsub_rn(dd.z, dn.z);
+  const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+  o[i * 3] = pose.c[3]; o[i * 3 + 1] = pose.c[7]; o[i * 3 + 2] = pose.c[11];
+  d[i * 3] = dd.x; d[i * 3 + 1] = dd.y; d[i * 3 + 2] = dd.z;
+  radii[i] = __fdiv_rn(__fmul_rn(len, 2.f), 3.4641016151377544f);  // * 2 / MathF.Sqrt(12)  (:152)
+  nears[i] = near; fars[i] = far;
+}
+
 // ---- SSIM (SN/MipHelpers.cs:688-757 ComputeSsim / ComputeSsimAverage; VectorImage.Convolve :903-927) -----------------
 // The reference convolves five whole images (a, b, a^2, b^2, ab) with a normalised size x size Gaussian over a ZERO-padded
 // border, one scalar triple loop per image.  Here a block owns a 16 x 16 pixel tile: both images' (16 + size - 1)^2 halo
@@ -146,6 +181,16 @@ int launch_ssim(const float* a, const float* b, int W, int H, float max_val, int
   const size_t smem = (size_t)2 * span * span * 3 * sizeof(float);
   k_ssim<<<dim3((unsigned)cdiv(W, kSsimTile), (unsigned)cdiv(H, kSsimTile)), kSsimTile * kSsimTile, smem, st>>>(a, b, W, H, filter_size, f, c1, c2,
                                                                                                                  map_out, block_sums);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_generate_rays(const float* c2w12_host, float focal, int W, int H, float near, float far, int edge_mode, long first, long n,
+                         float* o, float* d, float* radii, float* nears, float* fars, cudaStream_t st) {
+  if (n <= 0) return 0;
+  Pose pose;
+  for (int i = 0; i < 12; i++) pose.c[i] = c2w12_host[i];
+  k_generate_rays<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(pose, focal, W, H, near, far, edge_mode, first, n, o, d, radii, nears, fars);
   NERF_CHECK_LAUNCH();
   return 0;
 }

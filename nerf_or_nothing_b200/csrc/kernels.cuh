@@ -65,6 +65,9 @@ int launch_scale_by_inv(float* g, long n, const float* lm_sum_dev, cudaStream_t 
 int launch_draw_indices(uint64_t seed, uint32_t slot0, uint32_t step, long n, int R, long* idx, cudaStream_t st);
 int launch_gather_batch(const float* records, long n, const long* idx, uint64_t seed, uint32_t slot0, uint32_t step, int R, float* o,
                         float* d, float* radii, float* nears, float* fars, float* lm, float* pix, cudaStream_t st);
+// Dataset.GenerateRays (SN/Dataset.cs:111-176) for pixels [first, first + n) of one camera; c2w12_host: 3 x 4 row-major [R | t] on the HOST
+int launch_generate_rays(const float* c2w12_host, float focal, int W, int H, float near, float far, int edge_mode, long first, long n,
+                         float* o, float* d, float* radii, float* nears, float* fars, cudaStream_t st);
 int launch_sq_err(const float* a, const float* b, long n, double* out, cudaStream_t st);
 // SSIM map + per-block sums (SN/MipHelpers.cs:688-757); images [H, W, 3]; block_sums: ssim_blocks(W, H) doubles
 long ssim_blocks(int W, int H);

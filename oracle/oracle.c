@@ -102,6 +102,34 @@ void orc_init_params(const orc_config* c, uint64_t seed, float* params) {
     for (int j = 0; j < out[l]; j++) params[off++] = 0.0f;
 }
 
+/* Dataset.GenerateRays (SN/Dataset.cs:111-176), one camera, float arithmetic in the original's order: cameraDirs, rotation * dir
+ * (Matrix3x3 rows dotted left to right), radius = |d(x) - d(nextX)| * 2 / sqrt(12) with nextX = x at the last column (:151;
+ * edge_mode 1: the left neighbour instead).  c2w: 3 x 4 row-major [R | t]; pixels [first, first + n) row-major. */
+static void orc_view_dir_(const float* c, float focal, int W, int H, int x, int y, float* d) {
+  const float dx = ((float)x - (float)W * 0.5f + 0.5f) / focal, dy = -(((float)y - (float)H * 0.5f + 0.5f) / focal), dz = -1.0f;
+  d[0] = c[0] * dx + c[1] * dy + c[2] * dz;
+  d[1] = c[4] * dx + c[5] * dy + c[6] * dz;
+  d[2] = c[8] * dx + c[9] * dy + c[10] * dz;
+}
+void orc_generate_rays(const float* c2w, float focal, int W, int H, float near_, float far_, int edge_mode, long first, long n,
+                       float* o, float* d, float* radii, float* nears, float* fars) {
+  for (long i = 0; i < n; i++) {
+    const long p = first + i;
+    const int y = (int)(p / W), x = (int)(p % W);
+    float dd[3], dn[3];
+    orc_view_dir_(c2w, focal, W, H, x, y, dd);
+    int nx = x < W - 1 ? x + 1 : x;
+    if (edge_mode == 1 && x == W - 1 && W > 1) nx = x - 1;
+    orc_view_dir_(c2w, focal, W, H, nx, y, dn);
+    const float ex = dd[0] - dn[0], ey = dd[1] - dn[1], ez = dd[2] - dn[2];
+    const float len = sqrtf(ex * ex + ey * ey + ez * ez);
+    o[i * 3] = c2w[3]; o[i * 3 + 1] = c2w[7]; o[i * 3 + 2] = c2w[11];
+    d[i * 3] = dd[0]; d[i * 3 + 1] = dd[1]; d[i * 3 + 2] = dd[2];
+    radii[i] = len * 2 / sqrtf(12.0f);
+    nears[i] = near_; fars[i] = far_;
+  }
+}
+
 /* ComputeSsim (SN/MipHelpers.cs:688-727) with VectorImage.Convolve (:903-927) and CreateGaussianFilter (:739-756), float
  * arithmetic in the original's order: five zero-padded "same" convolutions of a, b, a*a, b*b, a*b with the normalised
  * fs x fs Gaussian (taps kx outer, ky inner), variances and the covariance clamped at 0, map = num / den.  Images are

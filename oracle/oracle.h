@@ -140,6 +140,8 @@ ORC_DECL(_f32, float)
 ORC_DECL(_f64, double)
 
 /* LR schedule — SN/MipHelpers.cs:758-773 (float arithmetic as in the C#). */
+void orc_generate_rays(const float* c2w, float focal, int W, int H, float near_, float far_, int edge_mode, long first, long n,
+                       float* o, float* d, float* radii, float* nears, float* fars); /* SN/Dataset.cs:111-176 */
 double orc_ssim(const float* a, const float* b, int W, int H, float max_val, int fs, float sigma, float k1, float k2,
                 float* map); /* SN/MipHelpers.cs:688-737 */
 float orc_learning_rate_decay(int step, float lr_init, float lr_final, int max_steps,

@@ -138,6 +138,19 @@ def learning_rate_decay(step, lr_init=5e-4, lr_final=5e-6, max_steps=1000000, lr
     return float(lib().orc_learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps, lr_delay_mult))
 
 
+def generate_rays(c2w, focal, width, height, near=2.0, far=6.0, edge_mode=1, first=0, n=None):
+    """Dataset.GenerateRays (SN/Dataset.cs:111-176) for one camera; c2w 3x4 row-major [R | t]."""
+    c = _arr(np.asarray(c2w).reshape(12), np.float32)
+    n = width * height - first if n is None else n
+    out = dict(origins=np.empty((n, 3), np.float32), directions=np.empty((n, 3), np.float32), radii=np.empty(n, np.float32),
+               nears=np.empty(n, np.float32), fars=np.empty(n, np.float32))
+    fn = lib().orc_generate_rays
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_long, C.c_long] + [C.c_void_p] * 5
+    fn(_p(c), focal, width, height, near, far, edge_mode, first, n, *[_p(out[k]) for k in ("origins", "directions", "radii", "nears", "fars")])
+    return out
+
+
 def ssim(a, b, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03):
     """(mean, map) of ComputeSsim / ComputeSsimAverage (SN/MipHelpers.cs:688-737); images [H, W, 3] float32."""
     a, b = _arr(a, np.float32), _arr(b, np.float32)

@@ -124,6 +124,33 @@ def test_checkpoint_resume_is_bitwise_identical(tmp_path):
         m2.load_checkpoint(tmp_path / "junk.ckpt")
 
 
+def test_generate_rays_and_render_view_match_oracle():
+    """Dataset.GenerateRays on the device (SN/Dataset.cs:111-176): the same bits as the CPU restatement for both edge modes and
+    a pixel sub-range; nerf_mipnerf_render_view (rays generated chunk by chunk on the device, only the pose crosses PCIe) gives
+    the same image bits as rendering the oracle's host ray arrays."""
+    from tests.test_oracle_cpu import _pose
+
+    W, H = 53, 41
+    c2w = _pose(3)
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    for mode in (0, 1):
+        got = nb.generate_rays(c2w, focal, W, H, edge_mode=mode)
+        ref = orc.generate_rays(c2w, focal, W, H, edge_mode=mode)
+        for k in ref:
+            np.testing.assert_array_equal(got[k], ref[k])
+    part = nb.generate_rays(c2w, focal, W, H, first_pixel=500, n_pixels=777)
+    for k in ref:
+        np.testing.assert_array_equal(part[k], ref[k][500:1277])
+    for precision in ("fp32", "bf16"):
+        m = nb.AcceleratedMipNeRF(nb.default_config(n_rays=512, n_samples=32, precision=precision))  # 2173 pixels: 5 chunks, ragged tail
+        rgb, depth, acc = m.render_view(c2w, focal, W, H)
+        rgb2, depth2, acc2 = m.render(ref["origins"], ref["directions"], ref["radii"], ref["nears"], ref["fars"])
+        np.testing.assert_array_equal(rgb, rgb2)
+        np.testing.assert_array_equal(depth, depth2)
+        np.testing.assert_array_equal(acc, acc2)
+        assert rgb.shape == (W * H, 3) and np.isfinite(rgb).all()
+
+
 def test_ssim_matches_oracle():
     """nerf_image_ssim (SN/MipHelpers.cs:688-737) against the CPU restatement: same taps in the same order in fp32, so the
     map agrees to rounding noise; sizes that are not multiples of the 16 x 16 tile, a different window, and the mean of an

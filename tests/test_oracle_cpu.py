@@ -267,3 +267,43 @@ def test_ssim_oracle_against_scipy_and_identities():
     assert abs(orc.ssim(b, a)[0] - mean) <= 1e-7
     worse = np.clip(a + rng.normal(0, 0.2, a.shape), 0, 1).astype(np.float32)
     assert orc.ssim(a, worse)[0] < mean < 1.0
+
+
+def _pose(seed=0):
+    """camera on a radius-4 sphere looking at the origin: 3x4 row-major [R | t] (columns of R: right, up, back)"""
+    rng = np.random.default_rng(seed)
+    th, ph = rng.uniform(0, 2 * np.pi), rng.uniform(0.2 * np.pi, 0.5 * np.pi)
+    cam = 4.0 * np.array([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)])
+    fwd = -cam / np.linalg.norm(cam)
+    right = np.cross(fwd, [0.0, 0.0, 1.0])
+    right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    return np.concatenate([np.stack([right, up, -fwd], -1), cam[:, None]], 1).astype(np.float32)
+
+
+def test_generate_rays_oracle_against_fp64_statement():
+    """SN/Dataset.cs:111-176 restated (oracle.c) against the same formulas written with numpy in fp64: directions, origins,
+    radii = |d(x) - d(x+1)| * 2 / sqrt(12); the reference's zero radius at the last column (edge_mode 0) and the
+    left-neighbour variant (edge_mode 1); a pixel sub-range equals the slice of the whole view."""
+    W, H = 37, 23
+    c2w = _pose(1)
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    R, t = c2w[:, :3].astype(np.float64), c2w[:, 3].astype(np.float64)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    cam = np.stack([(xs - W * 0.5 + 0.5) / focal, -(ys - H * 0.5 + 0.5) / focal, -np.ones_like(xs, dtype=np.float64)], -1)
+    d = cam @ R.T
+    for mode in (0, 1):
+        o = orc.generate_rays(c2w, focal, W, H, edge_mode=mode)
+        np.testing.assert_allclose(o["directions"].reshape(H, W, 3), d, rtol=2e-6, atol=2e-7)
+        np.testing.assert_array_equal(o["origins"], np.broadcast_to(c2w[:, 3], (W * H, 3)))
+        rad = np.linalg.norm(d[:, :-1] - d[:, 1:], axis=-1) * 2 / np.sqrt(12.0)
+        got = o["radii"].reshape(H, W)
+        np.testing.assert_allclose(got[:, :-1], rad, rtol=2e-3)  # a difference of nearly equal fp32 directions
+        if mode == 0:
+            assert (got[:, -1] == 0).all()                        # SN/Dataset.cs:151: the last column differences with itself
+        else:
+            np.testing.assert_allclose(got[:, -1], rad[:, -1], rtol=2e-3)
+        assert (o["nears"] == 2).all() and (o["fars"] == 6).all()
+        part = orc.generate_rays(c2w, focal, W, H, edge_mode=mode, first=100, n=333)
+        for k in o:
+            np.testing.assert_array_equal(part[k], o[k][100:433])
