@@ -307,3 +307,56 @@ def test_generate_rays_oracle_against_fp64_statement():
         part = orc.generate_rays(c2w, focal, W, H, edge_mode=mode, first=100, n=333)
         for k in o:
             np.testing.assert_array_equal(part[k], o[k][100:433])
+
+
+def test_resample_against_the_published_mipnerf_formulation():
+    """Pin P6 for hierarchical sampling (the reference's CUDA version is defective, A-D9, and its C# cannot run here): the
+    inversion of the piecewise-constant CDF written the way the mip-NeRF paper's public code states it — fully vectorised, with
+    comparison masks and max / min reductions instead of the C#'s per-sample interval search (SN/MipHelpers.cs:774-851) —
+    must give the same t-values as the oracle, for jittered and deterministic u, for peaked, flat and all-zero weights."""
+    R, S = 6, 32
+    rng = np.random.default_rng(7)
+    t = np.sort(rng.uniform(2, 6, (R, S + 1)), 1)
+    w = rng.uniform(0, 1, (R, S)) ** 6
+    w[1] = 0.0
+    w[2] = 1.0
+    w[3, :] = 0.0
+    w[3, 17] = 1.0
+    u01 = orc.sampling_uniforms(5, 3, 1, 0, R, S + 1).astype(np.float64)
+    pad_ = 0.01
+
+    def published(randomized):
+        wp = np.concatenate([w[:, :1], w, w[:, -1:]], 1)                       # blur-pool (mip-NeRF resample_along_rays)
+        wmax = np.maximum(wp[:, :-1], wp[:, 1:])
+        wb = 0.5 * (wmax[:, :-1] + wmax[:, 1:]) + pad_
+        wsum = wb.sum(-1, keepdims=True)
+        padding = np.maximum(0, 1e-5 - wsum)
+        wb = wb + padding / S
+        wsum = wsum + padding
+        pdf = wb / wsum
+        cdf = np.minimum(1, np.cumsum(pdf[:, :-1], -1))
+        cdf = np.concatenate([np.zeros((R, 1)), cdf, np.ones((R, 1))], -1)     # [R, S+1]
+        ns = S + 1
+        if randomized:
+            s = 1.0 / ns
+            u = np.arange(ns) * s + u01 * (s - 1e-7)
+            u = np.minimum(u, 1.0 - 1e-7)
+        else:
+            u = np.broadcast_to(np.linspace(0.0, 1.0 - 1.1920929e-7, ns), (R, ns))
+        mask = u[:, None, :] >= cdf[:, :, None]                                  # [R, bins+1, samples]
+
+        def find_interval(x):
+            x0 = np.max(np.where(mask, x[:, :, None], x[:, :1, None]), -2)
+            x1 = np.min(np.where(~mask, x[:, :, None], x[:, -1:, None]), -2)
+            return x0, x1
+
+        b0, b1 = find_interval(t)
+        c0, c1 = find_interval(cdf)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            frac = np.clip(np.nan_to_num((u - c0) / (c1 - c0), nan=0.0, posinf=0.0, neginf=0.0), 0, 1)
+        return b0 + frac * (b1 - b0)
+
+    for randomized in (1, 0):
+        got = orc.resample_t_vals(t, w, u01.astype(np.float32), pad_, randomized, prec="f64")
+        np.testing.assert_allclose(got, published(randomized), rtol=0, atol=1e-9)
+        assert np.all(np.diff(got, axis=1) >= -1e-12)
