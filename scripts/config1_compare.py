@@ -29,10 +29,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--rays", type=int, default=1024)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "config1_compare.json"))
+    ap.add_argument("--precisions", default="fp32,fp32_tc,bf16")
+    ap.add_argument("--window", type=int, default=50, help="steps per window of the windowed loss deviation")
     a = ap.parse_args()
     R, S = a.rays, 64
     ocfg = orc.default_config(n_samples=S)
-    models = {p: nb.AcceleratedMipNeRF(nb.default_config(n_rays=R, n_samples=S, precision=p)) for p in ("fp32", "fp32_tc", "bf16")}
+    models = {p: nb.AcceleratedMipNeRF(nb.default_config(n_rays=R, n_samples=S, precision=p)) for p in a.precisions.split(",")}
     opts = {p: nb.AcceleratedAdamOptimizer(m.GetLayerSizes()) for p, m in models.items()}
     params = orc.init_params(ocfg, 7)
     for m in models.values():
@@ -62,7 +64,12 @@ def main():
            "cpu_median_s_per_step": float(np.median(t_cpu)), "cpu_rays_per_s": R / float(np.median(t_cpu)), "loss_cpu": curves["cpu"]}
     for p, m in models.items():
         c = np.asarray(curves[p])
+        nw = len(c) // a.window
+        wc, wr = c[:nw * a.window].reshape(nw, a.window).mean(1), cpu[:nw * a.window].reshape(nw, a.window).mean(1)
         out[p] = {"loss": curves[p], "max_rel_loss_deviation_vs_cpu": float(np.max(np.abs(c - cpu) / cpu)),
+                  "window": a.window, "windowed_rel_deviation_vs_cpu": [float(x) for x in np.abs(wc - wr) / wr],
+                  "max_windowed_rel_deviation_vs_cpu": float(np.max(np.abs(wc - wr) / wr)),
+                  "max_windowed_deviation_over_initial_loss": float(np.max(np.abs(wc - wr)) / wr[0]),
                   "final_param_max_abs_diff_vs_cpu": float(np.abs(m.get_params() - params).max()),
                   "final_param_rel_l2_diff_vs_cpu": float(np.linalg.norm(m.get_params() - params) / np.linalg.norm(params)),
                   "gpu_median_ms_per_step_e2e": 1e3 * float(np.median(t_gpu[p])), "gpu_rays_per_s_e2e": R / float(np.median(t_gpu[p]))}
