@@ -75,7 +75,7 @@ typedef struct nerf_config {
 #define NERF_FLAG_NO_DEFERRED_REDUCE 8u     /* wgrad partial tiles reduced by a launch of their own */
 #define NERF_FLAG_NO_FUSED_ENCODE 16u       /* rendering: cast_rays + IPE + direction PE as a kernel of their own (planes through HBM)
                                               * instead of the encoder warps inside the fused MLP kernels */
-#define NERF_FLAG_NO_WEIGHT_MULTICAST 64u   /* fp32-accurate fused kernels: one CTA per launch slot, every CTA streams its own weights
+#define NERF_FLAG_NO_WEIGHT_MULTICAST 64u   /* fused kernels: one CTA per launch slot, every CTA streams its own weights
                                               * from L2, instead of 2-CTA clusters sharing each weight stage by TMA multicast */
 #define NERF_FLAG_FUSED_ENCODE_TRAIN 32u    /* training forward: encoder warps too.  Off by default: measured on a power-capped B200
                                               * (profiles/README.md, r02b) the fused training forward loses more than the 0.3 ms encode

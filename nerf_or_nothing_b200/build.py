@@ -60,7 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             logs[src.name] = log
             (OBJ / (src.stem + ".ptxas.log")).write_text(log)
     if force or _stale(LIB, objs):
-        cmd = [_nvcc()] + ARCH + ["-shared", "-o", str(LIB)] + [str(o) for o in objs] + ["-ldl"]
+        # --no-undefined: a declaration / definition mismatch between two .cu files must fail the build, not the first call
+        cmd = [_nvcc()] + ARCH + ["-shared", "-Xlinker", "--no-undefined", "-o", str(LIB)] + [str(o) for o in objs] + ["-ldl", "-lpthread", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -45,6 +45,12 @@ inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 // per device too.  Both are memoised per (kernel, current device); returns 0 or the cudaError_t of the first failure.
 int ensure_kernel_smem(const void* kernel, int dyn_smem_bytes);
 int device_sm_count();  // of the current device (memoised)
+// Launch a persistent one-CTA-per-SM kernel, optionally as thread-block clusters of `cluster` CTAs: sets the dynamic shared memory
+// opt-in (per device), rounds the grid up to whole clusters and caps it by what the device can hold at once
+// (cudaOccupancyMaxActiveClusters: clusters are placed inside a GPC, so an odd SM left over in a GPC cannot host one — a
+// persistent kernel must be ONE wave).  `arg` points at the kernel's single by-value parameter.
+int launch_persistent_clusters(const void* kernel, int grid, int threads, size_t smem, int smem_optin_bytes, int cluster, void* arg,
+                               cudaStream_t st);
 
 // Optional in-stream kernel timing (CUDA events around each launch group on the launching stream) so that
 // bench.py can report per-kernel durations measured live inside the timed region.  Off by default.

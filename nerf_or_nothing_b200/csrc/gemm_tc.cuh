@@ -87,7 +87,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
                              const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                              float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
-                             const RaySource* rays, long enc_scratch_rows, cudaStream_t st);
+                             const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st);
 // act_out != nullptr: also write every layer's activations + ReLU bit planes.  rays != nullptr: the kernel's encoder warps
 // build the encodings from the level's t-values (cast_rays + IPE + direction PE in-kernel) into `pos` / `dir`, which are
 // the level's planes (enc_scratch_rows == 0) or an L2-resident scratch of enc_scratch_rows rows (rendering)
@@ -95,7 +95,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
 // backward dgrad chain of the trunk as one kernel (bf16 planes; mlp_fused.cu)
 int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, const __nv_bfloat16* const* wt, const int* wt_pitch, int D, int W,
                            int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
-                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, cudaStream_t st);
+                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, bool pair, cudaStream_t st);
 // the same for the fp32-accurate split mode (hi/lo planes, three-term products; mlp_fused_split.cu)
 int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloat16* pos_lo, int pos_pitch, const __nv_bfloat16* dir_hi,
                                    const __nv_bfloat16* dir_lo, int dir_pitch, const __nv_bfloat16* const* w_hi,

@@ -45,6 +45,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 struct alignas(64) FusedParams {
   CUtensorMap map_pos, map_dir;     // encodings [M, 128] / [M, 64] bf16, box {64, 128}
   CUtensorMap map_w[kMaxSteps];     // weight planes [N, Kpad] bf16, box {64, 128}
+  CUtensorMap map_w64[kMaxSteps];   // the same planes, box {64, 64}: one CTA of a 2-CTA cluster fetches half a stage for both
   struct Step {
     int16_t n_act_kb;   // k-blocks read from the TMEM-resident activation (0 or width/64)
     int16_t enc_kind;   // 0 none, 1 position encoding, 2 direction encoding (shared-memory A operand)
@@ -165,8 +166,12 @@ __device__ __forceinline__ void dgrad_chunk(const uint32_t (&r)[32], uint32_t ma
 // whose TMA loads bring them into shared memory as the A operands of layer 0, the skip layer and the condition layer.
 // They run up to two pairs ahead of the MMAs (enc_free[j & 1] = pair j's loads have landed), so the encode of the next
 // pair is hidden under the current pair's MMAs and no encode kernel runs at all.
-template <int MODE>
+// CL = 2: thread-block clusters of two CTAs share every weight stage (see mlp_fused_split.cu): rank r fetches rows [64 r, 64 r + 64)
+// of the stage's [128 x 64] weight tile with `.multicast::cluster` into both rings, a slot is recycled when both CTAs' MMAs have
+// consumed it, every CTA walks the same number of tile pairs (phantom pairs load zeros and store nothing).
+template <int MODE, int CL>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_fused_fwd(const __grid_constant__ FusedParams p) {
+  static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
   constexpr bool TRAIN = MODE != 0;   // activations / gradients are written out
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kWStages - 1 : kWStages;
@@ -185,11 +190,14 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
 
   const int n_tiles = (int)((p.M + 127) / 128);
   const int n_pairs = (n_tiles + 1) / 2;
+  const int pairs_per_cta = (n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA: rings stay in lock-step
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
   int last_pos_step = 0;
   for (int s = 0; s < p.n_steps; s++) if (p.steps[s].enc_kind == 1) last_pos_step = s;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     mbar_init(&pos_full, 1); mbar_init(&pos_empty, 1); mbar_init(&dir_full, 1); mbar_init(&dir_empty, 1);
     mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8); mbar_init(&act_ready, 8); mbar_init(&act_lo_ready, 8);
     for (int b = 0; b < 2; b++) { mbar_init(&enc_ready[b], kEncWarps); mbar_init(&enc_free[b], 1); }
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;  // tile t: ACT at +256 t, ACC at +256 t + 128
 
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
     // ------------------------------------------------------------------ TMA producer: encodings per pair + weight ring
     if (lane == 0) {
       uint32_t wit = 0, pl = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
+      for (int pair = blockIdx.x; (int)pl < pairs_per_cta; pair += gridDim.x, pl++) {
         // rows of this pair's encodings in the tensor the maps view: the sample index, or this CTA's scratch buffer pl & 1
         const int row0 = (!DGRAD && p.enc_mode == 2) ? (blockIdx.x * 2 + (int)(pl & 1)) * 256 : pair * 256;
         if (!DGRAD && p.enc_mode) mbar_wait(&enc_ready[pl & 1], (pl >> 1) & 1);  // the encoder warps have written them
@@ -236,7 +245,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
               const int ws = wit % NS;
               mbar_wait(&w_empty[ws], ((wit / NS) & 1) ^ 1);
               mbar_arrive_expect_tx(&w_full[ws], kWStageBytes);
-              tma_load_2d(w_ring + (size_t)ws * kWStageBytes, &p.map_w[s], kb * 64, h * 128, &w_full[ws]);
+              if (CL == 1) tma_load_2d(w_ring + (size_t)ws * kWStageBytes, &p.map_w[s], kb * 64, h * 128, &w_full[ws]);
+              else tma_load_2d_multicast(w_ring + (size_t)ws * kWStageBytes + cta_rank * 8192, &p.map_w64[s], kb * 64, h * 128 + (int)cta_rank * 64,
+                                         &w_full[ws], kAllCtas);  // this CTA's 64 rows of the tile, for the whole cluster
             }
         }
       }
@@ -249,7 +260,11 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
     const uint64_t desc0 = make_smem_desc(0, 16, 1024);  // + (smem address >> 4)
     const uint32_t pos_base = smem_u32(pos_buf), dir_base = smem_u32(dir_buf), ring_base = smem_u32(w_ring);
     uint32_t wit = 0, pl = 0, n_acc = 0, n_act = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
+    auto release = [&](uint64_t* bar) {  // in EVERY CTA of the cluster: the peer multicasts into this CTA's slot too
+      if (CL == 1) umma_commit(bar);
+      else umma_commit_multicast(bar, kAllCtas);
+    };
+    for (; (int)pl < pairs_per_cta; pl++) {
       for (int s = 0; s < p.n_steps; s++) {
         const FusedParams::Step st = p.steps[s];
         for (int h = 0; h < st.n_halves; h++) {
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                   umma_bf16_ts(tmem_base + 256 * t + 128, tmem_base + 256 * t + kb * 32 + k * 8, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-              umma_commit(&w_empty[ws]);
+              release(&w_empty[ws]);
             }
           }
           if (wait_act) n_act++;
@@ -295,7 +310,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
                 for (int k = 0; k < 4; k++)
                   umma_bf16(tmem_base + 256 * t + 128, desc0 + ((a0 + t * a_tile) >> 4) + 2 * k, db + 2 * k, idesc,
                             (st.n_act_kb | kb | k) ? 1u : 0u);
-              umma_commit(&w_empty[ws]);
+              release(&w_empty[ws]);
             }
           }
           if (leader) umma_commit(&acc_full);
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
     if (!DGRAD && p.enc_mode) {
       const int et = threadIdx.x - 320;  // 0 .. 32 * kEncWarps
       uint32_t pl = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, pl++) {
+      for (int pair = blockIdx.x; (int)pl < pairs_per_cta; pair += gridDim.x, pl++) {
         if (pl >= 2) mbar_wait(&enc_free[pl & 1], ((pl >> 1) & 1) ^ 1);  // pair pl - 2 has been loaded out of this buffer
         const long out0 = p.enc_mode == 2 ? (long)(blockIdx.x * 2 + (int)(pl & 1)) * 256 : (long)pair * 256;
         for (int i = et; i < 256; i += 32 * kEncWarps) {
@@ -336,7 +351,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
     uint8_t* slot_row = slot + lane * 128;
     const int swz = lane & 7;
     uint32_t n_full = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int pi = 0, pair = blockIdx.x; pi < pairs_per_cta; pi++, pair += gridDim.x) {
       const int row_w = pair * 256 + t * 128 + (warp & 3) * 32;  // first row of this warp
       const long row = (long)row_w + lane;
       const bool row_ok = row < p.M;
@@ -471,7 +486,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
 
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
   if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+template <int MODE>
+int launch_fused(const FusedParams& p, int grid, int threads, size_t smem, bool pair, cudaStream_t st) {
+  const void* kern = pair ? (const void*)k_mlp_fused_fwd<MODE, 2> : (const void*)k_mlp_fused_fwd<MODE, 1>;
+  FusedParams pp = p;
+  return launch_persistent_clusters(kern, grid, threads, smem, 226 * 1024, pair ? 2 : 1, &pp, st);
 }
 
 }  // namespace
@@ -484,7 +507,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
                              const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                              float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
-                             const RaySource* rays, long enc_scratch_rows, cudaStream_t st) {
+                             const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxSteps || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
@@ -492,13 +515,12 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   const bool train = act_out != nullptr;
   const size_t smem = (size_t)(train ? kWStages - 1 : kWStages) * kWStageBytes + 2 * kEncBytes + (train ? 8 * kStageSlot : 0) +
                       (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
-  NERF_TRY(ensure_kernel_smem(train ? (const void*)k_mlp_fused_fwd<1> : (const void*)k_mlp_fused_fwd<0>, 226 * 1024));  // per device
   const int sms = device_sm_count();
   if (smem > 226 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
   FusedParams p;
   memset(&p, 0, sizeof(p));
   const int pairs = (int)cdiv(M, 256);
-  const int grid = pairs < sms ? pairs : sms;
+  const int grid = pair ? ((pairs < sms ? pairs : sms) + 1) / 2 * 2 : (pairs < sms ? pairs : sms);  // whole clusters
   // rays != nullptr: the kernel's encoder warps build the encodings from the t-values; `pos` / `dir` are then the level's
   // planes (training) or, with enc_scratch_rows > 0, a scratch of that many rows (>= grid * 512) that never leaves L2
   long map_rows = M;
@@ -518,6 +540,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   for (int s = 0; s <= D; s++) {
     const int N = s < D ? W : Wc;
     NERF_TRY(tc_make_tmap(&p.map_w[s], wplanes[s], N, kpad[s], kpad[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_w64[s], wplanes[s], N, kpad[s], kpad[s], 64));
     if (train) {
       NERF_TRY(tc_make_tmap(&p.map_act[s], act_out[s], M, N, N, 32));
       p.bits[s] = bits_out[s];
@@ -535,10 +558,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  if (train) k_mlp_fused_fwd<1><<<grid, kThreadsFE, smem, st>>>(p);
-  else k_mlp_fused_fwd<0><<<grid, kThreadsFE, smem, st>>>(p);
-  NERF_CHECK_LAUNCH();
-  return 0;
+  return train ? launch_fused<1>(p, grid, kThreadsFE, smem, pair, st) : launch_fused<0>(p, grid, kThreadsFE, smem, pair, st);
 }
 
 
@@ -548,9 +568,8 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
 // mask_bits[i] is the bit plane of that layer's activations.  wt[0] = W_cond^T [W, Wc]; wt[i] = W_{D-i}^T [W, W].
 int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, const __nv_bfloat16* const* wt, const int* wt_pitch, int D, int W,
                            int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
-                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, cudaStream_t st) {
+                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxSteps || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
-  NERF_TRY(ensure_kernel_smem((const void*)k_mlp_fused_fwd<2>, 226 * 1024));
   const int sms = device_sm_count();
   const size_t smem = (size_t)(kWStages - 1) * kWStageBytes + 2 * kEncBytes + 8 * kStageSlot + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 226 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
@@ -559,6 +578,7 @@ int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, cons
   NERF_TRY(tc_make_tmap(&p.map_pos, dz_cond, M, Wc, dz_cond_pitch, 128));  // A of step 0, loaded like the position encoding
   for (int s = 0; s < D; s++) {
     NERF_TRY(tc_make_tmap(&p.map_w[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_w64[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 64));
     NERF_TRY(tc_make_tmap(&p.map_act[s], dz_out[s], M, W, W, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     FusedParams::Step& stp = p.steps[s];
@@ -572,9 +592,7 @@ int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, cons
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
   const int pairs = (int)cdiv(M, 256);
-  k_mlp_fused_fwd<2><<<pairs < sms ? pairs : sms, kThreadsF, smem, st>>>(p);
-  NERF_CHECK_LAUNCH();
-  return 0;
+  return launch_fused<2>(p, pairs < sms ? pairs : sms, kThreadsF, smem, pair, st);
 }
 
 }  // namespace nerf

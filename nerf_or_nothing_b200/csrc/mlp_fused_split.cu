@@ -16,9 +16,6 @@
 #include <cuda.h>
 
 #include <cstring>
-#include <map>
-#include <mutex>
-#include <utility>
 
 #include "encode_rows.cuh"
 #include "gemm_tc.cuh"
@@ -451,50 +448,11 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
 }
 
 
-// launch on `grid` CTAs (rounded up to whole clusters); CL = 2 -> thread-block clusters of two CTAs
 template <int MODE>
 int launch_split(const SplitParams& p, int grid, int threads, size_t smem, bool pair, cudaStream_t st) {
   const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2> : (const void*)k_mlp_fused_split<MODE, 1>;
-  NERF_TRY(ensure_kernel_smem(kern, 218 * 1024));  // per device: the opt-in is a (kernel, device) property
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(pair ? (grid + 1) / 2 * 2 : grid));
-  cfg.blockDim = dim3((unsigned)threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = pair ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
-  if (pair) {
-    // A persistent kernel must be one wave: clusters are placed inside a GPC, so an odd SM left over in a GPC cannot host one.
-    // Size the grid by what the device can hold at once (memoised per kernel and device).
-    static std::mutex mu;
-    static std::map<std::pair<const void*, int>, int> cache;
-    int dev = 0;
-    NERF_CUDA(cudaGetDevice(&dev));
-    int max_clusters = 0;
-    {
-      std::lock_guard<std::mutex> lock(mu);
-      auto it = cache.find({kern, dev});
-      if (it == cache.end()) {
-        cudaLaunchConfig_t probe = cfg;
-        probe.gridDim = dim3((unsigned)(device_sm_count() / 2 * 2));
-        int n = 0;
-        NERF_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &probe));
-        it = cache.emplace(std::make_pair(kern, dev), n).first;
-      }
-      max_clusters = it->second;
-    }
-    if (max_clusters < 1) { set_error("fused kernel: no 2-CTA cluster fits on this device"); return 100001; }
-    if ((int)cfg.gridDim.x > 2 * max_clusters) cfg.gridDim = dim3((unsigned)(2 * max_clusters));
-  }
   SplitParams pp = p;
-  void* args[] = {&pp};
-  NERF_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
-  count_launch();
-  return 0;
+  return launch_persistent_clusters(kern, grid, threads, smem, 218 * 1024, pair ? 2 : 1, &pp, st);
 }
 
 }  // namespace

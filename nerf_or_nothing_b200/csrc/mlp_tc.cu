@@ -264,7 +264,7 @@ class TcMlp : public MlpEngine {
     }
     return launch_mlp_fused_forward(epos.hi, pos_pitch_, edir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
-                                    train ? act_out.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, st);
+                                    train ? act_out.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st);
   }
 
   int backward(int level, long M, const float* params, float* grads, const float* d_raw_density, const float* d_raw_rgb,
@@ -370,7 +370,7 @@ class TcMlp : public MlpEngine {
                                               fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), pair(), st));
       } else {
         NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
-                                        d_raw_density, dz_out.data(), masks.data(), st));
+                                        d_raw_density, dz_out.data(), masks.data(), pair(), st));
       }
     }
     {  // condition layer

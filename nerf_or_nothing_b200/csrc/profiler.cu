@@ -1,5 +1,6 @@
 // profiler.cu — in-stream CUDA-event timing of launch groups (see common.cuh).  Used by bench.py to measure
 // each kernel family's duration live inside the timed region; never enabled by default.
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -106,6 +107,48 @@ int device_sm_count() {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   g_sms[dev] = sms;
   return sms;
+}
+
+int launch_persistent_clusters(const void* kernel, int grid, int threads, size_t smem, int smem_optin_bytes, int cluster, void* arg,
+                               cudaStream_t st) {
+  NERF_TRY(ensure_kernel_smem(kernel, smem_optin_bytes));
+  if (cluster < 1) cluster = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((grid + cluster - 1) / cluster * cluster));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = (unsigned)cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  if (cluster > 1) {
+    static std::map<std::pair<const void*, int>, int> cache;  // (kernel, device) -> clusters resident at once
+    int dev = 0;
+    NERF_CUDA(cudaGetDevice(&dev));
+    int max_clusters = 0;
+    const int sms = device_sm_count();
+    {
+      std::lock_guard<std::mutex> lock(g_dev_mu);
+      auto it = cache.find({kernel, dev});
+      if (it == cache.end()) {
+        cudaLaunchConfig_t probe = cfg;
+        probe.gridDim = dim3((unsigned)(sms / cluster * cluster));
+        int n = 0;
+        NERF_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &probe));
+        it = cache.emplace(std::make_pair(kernel, dev), n).first;
+      }
+      max_clusters = it->second;
+    }
+    if (max_clusters < 1) { set_error("no %d-CTA cluster of this kernel fits on the device", cluster); return 100001; }
+    if ((int)cfg.gridDim.x > cluster * max_clusters) cfg.gridDim = dim3((unsigned)(cluster * max_clusters));
+  }
+  void* args[] = {arg};
+  NERF_CUDA(cudaLaunchKernelExC(&cfg, kernel, args));
+  count_launch();
+  return 0;
 }
 
 }  // namespace nerf

@@ -151,8 +151,8 @@ LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO
 # + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
 ENC_ALL = nb.FLAG_FUSED_ENCODE_TRAIN  # encoder warps in the training forward too (rendering has them by default)
 SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE),
-             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST)]
-SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast"]
+             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast"]
 
 
 @pytest.mark.parametrize("net", list(NETS))
@@ -307,14 +307,15 @@ def test_inkernel_encoding_is_bit_identical_to_the_encode_kernel(precision, R):
     assert m2.launch_count() - before - n1 >= 2 * 2  # no encode launches on the default path (2 kernels x 2 levels per chunk less)
 
 
+@pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
 @pytest.mark.parametrize("R", [700, 37, 2], ids=["R700-many-tiles", "R37-ragged", "R2-one-tile"])
-def test_weight_multicast_clusters_are_bit_identical_to_single_ctas(R):
-    """fp32-accurate fused kernels as 2-CTA clusters that share every weight stage by TMA multicast (mlp_fused_split.cu): the
+def test_weight_multicast_clusters_are_bit_identical_to_single_ctas(R, precision):
+    """The fused kernels as 2-CTA clusters that share every weight stage by TMA multicast (mlp_fused_split.cu): the
     arithmetic of a tile does not depend on which CTA walks it or on who fetched its weights, so render, loss and gradients
     must be the same bits as with one CTA per slot — with more tiles than CTAs (rings recycled many times), an odd tile count
     (a phantom tile keeps the pair's rings in lock-step) and fewer tiles than one cluster."""
-    m, ncfg, ocfg = _model(R, "fp32_tc", **NET)
-    m2, _, _ = _model(R, "fp32_tc", engine_flags=nb.FLAG_NO_WEIGHT_MULTICAST, **NET)
+    m, ncfg, ocfg = _model(R, precision, **NET)
+    m2, _, _ = _model(R, precision, engine_flags=nb.FLAG_NO_WEIGHT_MULTICAST, **NET)
     rays, pix, u = batch(R, ncfg.n_samples)
     params = _params_with_biases(ocfg)
     g1, l1 = _gradient_step(m, params, rays, pix, u)
