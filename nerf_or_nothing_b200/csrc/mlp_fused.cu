@@ -33,7 +33,7 @@ constexpr int kWStages = 6;                       // render; training gives one 
 constexpr int kWStageBytes = 128 * 128;           // [128 rows (N half) x 64 bf16]
 constexpr int kEncBytes = 2 * 16384 + 16384;      // per tile: position encoding 2 boxes of [128 x 64], direction 1 box
 constexpr int kMaxSteps = 12;
-constexpr int kStageSlot = 4096;                  // per epilogue warp: TWO [32 rows x 32 bf16] store boxes (2 KB each), used alternately
+constexpr int kStageSlot = 4096;                  // per epilogue warp: one [32 rows x 64 bf16] store box
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -63,7 +63,7 @@ struct alignas(64) FusedParams {
   int head_d_off, head_rgb_off;
   float* raw_density;   // [M]
   float* raw_rgb;       // [M, 3]
-  // training only: every step's activations [M, N] bf16 (box {32 cols, 32 rows}: one store per epilogue warp and 32-column chunk) and ReLU bit planes
+  // training only: every step's activations [M, N] bf16 (box {64, 32}, one store per epilogue warp) and ReLU bit planes
   CUtensorMap map_act[kMaxSteps];
   uint32_t* bits[kMaxSteps];
   // dgrad chain only: bits[s] is READ (ReLU mask of the step's output); step 0 adds the rank-1 term r1[row] * v1[col]
@@ -132,6 +132,13 @@ __device__ __forceinline__ uint32_t epi_chunk_any(int head_kind, const uint32_t 
   if (head_kind == 1) return epi_chunk<1, BITS>(r, bias, head_w, head, packed16);
   return epi_chunk<3, BITS>(r, bias, head_w, head, packed16);
 }
+// 16 packed words = 32 bf16 columns = half of this thread's 128-byte row of the warp's store box (128-byte swizzle)
+__device__ __forceinline__ void stage_half_row(uint8_t* row_ptr, int half, int swz, const uint32_t* pk) {
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    *reinterpret_cast<uint4*>(row_ptr + (((half * 4 + q) ^ swz) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
 // dgrad chain: one 32-column chunk of dX = dZ W (+ r1 v1^T), masked by the ReLU bits of the layer below, bf16 pairs out
 __device__ __forceinline__ void dgrad_chunk(const uint32_t (&r)[32], uint32_t mask, float r1, const float* v1, uint32_t* packed16) {
 #pragma unroll
@@ -341,7 +348,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t act = tmem_base + 256 * t + lane_off, acc = act + 128;
     uint8_t* slot = stage_buf + warp * kStageSlot;  // TRAIN: this warp's [32 x 64] bf16 store box
-    const int swz64 = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
+    uint8_t* slot_row = slot + lane * 128;
+    const int swz = lane & 7;
     uint32_t n_full = 0;
     for (int pi = 0, pair = blockIdx.x; pi < pairs_per_cta; pi++, pair += gridDim.x) {
       const int row_w = pair * 256 + t * 128 + (warp & 3) * 32;  // first row of this warp
@@ -353,23 +361,21 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
       for (int s = 0; s < p.n_steps; s++) {
         const FusedParams::Step st = p.steps[s];
         const float* head_w = s_const + (st.head == 3 ? p.head_rgb_off : p.head_d_off);
-        // TRAIN: the 32 packed columns of this thread's row go to one of the warp's two [32 x 32] store boxes (64-byte rows,
-        // 64-byte swizzle) and are shipped at once; the boxes alternate, so the TMA engine reads one while the warp fills the other
-        // (`half` = which box; a box is reused two calls later: at most ONE store may still be reading shared memory)
+        // TRAIN: 32 packed columns of this thread's row go to the warp's store box; every second call ships the box
         auto ship = [&](int col0, int half, const uint32_t* pk) {
           if (!TRAIN) return;
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          uint8_t* box = slot + half * 2048;
-          uint8_t* brow = box + lane * 64;
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-            *reinterpret_cast<uint4*>(brow + ((q ^ swz64) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&p.map_act[s], box, col0 + half * 32, row_w);
-            tma_store_commit();
+          if (half == 0) {
+            if (lane == 0) tma_store_wait_read<0>();  // the previous box of this warp has been read out
+            __syncwarp();
+          }
+          stage_half_row(slot_row, half, swz, pk);
+          if (half == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.map_act[s], slot, col0, row_w);
+              tma_store_commit();
+            }
           }
         };
         for (int h = 0; h < st.n_halves; h++) {
@@ -536,7 +542,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
     NERF_TRY(tc_make_tmap(&p.map_w[s], wplanes[s], N, kpad[s], kpad[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w64[s], wplanes[s], N, kpad[s], kpad[s], 64));
     if (train) {
-      NERF_TRY(tc_make_tmap_box(&p.map_act[s], act_out[s], M, N, N, 32, 32));
+      NERF_TRY(tc_make_tmap(&p.map_act[s], act_out[s], M, N, N, 32));
       p.bits[s] = bits_out[s];
     }
     FusedParams::Step& stp = p.steps[s];
@@ -573,7 +579,7 @@ int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, cons
   for (int s = 0; s < D; s++) {
     NERF_TRY(tc_make_tmap(&p.map_w[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w64[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 64));
-    NERF_TRY(tc_make_tmap_box(&p.map_act[s], dz_out[s], M, W, W, 32, 32));
+    NERF_TRY(tc_make_tmap(&p.map_act[s], dz_out[s], M, W, W, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     FusedParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
