@@ -77,8 +77,6 @@ typedef struct nerf_config {
                                               * instead of the encoder warps inside the fused MLP kernels */
 #define NERF_FLAG_NO_WEIGHT_MULTICAST 64u   /* fused kernels: one CTA per launch slot, every CTA streams its own weights
                                               * from L2, instead of 2-CTA clusters sharing each weight stage by TMA multicast */
-#define NERF_FLAG_DIRECT_ACT_STORES 128u    /* fused training kernels: activation / dZ planes written by 16-byte global stores straight from
-                                              * the epilogue registers instead of shared-memory boxes + TMA stores */
 #define NERF_FLAG_FUSED_ENCODE_TRAIN 32u    /* training forward: encoder warps too.  Off by default: measured on a power-capped B200
                                               * (profiles/README.md, r02b) the fused training forward loses more than the 0.3 ms encode
                                               * kernel costs, and the planes must reach HBM for the wgrad GEMMs either way */

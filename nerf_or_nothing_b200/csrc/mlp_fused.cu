@@ -65,10 +65,6 @@ struct alignas(64) FusedParams {
   float* raw_rgb;       // [M, 3]
   // training only: every step's activations [M, N] bf16 (box {64, 32}, one store per epilogue warp) and ReLU bit planes
   CUtensorMap map_act[kMaxSteps];
-  // direct_stores != 0: the epilogue threads write their 64-byte row segments of these planes themselves (four 16-byte global
-  // stores per 32 columns, whole 32-byte sectors) instead of staging a box in shared memory for a TMA store
-  __nv_bfloat16* act_ptr[kMaxSteps];
-  int direct_stores;
   uint32_t* bits[kMaxSteps];
   // dgrad chain only: bits[s] is READ (ReLU mask of the step's output); step 0 adds the rank-1 term r1[row] * v1[col]
   const float* r1;      // [M] dL/d raw_density
@@ -368,15 +364,6 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
         // TRAIN: 32 packed columns of this thread's row go to the warp's store box; every second call ships the box
         auto ship = [&](int col0, int half, const uint32_t* pk) {
           if (!TRAIN) return;
-          if (p.direct_stores) {
-            const int col = col0 + half * 32;
-            if (row_ok && col < st.n_cols) {
-              uint4* dst = reinterpret_cast<uint4*>(p.act_ptr[s] + row * st.n_cols + col);
-#pragma unroll
-              for (int q = 0; q < 4; q++) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            }
-            return;
-          }
           if (half == 0) {
             if (lane == 0) tma_store_wait_read<0>();  // the previous box of this warp has been read out
             __syncwarp();
@@ -520,7 +507,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
                              const __nv_bfloat16* const* wplanes, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                              const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                              float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_out, uint32_t* const* bits_out,
-                             const RaySource* rays, long enc_scratch_rows, bool pair, bool direct_stores, cudaStream_t st) {
+                             const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxSteps || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
@@ -556,7 +543,6 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
     NERF_TRY(tc_make_tmap(&p.map_w64[s], wplanes[s], N, kpad[s], kpad[s], 64));
     if (train) {
       NERF_TRY(tc_make_tmap(&p.map_act[s], act_out[s], M, N, N, 32));
-      p.act_ptr[s] = act_out[s];
       p.bits[s] = bits_out[s];
     }
     FusedParams::Step& stp = p.steps[s];
@@ -572,7 +558,6 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  p.direct_stores = direct_stores ? 1 : 0;
   return train ? launch_fused<1>(p, grid, kThreadsFE, smem, pair, st) : launch_fused<0>(p, grid, kThreadsFE, smem, pair, st);
 }
 
@@ -583,7 +568,7 @@ int launch_mlp_fused_forward(const __nv_bfloat16* pos, int pos_pitch, const __nv
 // mask_bits[i] is the bit plane of that layer's activations.  wt[0] = W_cond^T [W, Wc]; wt[i] = W_{D-i}^T [W, W].
 int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, const __nv_bfloat16* const* wt, const int* wt_pitch, int D, int W,
                            int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
-                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, bool pair, bool direct_stores, cudaStream_t st) {
+                           __nv_bfloat16* const* dz_out, const uint32_t* const* mask_bits, bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxSteps || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
   const size_t smem = (size_t)(kWStages - 1) * kWStageBytes + 2 * kEncBytes + 8 * kStageSlot + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
@@ -595,7 +580,6 @@ int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, cons
     NERF_TRY(tc_make_tmap(&p.map_w[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w64[s], wt[s], W, s == 0 ? Wc : W, wt_pitch[s], 64));
     NERF_TRY(tc_make_tmap(&p.map_act[s], dz_out[s], M, W, W, 32));
-    p.act_ptr[s] = dz_out[s];
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     FusedParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
@@ -607,7 +591,6 @@ int launch_mlp_fused_dgrad(const __nv_bfloat16* dz_cond, int dz_cond_pitch, cons
   }
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
-  p.direct_stores = direct_stores ? 1 : 0;
   const int pairs = (int)cdiv(M, 256);
   return launch_fused<2>(p, pairs < sms ? pairs : sms, kThreadsF, smem, pair, st);
 }

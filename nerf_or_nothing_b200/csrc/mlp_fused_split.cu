@@ -47,8 +47,6 @@ struct alignas(64) SplitParams {
   CUtensorMap map_w[kMaxStepsS][2];           // [hi, lo] weight planes [N, Kpad], box {64, 128}
   CUtensorMap map_act[kMaxStepsS][2];         // training: [hi, lo] activation planes [M, N], box {32, 32} (SWIZZLE_64B)
   uint32_t* bits[kMaxStepsS];                 // training: ReLU bit planes [M, N/32]
-  __nv_bfloat16* act_ptr[kMaxStepsS][2];      // the same planes as map_act: direct_stores != 0 -> written with 16-byte global stores
-  int direct_stores;
   struct Step {
     int16_t n_act_kb, enc_kind, n_enc_kb, n_halves;  // n_halves = ceil(N / 128): a 64-wide layer runs as one half whose upper
                                                      // 64 weight rows are the TMA's out-of-bounds zeros
@@ -348,18 +346,6 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
         // TRAIN: ship one 32-column chunk (both planes) of this warp's 32 rows
         auto ship = [&](int col, const uint32_t* hw, const uint32_t* lw) {
           if (!TRAIN) return;
-          if (p.direct_stores) {
-            if (row_ok && col < st.n_cols) {
-              uint4* dh = reinterpret_cast<uint4*>(p.act_ptr[s][0] + row * st.n_cols + col);
-              uint4* dl = reinterpret_cast<uint4*>(p.act_ptr[s][1] + row * st.n_cols + col);
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                dh[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-                dl[q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
-              }
-            }
-            return;
-          }
           if (lane == 0) tma_store_wait_read<0>();  // this warp's previous pair of boxes has been read out
           __syncwarp();
 #pragma unroll
@@ -478,7 +464,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, bool direct_stores, cudaStream_t st) {
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
@@ -517,7 +503,6 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
     if (train) {
       NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], act_hi[s], M, N, N, 32, 32));
       NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], act_lo[s], M, N, N, 32, 32));
-      p.act_ptr[s][0] = act_hi[s]; p.act_ptr[s][1] = act_lo[s];
       p.bits[s] = bits_out[s];
     }
     SplitParams::Step& stp = p.steps[s];
@@ -533,7 +518,6 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  p.direct_stores = direct_stores ? 1 : 0;
   return train ? launch_split<1>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0>(p, grid, kThreadsSE, smem, pair, st);
 }
 
@@ -544,7 +528,7 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, bool direct_stores, cudaStream_t st) {
+                                 bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
   const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
@@ -558,7 +542,6 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], dz_out_hi[s], M, W, W, 32, 32));
     NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
-    p.act_ptr[s][0] = dz_out_hi[s]; p.act_ptr[s][1] = dz_out_lo[s];
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     SplitParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
@@ -570,7 +553,6 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   }
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
-  p.direct_stores = direct_stores ? 1 : 0;
   const int tiles = (int)cdiv(M, 128);
   return launch_split<2>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
 }

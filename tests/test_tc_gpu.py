@@ -151,10 +151,8 @@ LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO
 # + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
 ENC_ALL = nb.FLAG_FUSED_ENCODE_TRAIN  # encoder warps in the training forward too (rendering has them by default)
 SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE),
-             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST),
-             ("fp32_tc", nb.FLAG_DIRECT_ACT_STORES), ("bf16", nb.FLAG_DIRECT_ACT_STORES)]
-SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast",
-             "fp32_tc-direct-stores", "bf16-direct-stores"]
+             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast"]
 
 
 @pytest.mark.parametrize("net", list(NETS))
@@ -328,22 +326,6 @@ def test_weight_multicast_clusters_are_bit_identical_to_single_ctas(R, precision
     np.testing.assert_array_equal(g1, g2)
     for a, b in zip(out1, out2):
         np.testing.assert_array_equal(a, b)
-
-
-@pytest.mark.parametrize("precision", ["fp32_tc", "bf16"])
-@pytest.mark.parametrize("net", list(NETS))
-def test_direct_activation_stores_are_bit_identical_to_tma_stores(precision, net):
-    """The training kernels can write their activation / dZ planes with 16-byte global stores from the epilogue registers
-    instead of shared-memory boxes + TMA stores: the same planes, so the same gradient bits (ragged tile included)."""
-    R = 37
-    m, ncfg, ocfg = _model(R, precision, **NETS[net])
-    m2, _, _ = _model(R, precision, engine_flags=nb.FLAG_DIRECT_ACT_STORES, **NETS[net])
-    rays, pix, u = batch(R, ncfg.n_samples)
-    params = _params_with_biases(ocfg)
-    g1, l1 = _gradient_step(m, params, rays, pix, u)
-    g2, l2 = _gradient_step(m2, params, rays, pix, u)
-    assert l1 == l2
-    np.testing.assert_array_equal(g1, g2)
 
 
 @pytest.mark.parametrize("precision,flags", SCHEDULES, ids=SCHED_IDS)
