@@ -68,7 +68,7 @@ typedef struct nerf_config {
   uint32_t engine_flags;   /* NERF_FLAG_*: A/B switches of the tensor-core engine (0 = the shipped schedule) */
 } nerf_config;
 
-/* engine_flags: bits 0-4, 6 and 7 select the slower, simpler path the default replaced, bit 5 an alternative that is not the default — parity tests compare them. */
+/* engine_flags: bits 0-4 and 6 select the slower, simpler path the default replaced, bit 5 an alternative that is not the default — parity tests compare them. */
 #define NERF_FLAG_NO_FUSED_FORWARD 1u       /* render / forward-only: one GEMM launch per layer instead of the fused kernel */
 #define NERF_FLAG_NO_FUSED_TRAIN_FORWARD 2u /* training forward: per-layer launches */
 #define NERF_FLAG_NO_FUSED_DGRAD 4u         /* backward: per-layer dgrad launches instead of the fused chain */
@@ -77,8 +77,6 @@ typedef struct nerf_config {
                                               * instead of the encoder warps inside the fused MLP kernels */
 #define NERF_FLAG_NO_WEIGHT_MULTICAST 64u   /* fused kernels: one CTA per launch slot, every CTA streams its own weights
                                               * from L2, instead of 2-CTA clusters sharing each weight stage by TMA multicast */
-#define NERF_FLAG_SMALL_STORE_BOXES 128u    /* fp32-accurate fused training kernels: one [32 x 32] TMA store box per 32-column chunk (the round-1
-                                              * epilogue) instead of one [32 x 64] box per 64 columns */
 #define NERF_FLAG_FUSED_ENCODE_TRAIN 32u    /* training forward: encoder warps too.  Off by default: measured on a power-capped B200
                                               * (profiles/README.md, r02b) the fused training forward loses more than the 0.3 ms encode
                                               * kernel costs, and the planes must reach HBM for the wgrad GEMMs either way */

@@ -102,15 +102,14 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, bool small_boxes,
-                                   cudaStream_t st);
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st);
 // pair: run as 2-CTA clusters sharing every weight stage by TMA multicast (halves the L2 weight traffic; mlp_fused_split.cu)
 
 int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfloat16* dz_cond_lo, int dz_cond_pitch,
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, bool small_boxes, cudaStream_t st);
+                                 bool pair, cudaStream_t st);
 
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]

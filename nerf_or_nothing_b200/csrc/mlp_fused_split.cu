@@ -11,7 +11,7 @@
 // A layer is two N-halves; per half and 64-wide k-block one 32 KB ring stage brings W_hi|W_lo [128 x 64] and feeds the
 // MMAs A_hi*W_hi, A_lo*W_hi, A_hi*W_lo (128x128x16 each).  The eight epilogue warps (two per TMEM lane quarter) apply
 // bias + ReLU, split into hi/lo, write both planes back into ACT in place once the layer's MMAs are complete, and
-// (training) ship them through 128-byte-swizzled [32 rows x 64 columns] boxes with their own TMA stores.  The encodings of layer 0,
+// (training) ship them through 64-byte-swizzled [32 x 32] boxes with their own TMA stores.  The encodings of layer 0,
 // the skip layer and the condition layer stream through the same ring as shared-memory A operands.
 #include <cuda.h>
 
@@ -30,9 +30,9 @@ constexpr int kThreadsS = 320;            // 8 epilogue warps + TMA producer + M
 constexpr int kEncWarpsS = 2;             // forward kernels: + 2 encoder warps (cast_rays + IPE + direction PE in-kernel)
 constexpr int kThreadsSE = kThreadsS + 32 * kEncWarpsS;
 constexpr int kEpiWarps = 8;
-constexpr int kNSInfer = 6, kNSTrain = 4;  // operand ring: 32 KB stages (a weight plane tile [<=256 x 64], or an encoding k-block's hi|lo tiles)
+constexpr int kNSInfer = 6, kNSTrain = 5;  // operand ring: 32 KB stages (a weight plane tile [<=256 x 64], or an encoding k-block's hi|lo tiles)
 constexpr int kStageB = 256 * 128;        // 32 KB
-constexpr int kSlotB = 2 * 4096;          // per epilogue warp: one [32 rows x 64 columns] hi box + one lo box (128-byte rows, SWIZZLE_128B)
+constexpr int kSlotB = 2 * 2048;          // per epilogue warp: one [32 x 32] hi box + one lo box
 constexpr int kMaxStepsS = 12;
 
 __device__ __forceinline__ uint32_t pack2s(float a, float b) {
@@ -45,9 +45,7 @@ __device__ __forceinline__ uint32_t pack2s(float a, float b) {
 struct alignas(64) SplitParams {
   CUtensorMap map_pos[2], map_dir[2];         // [hi, lo] encodings [M, 128] / [M, 64], box {64, 128}
   CUtensorMap map_w[kMaxStepsS][2];           // [hi, lo] weight planes [N, Kpad], box {64, 128}
-  CUtensorMap map_act[kMaxStepsS][2];         // training: [hi, lo] activation planes [M, N], box {64 columns, 32 rows} (SWIZZLE_128B)
-  CUtensorMap map_act32[kMaxStepsS][2];       // the same planes, box {32, 32} (SWIZZLE_64B): small_boxes != 0 ships every 32-column chunk
-  int small_boxes;                            // at once (the round-1 epilogue; A/B switch NERF_FLAG_SMALL_STORE_BOXES)
+  CUtensorMap map_act[kMaxStepsS][2];         // training: [hi, lo] activation planes [M, N], box {32, 32} (SWIZZLE_64B)
   uint32_t* bits[kMaxStepsS];                 // training: ReLU bit planes [M, N/32]
   struct Step {
     int16_t n_act_kb, enc_kind, n_enc_kb, n_halves;  // n_halves = ceil(N / 128): a 64-wide layer runs as one half whose upper
@@ -331,9 +329,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     // ------------------------------------------------------------------ epilogue: lane quarter warp % 4, column half warp / 4
     const int qtr = warp & 3, ch = warp >> 2;
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    uint8_t* slot = stage_buf + warp * kSlotB;   // TRAIN: [32 x 64] hi box + lo box: this warp's 64 columns of a half, one store each
-    uint8_t* slot_row = slot + lane * 128;
-    const int swz = lane & 7;                    // SWIZZLE_128B: 16-byte chunk index ^ (row & 7)
+    uint8_t* slot = stage_buf + warp * kSlotB;   // TRAIN: [32 x 32] hi box + lo box
+    uint8_t* slot_row = slot + lane * 64;
+    const int swz = (lane >> 1) & 3;             // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
     uint32_t n_full[2] = {0, 0};
     for (int ti = 0, tile = blockIdx.x; ti < tiles_per_cta; ti++, tile += gridDim.x) {
       const int row_w = tile * 128 + qtr * 32;
@@ -346,46 +344,21 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
         const SplitParams::Step st = p.steps[s];
         float head[3] = {0.f, 0.f, 0.f};
         // TRAIN: ship one 32-column chunk (both planes) of this warp's 32 rows
-        // `part` 0 / 1 = the first / second 32 columns of this warp's 64: the boxes are shipped when the second part is staged
-        auto ship = [&](int col, int part, const uint32_t* hw, const uint32_t* lw) {
+        auto ship = [&](int col, const uint32_t* hw, const uint32_t* lw) {
           if (!TRAIN) return;
-          if (p.small_boxes) {  // one [32 x 32] hi box + lo box per chunk, 64-byte rows
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
-            uint8_t* r64 = slot + lane * 64;
-            const int s64 = (lane >> 1) & 3;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              *reinterpret_cast<uint4*>(r64 + ((q ^ s64) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-              *reinterpret_cast<uint4*>(r64 + 4096 + ((q ^ s64) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.map_act32[s][0], slot, col, row_w);
-              tma_store_2d(&p.map_act32[s][1], slot + 4096, col, row_w);
-              tma_store_commit();
-            }
-            return;
-          }
-          if (part == 0) {
-            if (lane == 0) tma_store_wait_read<0>();  // this warp's previous pair of boxes has been read out
-            __syncwarp();
-          }
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous pair of boxes has been read out
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            const int c16 = ((part * 4 + q) ^ swz) << 4;
-            *reinterpret_cast<uint4*>(slot_row + c16) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-            *reinterpret_cast<uint4*>(slot_row + 4096 + c16) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+            *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+            *reinterpret_cast<uint4*>(slot_row + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
           }
-          if (part == 1) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.map_act[s][0], slot, col - 32, row_w);
-              tma_store_2d(&p.map_act[s][1], slot + 4096, col - 32, row_w);
-              tma_store_commit();
-            }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.map_act[s][0], slot, col, row_w);
+            tma_store_2d(&p.map_act[s][1], slot + 2048, col, row_w);
+            tma_store_commit();
           }
         };
         for (int h = 0; h < st.n_halves; h++) {
@@ -426,15 +399,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           }
           if (!last_half) {
             m0 = chunk(r0, 0, held_h, held_l);
-            ship(col_t, 0, held_h, held_l);
+            ship(col_t, held_h, held_l);
             m1 = chunk(r1, 1, held_h + 16, held_l + 16);
-            ship(col_t + 32, 1, held_h + 16, held_l + 16);
+            ship(col_t + 32, held_h + 16, held_l + 16);
           } else {
             uint32_t hw[16], lw[16];
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
             m0 = chunk(r0, 0, hw, lw);
             if (st.produces) { tmem_st_16(ACT_HI + out, hw); tmem_st_16(ACT_LO + out, lw); }
-            ship(col_t, 0, hw, lw);
+            ship(col_t, hw, lw);
             m1 = chunk(r1, 1, hw, lw);
             if (st.produces) {
               tmem_st_16(ACT_HI + out + 16, hw); tmem_st_16(ACT_LO + out + 16, lw);
@@ -446,7 +419,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
                 mbar_arrive(&act_ready);
               }
             }
-            ship(col_t + 32, 1, hw, lw);
+            ship(col_t + 32, hw, lw);
           }
           if (MODE == 1 && row_ok && col_t < st.n_cols) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)) = make_uint2(m0, m1);
         }
@@ -491,7 +464,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, bool small_boxes, cudaStream_t st) {
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
@@ -528,10 +501,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], w_hi[s], N, kpad[s], kpad[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], w_lo[s], N, kpad[s], kpad[s], 128));
     if (train) {
-      NERF_TRY(tc_make_tmap(&p.map_act[s][0], act_hi[s], M, N, N, 32));
-      NERF_TRY(tc_make_tmap(&p.map_act[s][1], act_lo[s], M, N, N, 32));
-      NERF_TRY(tc_make_tmap_box(&p.map_act32[s][0], act_hi[s], M, N, N, 32, 32));
-      NERF_TRY(tc_make_tmap_box(&p.map_act32[s][1], act_lo[s], M, N, N, 32, 32));
+      NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], act_hi[s], M, N, N, 32, 32));
+      NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], act_lo[s], M, N, N, 32, 32));
       p.bits[s] = bits_out[s];
     }
     SplitParams::Step& stp = p.steps[s];
@@ -547,7 +518,6 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  p.small_boxes = small_boxes ? 1 : 0;
   return train ? launch_split<1>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0>(p, grid, kThreadsSE, smem, pair, st);
 }
 
@@ -558,7 +528,7 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, bool small_boxes, cudaStream_t st) {
+                                 bool pair, cudaStream_t st) {
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
   const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
@@ -570,10 +540,8 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   for (int s = 0; s < D; s++) {
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], wt_hi[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
-    NERF_TRY(tc_make_tmap(&p.map_act[s][0], dz_out_hi[s], M, W, W, 32));
-    NERF_TRY(tc_make_tmap(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32));
-    NERF_TRY(tc_make_tmap_box(&p.map_act32[s][0], dz_out_hi[s], M, W, W, 32, 32));
-    NERF_TRY(tc_make_tmap_box(&p.map_act32[s][1], dz_out_lo[s], M, W, W, 32, 32));
+    NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], dz_out_hi[s], M, W, W, 32, 32));
+    NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     SplitParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
@@ -585,7 +553,6 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   }
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
-  p.small_boxes = small_boxes ? 1 : 0;
   const int tiles = (int)cdiv(M, 128);
   return launch_split<2>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
 }

@@ -151,8 +151,8 @@ LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO
 # + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
 ENC_ALL = nb.FLAG_FUSED_ENCODE_TRAIN  # encoder warps in the training forward too (rendering has them by default)
 SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE),
-             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST), ("fp32_tc", nb.FLAG_SMALL_STORE_BOXES)]
-SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast", "fp32_tc-small-store-boxes"]
+             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast"]
 
 
 @pytest.mark.parametrize("net", list(NETS))
