@@ -165,7 +165,7 @@ double orc_ssim(const float* a, const float* b, int W, int H, float max_val, int
       fsum += filt[i * fs + j];
     }
   for (int i = 0; i < fs * fs; i++) filt[i] /= fsum;
-  float *mu0 = malloc(n * 4), *mu1 = malloc(n * 4), *s00 = malloc(n * 4), *s11 = malloc(n * 4), *s01 = malloc(n * 4), *tmp = malloc(n * 4);
+  float *mu0 = malloc(n * 4), *mu1 = malloc(n * 4), *s00 = malloc(n * 4), *s11 = malloc(n * 4), *s01 = malloc(n * 4), *tmp = calloc(n, 4);
   orc_convolve_(a, W, H, filt, fs, mu0);
   orc_convolve_(b, W, H, filt, fs, mu1);
   for (size_t i = 0; i < n; i++) tmp[i] = a[i] * a[i];
