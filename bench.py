@@ -463,6 +463,14 @@ def measure_render(job, args, precision, steps=None):
     w0 = time.perf_counter()
     model.render(*hb)
     ms_e2e = job.max_over_ranks((time.perf_counter() - w0) * 1e3)
+    # the same pixels rendered straight from the camera pose: rays generated on the device (Dataset.GenerateRays), image to the host
+    from nerf_or_nothing_b200.scene import view_pose
+
+    c2w, focal = view_pose(0, width=800)
+    model.render_view(c2w, focal, 800, 800, first_pixel=lo, n_pixels=n)
+    w0 = time.perf_counter()
+    model.render_view(c2w, focal, 800, 800, first_pixel=lo, n_pixels=n)
+    ms_pose = job.max_over_ranks((time.perf_counter() - w0) * 1e3)
     clk = job.clocks.window(t0, t1)
     hbm_peak, tc_peak, peak_src = peaks()
     work, _ = algorithmic_work(n, N_SAMPLES)
@@ -474,6 +482,8 @@ def measure_render(job, args, precision, steps=None):
     return {"value": total / (ms / 1e3), "unit": UNIT, "ms_per_image": ms, "steps": steps, "precision": precision, "rays": total,
             "rays_per_gpu": n, "chunk_rays": chunk, "gpu_launches": int(launches), "clocks": clk,
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n * 5 * 4},
+            "from_pose": {"value": total / (ms_pose / 1e3), "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n * 5 * 4,
+                          "note": "nerf_mipnerf_render_view: the view's rays generated on the device from its 3x4 pose"},
             "roofline": {"kernel": "mlp_fwd_gemm", "bound": "tensor", "achieved": None if ach is None else round(ach, 2), "peak": tc_peak,
                          "unit": "TFLOP/s", "frac": None if ach is None else round(ach / tc_peak, 4), "traffic": None, "peak_source": peak_src,
                          "share_of_step": round(fwd_ms / ms, 4) if ms else None},
@@ -622,7 +632,8 @@ def render_arm(args):
               "config": {"workload": "configs[3]: full-image 800x800 render (640000 rays, 128+128 samples), forward only, rays split "
                                      f"across {job.world} GPU(s)", "rays_per_gpu": r["rays_per_gpu"], "chunk_rays": r["chunk_rays"],
                          "precision": args.precision, "l2": "per-chunk working set (>1 GB of encodings / heads) exceeds the 126 MB L2; no flush needed"},
-              "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "roofline": r["roofline"], "kernels": r["kernels"]})
+              "e2e": r["e2e"], "from_pose": r["from_pose"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "roofline": r["roofline"],
+              "kernels": r["kernels"]})
     job.close()
 
 

@@ -10,6 +10,22 @@ from __future__ import annotations
 
 import numpy as np
 
+def view_pose(view=0, width=800, n_views=8, scene_seed=1234):
+    """(c2w [3,4] float32 row-major [R | t], focal) of camera `view` of the synthetic scene: what
+    `nerf_mipnerf_render_view` takes to render that view with the rays generated on the device."""
+    rng = np.random.default_rng(scene_seed)
+    focal = 0.5 * width / np.tan(0.5 * 0.6911112070083618)
+    th = rng.uniform(0, 2 * np.pi, n_views)
+    ph = rng.uniform(0.15 * np.pi, 0.5 * np.pi, n_views)
+    cam = 4.0 * np.stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)], -1)[view]
+    fwd = -cam / np.linalg.norm(cam)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0]))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    c2w = np.concatenate([np.stack([right, upv, -fwd], -1), cam[:, None]], 1)
+    return c2w.astype(np.float32), float(focal)
+
+
 def synthetic_rays(n_rays, width=800, height=800, n_views=8, seed=2024, scene_seed=1234, near=2.0, far=6.0):
     """Blender-style synthetic batch: pinhole cameras on a radius-4 sphere looking at the origin,
     ray formulas of SN/Dataset.cs:111-176, analytic blob colours in [0,1], white background.
