@@ -68,7 +68,7 @@ typedef struct nerf_config {
   uint32_t engine_flags;   /* NERF_FLAG_*: A/B switches of the tensor-core engine (0 = the shipped schedule) */
 } nerf_config;
 
-/* engine_flags: bits 0-4 and 6 select the slower, simpler path the default replaced, bit 5 an alternative that is not the default — parity tests compare them. */
+/* engine_flags: bits 0-4 and 6 select the slower, simpler path the default replaced, bits 5 and 7 alternatives that are not the default — parity tests compare them. */
 #define NERF_FLAG_NO_FUSED_FORWARD 1u       /* render / forward-only: one GEMM launch per layer instead of the fused kernel */
 #define NERF_FLAG_NO_FUSED_TRAIN_FORWARD 2u /* training forward: per-layer launches */
 #define NERF_FLAG_NO_FUSED_DGRAD 4u         /* backward: per-layer dgrad launches instead of the fused chain */
@@ -80,6 +80,13 @@ typedef struct nerf_config {
 #define NERF_FLAG_FUSED_ENCODE_TRAIN 32u    /* training forward: encoder warps too.  Off by default: measured on a power-capped B200
                                               * (profiles/README.md, r02b) the fused training forward loses more than the 0.3 ms encode
                                               * kernel costs, and the planes must reach HBM for the wgrad GEMMs either way */
+
+#define NERF_FLAG_WGRAD_FP16 128u           /* fp32-accurate mode, opt-in: the wgrad operands (activations, encodings, dZ times a per-level
+                                              * power of two) leave the fused kernels as ONE fp16 plane each instead of hi + lo bf16 planes,
+                                              * and the wgrad GEMMs run one fp16 MMA per product instead of three bf16 ones: half the HBM
+                                              * traffic of the backward pass.  Forward, dgrad chain and everything per-ray are unchanged.
+                                              * Gradient accuracy: ~1e-5 of the gradient's scale on a real step (sums over ~5e5 samples),
+                                              * up to ~1e-3 on sums that cancel like a random walk — outside the mode's 1e-4, so not the default */
 
 typedef struct nerf_mipnerf nerf_mipnerf;   /* AcceleratedMipNeRF + its embedded AcceleratedMLP */
 typedef struct nerf_adam nerf_adam;         /* AcceleratedAdamOptimizer */

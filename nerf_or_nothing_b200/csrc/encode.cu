@@ -6,6 +6,8 @@
 // block stages a [32 samples x 6*deg] tile in shared memory and streams it out with 128-bit stores.
 // The fused kernel goes straight from t-values to encodings and can emit the bf16 hi/lo planes the
 // tcgen05 MLP consumes, so mean/cov never touch HBM.
+#include <cuda_fp16.h>
+
 #include "encode_rows.cuh"
 #include "kernels.cuh"
 
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(kTileSamples * kFreqLanes)
 k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ o,
              const float* __restrict__ d, const float* __restrict__ radii, long M, int S, int deg,
              float* __restrict__ enc_f32, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-             int pitch_h) {
+             int pitch_h, __half* __restrict__ h16) {
   extern __shared__ float tile[];  // [kTileSamples][P]
   __shared__ Gauss gs[kTileSamples];
   const int P = 6 * deg;
@@ -98,6 +100,7 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
         if (lo)
           *reinterpret_cast<__nv_bfloat162*>(lo + off0 + col) =
               __nv_bfloat162(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+        if (h16) *reinterpret_cast<__half2*>(h16 + off0 + col) = __floats2half2_rn(a, b);
       }
     }
   }
@@ -108,9 +111,10 @@ k_encode_pos(const float* __restrict__ in0, const float* __restrict__ in1, const
 // and/or the zero-padded bf16 hi/lo rows), then replicated to the ray's S sample rows with 16-byte stores.
 __global__ void __launch_bounds__(128)
 k_encode_dir(const float* __restrict__ d, int R, int S, int deg, float* __restrict__ f32, int pitch_f,
-             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int pitch_h) {
+             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int pitch_h, __half* __restrict__ h16) {
   __shared__ __align__(16) float row_f[64];
   __shared__ __align__(16) __nv_bfloat16 row_h[64], row_l[64];
+  __shared__ __align__(16) __half row_16[64];
   const int r = blockIdx.x;
   const int Dd = 3 + 6 * deg;
   if (threadIdx.x < 64) {
@@ -126,6 +130,7 @@ k_encode_dir(const float* __restrict__ d, int R, int S, int deg, float* __restri
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     row_h[c] = h;
     row_l[c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    row_16[c] = __float2half_rn(v);
   }
   __syncthreads();
   const long m0 = (long)r * S;
@@ -143,6 +148,7 @@ k_encode_dir(const float* __restrict__ d, int R, int S, int deg, float* __restri
       const uint4 vh = c < 8 ? reinterpret_cast<const uint4*>(row_h)[c] : z;
       reinterpret_cast<uint4*>(hi + (m0 + s) * pitch_h)[c] = vh;
       if (lo) reinterpret_cast<uint4*>(lo + (m0 + s) * pitch_h)[c] = c < 8 ? reinterpret_cast<const uint4*>(row_l)[c] : z;
+      if (h16) reinterpret_cast<uint4*>(h16 + (m0 + s) * pitch_h)[c] = c < 8 ? reinterpret_cast<const uint4*>(row_16)[c] : z;
     }
   }
 }
@@ -162,11 +168,11 @@ int launch_encode_input_data(const float* means, const float* covs, const float*
   const long M = (long)R * S;
   const size_t smem = (size_t)kTileSamples * 6 * deg_point * sizeof(float);
   k_encode_pos<false><<<(unsigned)cdiv(M, kTileSamples), kTileSamples * kFreqLanes, smem, st>>>(
-      means, covs, nullptr, nullptr, nullptr, M, S, deg_point, enc_pos, nullptr, nullptr, 0);
+      means, covs, nullptr, nullptr, nullptr, M, S, deg_point, enc_pos, nullptr, nullptr, 0, nullptr);
   NERF_CHECK_LAUNCH();
   if (enc_dir) {
     if (3 + 6 * deg_view > 64) { set_error("encode: deg_view too large"); return 100001; }
-    k_encode_dir<<<(unsigned)R, 128, 0, st>>>(dirs, R, S, deg_view, enc_dir, 3 + 6 * deg_view, nullptr, nullptr, 0);
+    k_encode_dir<<<(unsigned)R, 128, 0, st>>>(dirs, R, S, deg_view, enc_dir, 3 + 6 * deg_view, nullptr, nullptr, 0, nullptr);
     NERF_CHECK_LAUNCH();
   }
   return 0;
@@ -177,12 +183,12 @@ int launch_cast_encode_fused(const float* t, const float* o, const float* d, con
   const long M = (long)R * S;
   const size_t smem = (size_t)kTileSamples * 6 * deg_point * sizeof(float);
   k_encode_pos<true><<<(unsigned)cdiv(M, kTileSamples), kTileSamples * kFreqLanes, smem, st>>>(
-      t, nullptr, o, d, radii, M, S, deg_point, out.enc_pos_f32, out.pos_hi, out.pos_lo, out.pos_pitch_h);
+      t, nullptr, o, d, radii, M, S, deg_point, out.enc_pos_f32, out.pos_hi, out.pos_lo, out.pos_pitch_h, static_cast<__half*>(out.pos_f16));
   NERF_CHECK_LAUNCH();
   if (out.enc_dir_f32 || out.dir_hi) {
     if (3 + 6 * deg_view > 64) { set_error("encode: deg_view too large"); return 100001; }
     k_encode_dir<<<(unsigned)R, 128, 0, st>>>(d, R, S, deg_view, out.enc_dir_f32, out.dir_pitch_f32, out.dir_hi, out.dir_lo,
-                                              out.dir_pitch_h);
+                                              out.dir_pitch_h, static_cast<__half*>(out.dir_f16));
     NERF_CHECK_LAUNCH();
   }
   return 0;

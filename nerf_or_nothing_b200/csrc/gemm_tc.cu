@@ -15,6 +15,7 @@
 // fp32-accurate mode (NERF_PRECISION_FP32_TC): x = hi + lo with hi = bf16(x), lo = bf16(x - hi); the product keeps
 // hi*hi + hi*lo + lo*hi (error ~2^-17 per product), expressed as three k-blocks per K slice.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -45,6 +46,7 @@ __device__ __forceinline__ void f4_add(float4& s, const float4 v) { s.x += v.x; 
 __device__ __forceinline__ void reduce_job_slot(const ReduceJob& j, long idx) {
   const int c4 = (j.cols + 3) >> 2;
   const long n1 = (long)j.rows * c4;
+  const float mul = j.mul ? __ldg(j.mul) : 1.0f;  // a power of two: exact
   if (idx < n1) {
     const int i = (int)(idx / c4), c = (int)(idx % c4) * 4;
     const float* src = j.ws + (long)i * j.ldw + c;
@@ -61,10 +63,10 @@ __device__ __forceinline__ void reduce_job_slot(const ReduceJob& j, long idx) {
     if (z + 1 < j.splits) f4_add(s1, __ldg(reinterpret_cast<const float4*>(src + (long)(z + 1) * j.stride)));
     if (z + 2 < j.splits) f4_add(s2, __ldg(reinterpret_cast<const float4*>(src + (long)(z + 2) * j.stride)));
     float* o = j.out + (long)i * j.ldo + j.coff + c;
-    o[0] += (s0.x + s1.x) + (s2.x + s3.x);
-    if (c + 1 < j.cols) o[1] += (s0.y + s1.y) + (s2.y + s3.y);
-    if (c + 2 < j.cols) o[2] += (s0.z + s1.z) + (s2.z + s3.z);
-    if (c + 3 < j.cols) o[3] += (s0.w + s1.w) + (s2.w + s3.w);
+    o[0] += ((s0.x + s1.x) + (s2.x + s3.x)) * mul;
+    if (c + 1 < j.cols) o[1] += ((s0.y + s1.y) + (s2.y + s3.y)) * mul;
+    if (c + 2 < j.cols) o[2] += ((s0.z + s1.z) + (s2.z + s3.z)) * mul;
+    if (c + 3 < j.cols) o[3] += ((s0.w + s1.w) + (s2.w + s3.w)) * mul;
   } else if (idx - n1 < j.n2) {
     const int jb = (int)(idx - n1);
     const float* src = j.ws2 + jb;
@@ -77,7 +79,7 @@ __device__ __forceinline__ void reduce_job_slot(const ReduceJob& j, long idx) {
     if (z < j.splits) s0 += src[(long)z * j.stride2];
     if (z + 1 < j.splits) s1 += src[(long)(z + 1) * j.stride2];
     if (z + 2 < j.splits) s2 += src[(long)(z + 2) * j.stride2];
-    j.out2[jb] += (s0 + s1) + (s2 + s3);
+    j.out2[jb] += ((s0 + s1) + (s2 + s3)) * mul;
   }
 }
 
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(128) k_reduce_job(const ReduceJob j) {
 //                                 + an N=16 MMA of the same dZ tile against a constant tile of ones: TMEM columns
 //                                 256..271 accumulate colsum(dZ) = the bias gradient for free
 //   warps 0-3      epilogue       tcgen05.ld -> fp32 partial tile [split][row][col] (+ bias column)
+// p.f16_ops: the planes hold fp16 (the fp32-accurate mode's wgrad operands, see mlp_tc.cu) — same tiles, same descriptors,
+// only the instruction descriptor's operand formats and the tile of ones differ.
 // One CTA per SM (192 KB ring, 512 TMEM columns); the kernel runs at the HBM roofline of reading dZ and X once.
 __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 2048; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  for (int i = threadIdx.x; i < 2048; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = p.f16_ops ? 0x3C003C00u : 0x3F803F80u;  // 1.0
   fence_proxy_async();
   if (warp == 4) {
     tmem_alloc<512>(&tmem_base_smem);
@@ -155,8 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const __grid_constant_
   } else if (warp == 5) {
     {  // ---------------------------------------------------------------- MMA issuer (uniform warp, one elected lane issues)
       const bool leader = elect_one();
-      const uint32_t idesc = make_idesc_bf16(128, BN, true, true);
-      const uint32_t idesc_bias = make_idesc_bf16(128, 16, true, true);
+      const uint32_t idesc = p.f16_ops ? make_idesc_f16(128, BN, true, true) : make_idesc_bf16(128, BN, true, true);
+      const uint32_t idesc_bias = p.f16_ops ? make_idesc_f16(128, 16, true, true) : make_idesc_bf16(128, 16, true, true);
       const uint64_t desc0 = make_smem_desc(0, 8192, 1024);  // + (shared address >> 4)
       const uint32_t ones_base = smem_u32(ones), smem_base = smem_u32(smem);
       for (int i = 0; i < n_kb; i++) {
@@ -534,7 +538,9 @@ k_thin_fwd_planes(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __r
 template <int NN>
 __global__ void __launch_bounds__(256)
 k_thin_dgrad_planes(const float* __restrict__ dZ, const float* __restrict__ W, long M, int K, const uint32_t* __restrict__ mask_bits,
-                    int ld_bits, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int ldo) {
+                    int ld_bits, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, int ldo, __half* __restrict__ o16,
+                    const float* __restrict__ scale16) {
+  const float s16 = o16 ? __ldg(scale16) : 1.0f;  // o16: a third plane fp16(dX * s16) for the fp16 wgrad GEMMs
   const int k8 = K >> 3;                      // chunks per row (blockDim.x is a multiple of it)
   const int k = (threadIdx.x % k8) * 8;
   const int rows_per_block = blockDim.x / k8;
@@ -559,6 +565,9 @@ k_thin_dgrad_planes(const float* __restrict__ dZ, const float* __restrict__ W, l
     }
     *reinterpret_cast<uint4*>(oh + m * ldo + k) =
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    if (o16)
+      *reinterpret_cast<uint4*>(o16 + m * ldo + k) = make_uint4(pack_f16x2_sat(v[0] * s16, v[1] * s16), pack_f16x2_sat(v[2] * s16, v[3] * s16),
+                                                                pack_f16x2_sat(v[4] * s16, v[5] * s16), pack_f16x2_sat(v[6] * s16, v[7] * s16));
     if (ol) {
 #pragma unroll
       for (int j = 0; j < 8; j++) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
@@ -572,7 +581,8 @@ k_thin_dgrad_planes(const float* __restrict__ dZ, const float* __restrict__ W, l
 // columns (16-byte plane loads); a warp covers 32 / (K/8) rows per load instruction (two rows when K = 128), 4 loads in
 // flight; row groups and the 8 warps are then summed through shuffles / shared memory.  part[block][n*K + k],
 // partb[block][n].   K <= 256, K a multiple of 8.  NN = compile-time head width (1 or 3): no FMAs on absent heads.
-template <int NN>
+// F16: xh is ONE fp16 plane (xl unused).
+template <int NN, bool F16>
 __global__ void __launch_bounds__(256)
 k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int ldx,
                             const float* __restrict__ dZ, long M, int N, int K, long chunk, float* __restrict__ part,
@@ -602,7 +612,7 @@ k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
       const long mm = m + (long)step * u;
       const bool ok = mm < m1;
       h[u] = (ok && active) ? __ldg(reinterpret_cast<const uint4*>(xh + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
-      l[u] = (ok && active && xl) ? __ldg(reinterpret_cast<const uint4*>(xl + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
+      l[u] = (!F16 && ok && active && xl) ? __ldg(reinterpret_cast<const uint4*>(xl + mm * ldx + k)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int n = 0; n < NN; n++) g[u][n] = ok ? __ldg(dZ + mm * NN + n) : 0.f;
     }
@@ -612,8 +622,13 @@ k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
       float x[8];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        x[2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-        x[2 * q + 1] = __uint_as_float(hw[q] & 0xFFFF0000u) + __uint_as_float(lw[q] & 0xFFFF0000u);
+        if (F16) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+          x[2 * q] = f.x; x[2 * q + 1] = f.y;
+        } else {
+          x[2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+          x[2 * q + 1] = __uint_as_float(hw[q] & 0xFFFF0000u) + __uint_as_float(lw[q] & 0xFFFF0000u);
+        }
       }
 #pragma unroll
       for (int n = 0; n < NN; n++) {
@@ -967,17 +982,19 @@ int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int
 }
 
 int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const uint32_t* mask_bits, int ld_bits,
-                             __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st) {
+                             __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st, void* o16v, const float* scale16) {
+  __half* o16 = static_cast<__half*>(o16v);
+  if (o16 && !scale16) { set_error("thin_dgrad_planes: the fp16 plane needs its scale"); return 100001; }
   if (K % 8 || K > 2048 || N < 1 || N > 4 || ((uintptr_t)W & 15)) { set_error("thin_dgrad_planes: N=%d K=%d / W alignment", N, K); return 100001; }
   const int rows_per_block = 256 / (K / 8);
   const unsigned threads = (unsigned)(rows_per_block * (K / 8));  // whole rows per block
   long blocks = cdiv(M, rows_per_block);
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride over the rows: the weights are loaded once per thread
   switch (N) {
-    case 1: k_thin_dgrad_planes<1><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
-    case 2: k_thin_dgrad_planes<2><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
-    case 3: k_thin_dgrad_planes<3><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
-    default: k_thin_dgrad_planes<4><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo); break;
+    case 1: k_thin_dgrad_planes<1><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo, o16, scale16); break;
+    case 2: k_thin_dgrad_planes<2><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo, o16, scale16); break;
+    case 3: k_thin_dgrad_planes<3><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo, o16, scale16); break;
+    default: k_thin_dgrad_planes<4><<<(unsigned)blocks, threads, 0, st>>>(dZ, W, M, K, mask_bits, ld_bits, oh, ol, ldo, o16, scale16); break;
   }
   NERF_CHECK_LAUNCH();
   return 0;
@@ -1017,7 +1034,7 @@ long thin_wgrad_chunk(long M) {  // ~4 blocks per SM, at least 256 rows each
 }
 
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
-                             long M, int N, int K, float* workspace, cudaStream_t st) {
+                             long M, int N, int K, float* workspace, cudaStream_t st, bool x_f16) {
   if (N > 4) { set_error("thin_wgrad_planes: N=%d", N); return 100001; }
   if (N > 3 || K % 8) { set_error("thin_wgrad_planes: N=%d K=%d unsupported", N, K); return 100001; }
   const long chunk = thin_wgrad_chunk(M);
@@ -1026,12 +1043,88 @@ int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __n
   float* partb = workspace + (size_t)chunks * N * 256;
   for (int k0 = 0; k0 < K; k0 += 256) {  // the kernel covers 256 columns (8 per lane) per pass
     const int kp = K - k0 < 256 ? K - k0 : 256;
-    if (N == 1) k_thin_wgrad_planes_partial<1><<<chunks, 256, 0, st>>>(xh + k0, xl ? xl + k0 : nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
-    else if (N == 3) k_thin_wgrad_planes_partial<3><<<chunks, 256, 0, st>>>(xh + k0, xl ? xl + k0 : nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    const __nv_bfloat16* xlk = xl ? xl + k0 : nullptr;
+    if (N == 1 && x_f16) k_thin_wgrad_planes_partial<1, true><<<chunks, 256, 0, st>>>(xh + k0, nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    else if (N == 3 && x_f16) k_thin_wgrad_planes_partial<3, true><<<chunks, 256, 0, st>>>(xh + k0, nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
+    else if (N == 1) k_thin_wgrad_planes_partial<1, false><<<chunks, 256, 0, st>>>(xh + k0, xlk, ldx, dZ, M, N, kp, chunk, part, partb);
+    else if (N == 3) k_thin_wgrad_planes_partial<3, false><<<chunks, 256, 0, st>>>(xh + k0, xlk, ldx, dZ, M, N, kp, chunk, part, partb);
     else { set_error("thin_wgrad_planes: N=%d unsupported", N); return 100001; }
     NERF_CHECK_LAUNCH();
     NERF_TRY(launch_reduce_partials2(part, chunks, (long)N * kp, N, kp, kp, dW, K, k0, (db && k0 == 0) ? partb : nullptr, N, N, db, st));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------- fp16 operand planes of the fp32-accurate mode's wgrad
+namespace {
+
+// max |x| over the head gradients of a level -> the power-of-two scale of its fp16 dZ planes.  Non-negative floats order like
+// their bit patterns, so the block maxima meet in one atomicMax; the last block (ticket) turns the maximum into
+// s = 2^-floor(log2 max), 1/s and re-zeroes the scratch for the next launch.
+__global__ void __launch_bounds__(256) k_dz_scale(const float* __restrict__ a, long na, const float* __restrict__ b, long nb,
+                                                  float* __restrict__ out, unsigned* __restrict__ scratch) {
+  __shared__ unsigned red[8];
+  unsigned m = 0u;
+  const long stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long na4 = na >> 2, nb4 = nb >> 2;
+  for (long i = t0; i < na4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a) + i);
+    m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+  }
+  for (long i = na4 * 4 + t0; i < na; i += stride) m = max(m, __float_as_uint(fabsf(a[i])));
+  for (long i = t0; i < nb4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(b) + i);
+    m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+  }
+  for (long i = nb4 * 4 + t0; i < nb; i += stride) m = max(m, __float_as_uint(fabsf(b[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; w++) m = max(m, red[w]);
+    atomicMax(&scratch[0], m);
+    __threadfence();
+    if (atomicAdd(&scratch[1], 1u) == gridDim.x - 1) {  // last block: every maximum has arrived
+      __threadfence();
+      const unsigned mx = atomicExch(&scratch[0], 0u);
+      scratch[1] = 0u;
+      unsigned e = (mx >> 23) & 0xFFu;  // biased exponent of the maximum; 0 (all zero / subnormal) and inf / nan: no scaling
+      if (e == 0u || e == 255u) e = 127u;
+      if (e > 253u) e = 253u;
+      out[0] = __uint_as_float((254u - e) << 23);  // 2^(127 - e)
+      out[1] = __uint_as_float(e << 23);           // 2^(e - 127)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_f32_to_f16_plane(const float* __restrict__ src, int sp, long rows, int cols, __half* __restrict__ dst,
+                                                          int dp, int dcols) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * dcols) return;
+  const long r = idx / dcols;
+  const int c = (int)(idx % dcols);
+  dst[r * dp + c] = __float2half_rn(c < cols ? src[r * sp + c] : 0.f);
+}
+
+}  // namespace
+
+int launch_dz_scale(const float* d_raw_rgb, const float* d_raw_density, long M, float* out, unsigned* scratch, cudaStream_t st) {
+  if (((uintptr_t)d_raw_rgb | (uintptr_t)d_raw_density) & 15) { set_error("dz_scale: head gradients must be 16-byte aligned"); return 100001; }
+  long blocks = cdiv(M, 256 * 4);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  k_dz_scale<<<(unsigned)blocks, 256, 0, st>>>(d_raw_rgb, 3 * M, d_raw_density, M, out, scratch);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_f32_to_f16_plane(const float* src, int src_pitch, long rows, int cols, void* dst, int dst_pitch, int dst_cols, cudaStream_t st) {
+  const long n = rows * dst_cols;
+  if (n <= 0) return 0;
+  k_f32_to_f16_plane<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(src, src_pitch, rows, cols, static_cast<__half*>(dst), dst_pitch, dst_cols);
+  NERF_CHECK_LAUNCH();
   return 0;
 }
 

@@ -23,6 +23,7 @@ struct ReduceJob {
   float* out2;
   long stride, stride2;
   int splits, rows, cols, ldw, ldo, coff, n2;
+  const float* mul;  // optional device scalar: the sums are multiplied by *mul (the power-of-two un-scaling of fp16 dZ planes)
 };
 
 struct alignas(64) TcParams {
@@ -33,6 +34,7 @@ struct alignas(64) TcParams {
   // ---- MN-major mode (wgrad): grid = (out_rows/128, ceil(out_cols/BN), splits); reduction over the rows of the planes
   int n_pass;
   int8_t pass_a[4], pass_b[4];
+  int f16_ops;     // MN-major: the planes hold fp16 (one pass), not bf16
   int a_col0;      // column of the A plane where this launch's output rows start (usually 0)
   int split_len;   // reduction rows per split (multiple of 64)
   long red_len;    // total reduction length (rows of the planes = samples)
@@ -102,14 +104,17 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st);
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st,
+                                   bool act_f16 = false);
+// act_f16 (training): act_hi[s] is ONE fp16 plane per layer (act_lo unused) — the X operands of the fp16 wgrad GEMMs
 // pair: run as 2-CTA clusters sharing every weight stage by TMA multicast (halves the L2 weight traffic; mlp_fused_split.cu)
 
 int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfloat16* dz_cond_lo, int dz_cond_pitch,
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, cudaStream_t st);
+                                 bool pair, cudaStream_t st, const float* dz_scale_f16 = nullptr);
+// dz_scale_f16 != nullptr: dz_out_hi[s] is ONE fp16 plane that receives dZ * *dz_scale_f16 (device scalar, launch_dz_scale)
 
 // helpers on bf16 planes ------------------------------------------------------------------------------
 // fp32 [rows, cols] (pitch src_pitch) -> hi/lo planes (pitch dst_pitch, zero padded); transpose writes dst[c, r]
@@ -133,10 +138,18 @@ int launch_gather_f32(const float* src, float* dst, const GatherJobs& jobs, cuda
 // heads on planes (N <= 4)
 int launch_thin_fwd_planes(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, const float* W, const float* b,
                            float* Y, long M, int N, int K, cudaStream_t st);
+// o16 (optional): a third output plane fp16(dX * *scale16), same pitch — the dZ operand of the fp16 wgrad GEMMs
 int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int K, const uint32_t* mask_bits, int ld_bits,
-                             __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st);
+                             __nv_bfloat16* oh, __nv_bfloat16* ol, int ldo, cudaStream_t st, void* o16 = nullptr,
+                             const float* scale16 = nullptr);
+// x_f16: xh is one fp16 plane (xl ignored)
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
-                             long M, int N, int K, float* workspace, cudaStream_t st);
+                             long M, int N, int K, float* workspace, cudaStream_t st, bool x_f16 = false);
+// Device scalars for the fp16 dZ planes of one level: out[0] = s = 2^-floor(log2(max |d_raw|)) (so that the largest head gradient
+// lands in [1, 2)), out[1] = 1 / s.  scratch: 2 zero-initialised words (left zeroed).  One launch, no host round trip.
+int launch_dz_scale(const float* d_raw_rgb, const float* d_raw_density, long M, float* out, unsigned* scratch, cudaStream_t st);
+// fp32 [rows, cols] (pitch src_pitch) -> one fp16 plane (pitch dst_pitch, zero padded up to dst_cols)
+int launch_f32_to_f16_plane(const float* src, int src_pitch, long rows, int cols, void* dst, int dst_pitch, int dst_cols, cudaStream_t st);
 // db[n] += sum_m (hi + lo)[m, n]
 int launch_colsum_planes(const __nv_bfloat16* h, const __nv_bfloat16* l, int ld, long M, int N, float* db, float* workspace,
                          cudaStream_t st);

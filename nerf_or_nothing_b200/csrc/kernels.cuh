@@ -34,6 +34,8 @@ struct EncodeOut {
   int dir_pitch_f32 = 0;
   __nv_bfloat16 *pos_hi = nullptr, *pos_lo = nullptr, *dir_hi = nullptr, *dir_lo = nullptr;
   int pos_pitch_h = 0, dir_pitch_h = 0;
+  // optional third planes, fp16, same pitches: the X operands of the fp32-accurate mode's fp16 wgrad GEMMs (mlp_tc.cu)
+  void *pos_f16 = nullptr, *dir_f16 = nullptr;
 };
 int launch_cast_encode_fused(const float* t, const float* o, const float* d, const float* radii, int R, int S,
                              int deg_point, int deg_view, EncodeOut out, cudaStream_t st);

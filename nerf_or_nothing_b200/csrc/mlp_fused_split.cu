@@ -61,6 +61,9 @@ struct alignas(64) SplitParams {
   float* raw_density;
   float* raw_rgb;
   const float* r1;  // dgrad chain: [M] dL/d raw_density (rank-1 term of step 0); bits[] are then READ as ReLU masks
+  // F16 kernels (the wgrad GEMMs multiply fp16 planes, see mlp_tc.cu): map_act[s][0] views ONE fp16 plane per layer; the dgrad
+  // chain stores fp16(dZ * *dz_scale), a power of two chosen per level from the head gradients (launch_dz_scale)
+  const float* dz_scale;
   // forward only — in-kernel cast_rays + IPE + direction PE (see FusedParams::enc_mode in mlp_fused.cu): 0 = planes written by
   // another kernel, 1 = the encoder warps write the level's hi/lo planes, 2 = a per-CTA double-buffered scratch (128 rows each)
   int enc_mode;
@@ -71,9 +74,10 @@ struct alignas(64) SplitParams {
 namespace {
 
 // bias + ReLU + hi/lo split of one 32-column chunk; optional ReLU mask (bit j = column j passed) and head FMAs
-template <bool BITS>
+// F16: also the chunk as 16 packed fp16 pairs (fw) — what the training forward stores for the wgrad GEMMs in that mode
+template <bool BITS, bool F16>
 __device__ __forceinline__ uint32_t split_chunk(const uint32_t (&r)[32], const float* bias, int head_n, const float* head_w, float (&head)[3],
-                                                uint32_t* hw, uint32_t* lw) {
+                                                uint32_t* hw, uint32_t* lw, uint32_t* fw) {
   float x[32];
   const float4* bv = reinterpret_cast<const float4*>(bias);
 #pragma unroll
@@ -113,13 +117,15 @@ __device__ __forceinline__ uint32_t split_chunk(const uint32_t (&r)[32], const f
   for (int q = 0; q < 16; q++) {
     hw[q] = pack2s(x[2 * q], x[2 * q + 1]);
     lw[q] = pack2s(x[2 * q] - __uint_as_float(hw[q] << 16), x[2 * q + 1] - __uint_as_float(hw[q] & 0xFFFF0000u));
+    if (F16) fw[q] = pack_f16x2_sat(x[2 * q], x[2 * q + 1]);
   }
   return mask;
 }
 
 // dgrad chain: one 32-column chunk of dX = dZ W (+ r1 v1^T), masked by the ReLU bits of the layer below, split into hi/lo
+template <bool F16>
 __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint32_t mask, float r1, const float* v1, uint32_t* hw,
-                                                  uint32_t* lw) {
+                                                  uint32_t* lw, uint32_t* fw, float s16) {
 #pragma unroll
   for (int q = 0; q < 16; q++) {
     float x0 = __uint_as_float(r[2 * q]), x1 = __uint_as_float(r[2 * q + 1]);
@@ -128,6 +134,7 @@ __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint3
     x1 = ((mask >> (2 * q + 1)) & 1u) ? x1 : 0.f;
     hw[q] = pack2s(x0, x1);
     lw[q] = pack2s(x0 - __uint_as_float(hw[q] << 16), x1 - __uint_as_float(hw[q] & 0xFFFF0000u));
+    if (F16) fw[q] = pack_f16x2_sat(x0 * s16, x1 * s16);
   }
 }
 
@@ -151,9 +158,13 @@ __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint3
 // halves.  A slot is recycled when BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto w_empty, count CL).
 // Encoding stages stay per-CTA (own tile).  Every CTA of the grid walks the same NUMBER of tiles (phantom tiles past the end
 // load zeros and store nothing) so that the rings never diverge.
-template <int MODE, int CL>
+// F16 (training modes): what leaves the SM for the wgrad GEMMs is ONE fp16 plane per layer (activations, or dZ times the level's
+// power-of-two scale) instead of the hi + lo bf16 planes — half the store traffic here, half the read traffic and one MMA
+// instead of three there.  Everything on chip (ACT_hi | ACT_lo, the three-term products) is unchanged.
+template <int MODE, int CL, bool F16>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
   static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
+  static_assert(!F16 || MODE != 0, "the fp16 planes exist in the training kernels only");
   constexpr bool TRAIN = MODE != 0;
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     if (lane == 0) {
       for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_pos[q]); if (!DGRAD) prefetch_tmap(&p.map_dir[q]); }
       for (int s = 0; s < p.n_steps; s++)
-        for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_w[s][q]); if (TRAIN) prefetch_tmap(&p.map_act[s][q]); }
+        for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_w[s][q]); if (TRAIN && (q == 0 || !F16)) prefetch_tmap(&p.map_act[s][q]); }
     }
   }
   tc_fence_before_sync();
@@ -339,25 +350,30 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
       const long row = (long)row_w + lane;
       const bool row_ok = row < p.M;
       const float r1v = (DGRAD && row_ok) ? __ldg(p.r1 + row) : 0.f;
+      const float s16 = (DGRAD && F16) ? __ldg(p.dz_scale) : 1.0f;
       uint32_t held_h[32], held_l[32];           // first half's words wait here until the second half's MMAs have read ACT
       for (int s = 0; s < p.n_steps; s++) {
         const SplitParams::Step st = p.steps[s];
         float head[3] = {0.f, 0.f, 0.f};
         // TRAIN: ship one 32-column chunk (both planes) of this warp's 32 rows
-        auto ship = [&](int col, const uint32_t* hw, const uint32_t* lw) {
+        auto ship = [&](int col, const uint32_t* hw, const uint32_t* lw, const uint32_t* fw) {
           if (!TRAIN) return;
-          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous pair of boxes has been read out
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous box (pair) has been read out
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-            *reinterpret_cast<uint4*>(slot_row + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+            if (F16) {
+              *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(fw[4 * q], fw[4 * q + 1], fw[4 * q + 2], fw[4 * q + 3]);
+            } else {
+              *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+              *reinterpret_cast<uint4*>(slot_row + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+            }
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&p.map_act[s][0], slot, col, row_w);
-            tma_store_2d(&p.map_act[s][1], slot + 2048, col, row_w);
+            if (!F16) tma_store_2d(&p.map_act[s][1], slot + 2048, col, row_w);
             tma_store_commit();
           }
         };
@@ -371,12 +387,13 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           uint2 mk = make_uint2(0u, 0u);  // DGRAD: ReLU mask words of this thread's 64 columns (requested before the wait)
           if (DGRAD && row_ok && col_t < st.n_cols) mk = __ldg(reinterpret_cast<const uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)));
           const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + col_t : nullptr;
+          uint32_t fw[F16 ? 16 : 1];  // F16: the chunk as fp16 pairs, shipped at once
           auto chunk = [&](const uint32_t (&r)[32], int c, uint32_t* hw_, uint32_t* lw_) -> uint32_t {
             if (DGRAD) {
-              dgrad_split_chunk(r, c == 0 ? mk.x : mk.y, r1v, v1 ? v1 + c * 32 : nullptr, hw_, lw_);
+              dgrad_split_chunk<F16>(r, c == 0 ? mk.x : mk.y, r1v, v1 ? v1 + c * 32 : nullptr, hw_, lw_, fw, s16);
               return 0u;
             }
-            return split_chunk<MODE == 1>(r, bias + c * 32, st.head, head_w + c * 32, head, hw_, lw_);
+            return split_chunk<MODE == 1, F16>(r, bias + c * 32, st.head, head_w + c * 32, head, hw_, lw_, fw);
           };
           mbar_wait(&acc_full[h], n_full[h] & 1);
           n_full[h]++;
@@ -399,15 +416,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           }
           if (!last_half) {
             m0 = chunk(r0, 0, held_h, held_l);
-            ship(col_t, held_h, held_l);
+            ship(col_t, held_h, held_l, fw);
             m1 = chunk(r1, 1, held_h + 16, held_l + 16);
-            ship(col_t + 32, held_h + 16, held_l + 16);
+            ship(col_t + 32, held_h + 16, held_l + 16, fw);
           } else {
             uint32_t hw[16], lw[16];
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
             m0 = chunk(r0, 0, hw, lw);
             if (st.produces) { tmem_st_16(ACT_HI + out, hw); tmem_st_16(ACT_LO + out, lw); }
-            ship(col_t, hw, lw);
+            ship(col_t, hw, lw, fw);
             m1 = chunk(r1, 1, hw, lw);
             if (st.produces) {
               tmem_st_16(ACT_HI + out + 16, hw); tmem_st_16(ACT_LO + out + 16, lw);
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
                 mbar_arrive(&act_ready);
               }
             }
-            ship(col_t + 32, hw, lw);
+            ship(col_t + 32, hw, lw, fw);
           }
           if (MODE == 1 && row_ok && col_t < st.n_cols) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)) = make_uint2(m0, m1);
         }
@@ -448,9 +465,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
 }
 
 
-template <int MODE>
+template <int MODE, bool F16>
 int launch_split(const SplitParams& p, int grid, int threads, size_t smem, bool pair, cudaStream_t st) {
-  const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2> : (const void*)k_mlp_fused_split<MODE, 1>;
+  const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2, F16> : (const void*)k_mlp_fused_split<MODE, 1, F16>;
   SplitParams pp = p;
   return launch_persistent_clusters(kern, grid, threads, smem, 218 * 1024, pair ? 2 : 1, &pp, st);
 }
@@ -464,7 +481,9 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const __nv_bfloat16* const* w_lo, const int* kpad, const int* in_b, int D, int W, int Wc, long M,
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
-                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st) {
+                                   uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st,
+                                   bool act_f16) {
+  if (act_f16 && (!act_hi || rays)) { set_error("fused forward: fp16 activation planes are a training option with the encode kernel"); return 100001; }
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
     return 100001;
@@ -501,8 +520,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], w_hi[s], N, kpad[s], kpad[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], w_lo[s], N, kpad[s], kpad[s], 128));
     if (train) {
-      NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], act_hi[s], M, N, N, 32, 32));
-      NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], act_lo[s], M, N, N, 32, 32));
+      NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], act_hi[s], M, N, N, 32, 32));  // act_f16: the layer's ONE fp16 plane
+      if (!act_f16) NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], act_lo[s], M, N, N, 32, 32));
       p.bits[s] = bits_out[s];
     }
     SplitParams::Step& stp = p.steps[s];
@@ -518,7 +537,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
-  return train ? launch_split<1>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0>(p, grid, kThreadsSE, smem, pair, st);
+  if (act_f16) return launch_split<1, true>(p, grid, kThreadsSE, smem, pair, st);
+  return train ? launch_split<1, false>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0, false>(p, grid, kThreadsSE, smem, pair, st);
 }
 
 
@@ -528,7 +548,8 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, cudaStream_t st) {
+                                 bool pair, cudaStream_t st, const float* dz_scale_f16) {
+  const bool f16 = dz_scale_f16 != nullptr;  // dz_out_hi[s] is then ONE fp16 plane holding dZ * *dz_scale_f16 (dz_out_lo unused)
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
   const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
@@ -541,7 +562,7 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], wt_hi[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], dz_out_hi[s], M, W, W, 32, 32));
-    NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
+    if (!f16) NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
     SplitParams::Step& stp = p.steps[s];
     if (s == 0) { stp.n_act_kb = 0; stp.enc_kind = 1; stp.n_enc_kb = (int16_t)(Wc / 64); }
@@ -552,9 +573,10 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
     stp.head = 0; stp.bias_off = 0;
   }
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
-  p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density;
+  p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density; p.dz_scale = dz_scale_f16;
   const int tiles = (int)cdiv(M, 128);
-  return launch_split<2>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
+  if (f16) return launch_split<2, true>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
+  return launch_split<2, false>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
 }
 
 }  // namespace nerf

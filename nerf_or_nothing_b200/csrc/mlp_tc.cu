@@ -21,8 +21,10 @@ namespace {
 
 struct Plane {
   __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  __nv_bfloat16* f16 = nullptr;  // fp16 plane of the same tensor (typed as a 2-byte carrier): wgrad operand in the w16 mode
   int pitch = 0;  // elements per row (multiple of 64)
 };
+enum PlaneKind { PLANE_DEFAULT = 0, PLANE_F16_ONLY = 1, PLANE_PLUS_F16 = 2 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -41,15 +43,33 @@ class TcMlp : public MlpEngine {
     }
     pos_pitch_ = round_up(s_.P, 64);
     dir_pitch_ = round_up(s_.Dd, 64);
+    // NERF_FLAG_WGRAD_FP16 (fp32-accurate mode, fused kernels; opt-in): the wgrad operands (activations, encodings, dZ) are kept
+    // as ONE fp16 plane each instead of hi + lo bf16 planes — half the HBM traffic of the backward pass and one MMA per product
+    // in wgrad.  The forward and the dgrad chain, where an error would propagate through the layers and flip ReLU masks, keep
+    // the three-term products on chip.  Each wgrad operand then carries a 2^-12 relative rounding: on the real training step
+    // the sums over ~5e5 samples average it out (whole-step gradient ~1e-5 of its scale against fp64), but a sum whose terms
+    // cancel like a random walk keeps ~3e-4 of its scale — outside the 1e-4 contract of the mode, hence not the default.
+    w16_ = (flags_ & NERF_FLAG_WGRAD_FP16) != 0;
+    if (w16_ && !(split_ && can_fuse_forward() &&
+                  !(flags_ & (NERF_FLAG_NO_FUSED_TRAIN_FORWARD | NERF_FLAG_NO_FUSED_DGRAD | NERF_FLAG_FUSED_ENCODE_TRAIN)))) {
+      set_error("NERF_FLAG_WGRAD_FP16 needs NERF_PRECISION_FP32_TC with the fused training kernels (widths 256/128 or 128/64, no per-layer / encoder-warp flags)");
+      return 100001;
+    }
     levels_.resize(n_levels);
+    if (w16_) {
+      NERF_CUDA(cudaMalloc(&dz_sc_, (size_t)n_levels * 2 * sizeof(float) + 2 * sizeof(unsigned)));
+      owned_.push_back(dz_sc_);
+      NERF_CUDA(cudaMemset(dz_sc_, 0, (size_t)n_levels * 2 * sizeof(float) + 2 * sizeof(unsigned)));
+      dz_sc_scratch_ = reinterpret_cast<unsigned*>(dz_sc_ + (size_t)n_levels * 2);
+    }
     for (auto& lv : levels_) {
-      NERF_TRY(alloc_plane(&lv.enc_pos, max_rows, pos_pitch_));
-      NERF_TRY(alloc_plane(&lv.enc_dir, max_rows, dir_pitch_));
+      NERF_TRY(alloc_plane(&lv.enc_pos, max_rows, pos_pitch_, w16_ ? PLANE_PLUS_F16 : PLANE_DEFAULT));
+      NERF_TRY(alloc_plane(&lv.enc_dir, max_rows, dir_pitch_, w16_ ? PLANE_PLUS_F16 : PLANE_DEFAULT));
       lv.acts.resize(s_.D + s_.C);
       lv.bits.resize(s_.D + s_.C);
       for (int i = 0; i < s_.D + s_.C; i++) {
         const int w = i < s_.D ? s_.W : s_.Wc;
-        NERF_TRY(alloc_plane(&lv.acts[i], max_rows, w));
+        NERF_TRY(alloc_plane(&lv.acts[i], max_rows, w, w16_ ? PLANE_F16_ONLY : PLANE_DEFAULT));
         const size_t nb = (size_t)max_rows * (w / 32) * sizeof(uint32_t);
         NERF_CUDA(cudaMalloc(&lv.bits[i], nb));
         owned_.push_back(lv.bits[i]);
@@ -57,8 +77,8 @@ class TcMlp : public MlpEngine {
       }
     }
     const int mw = s_.W > s_.Wc ? s_.W : s_.Wc;
-    NERF_TRY(alloc_plane(&dz_[0], max_rows, mw));
-    NERF_TRY(alloc_plane(&dz_[1], max_rows, mw));
+    NERF_TRY(alloc_plane(&dz_[0], max_rows, mw, w16_ ? PLANE_PLUS_F16 : PLANE_DEFAULT));
+    if (!w16_) NERF_TRY(alloc_plane(&dz_[1], max_rows, mw));  // ping-pong partner of the per-layer dgrad launches
     wp_.resize(s_.L); wtp_.resize(s_.L);
     size_t ws = 1 << 20;
     for (int l = 0; l < s_.L; l++) {
@@ -93,12 +113,17 @@ class TcMlp : public MlpEngine {
     EncodeOut o;
     o.pos_hi = levels_[level].enc_pos.hi; o.pos_lo = levels_[level].enc_pos.lo; o.pos_pitch_h = pos_pitch_;
     o.dir_hi = levels_[level].enc_dir.hi; o.dir_lo = levels_[level].enc_dir.lo; o.dir_pitch_h = dir_pitch_;
+    o.pos_f16 = levels_[level].enc_pos.f16; o.dir_f16 = levels_[level].enc_dir.f16;
     return o;
   }
 
   int import_encodings(int level, const float* enc_pos, const float* enc_dir, long M, cudaStream_t st) override {
     Level& lv = levels_[level];
     NERF_TRY(launch_f32_to_planes(enc_pos, s_.P, M, s_.P, lv.enc_pos.hi, lv.enc_pos.lo, pos_pitch_, pos_pitch_, false, 0, st));
+    if (w16_) {
+      NERF_TRY(launch_f32_to_f16_plane(enc_pos, s_.P, M, s_.P, lv.enc_pos.f16, pos_pitch_, pos_pitch_, st));
+      NERF_TRY(launch_f32_to_f16_plane(enc_dir, s_.Dd, M, s_.Dd, lv.enc_dir.f16, dir_pitch_, dir_pitch_, st));
+    }
     return launch_f32_to_planes(enc_dir, s_.Dd, M, s_.Dd, lv.enc_dir.hi, lv.enc_dir.lo, dir_pitch_, dir_pitch_, false, 0, st);
   }
 
@@ -250,8 +275,9 @@ class TcMlp : public MlpEngine {
     }
     const int head_d_off = D * 256 + 128, head_rgb_off = head_d_off + 260, n_consts = head_rgb_off + 3 * 128 + 4;
     NERF_TRY(ensure_fconsts(params, st));
+    const bool f16 = train && w16_;  // training in the w16 mode: every layer's activations leave as one fp16 plane
     std::vector<__nv_bfloat16*> act_out(D + 1);
-    for (int s = 0; s <= D; s++) act_out[s] = lv.acts[s].hi;
+    for (int s = 0; s <= D; s++) act_out[s] = f16 ? lv.acts[s].f16 : lv.acts[s].hi;
     ProfScope ps(PC_MLP_FWD, st);
     if (split_) {
       std::vector<const __nv_bfloat16*> wlo(D + 1);
@@ -260,7 +286,7 @@ class TcMlp : public MlpEngine {
       return launch_mlp_fused_forward_split(epos.hi, epos.lo, pos_pitch_, edir.hi, edir.lo, dir_pitch_, wpl.data(),
                                             wlo.data(), kpad.data(), in_b.data(), D, s_.W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                             head_rgb_off, bias_off.data(), raw_density, raw_rgb, train ? act_out.data() : nullptr,
-                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st);
+                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st, f16);
     }
     return launch_mlp_fused_forward(epos.hi, pos_pitch_, edir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
@@ -287,12 +313,15 @@ class TcMlp : public MlpEngine {
     const int D = s_.D, C = s_.C, W = s_.W, Wc = s_.Wc;
     Plane* cur = &dz_[0];
     Plane* nxt = &dz_[1];
+    float* sc = w16_ ? dz_sc_ + 2 * level : nullptr;  // [s, 1/s]: power-of-two scale of this level's fp16 dZ planes
     {  // rgb head
       const LayerInfo& L = s_.layers[D + C + 1];
       const Plane& x = lv.acts[D + C - 1];
       ProfScope ps(PC_MLP_HEADS_BWD, st);
-      NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st));
-      NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st));
+      if (w16_) NERF_TRY(launch_dz_scale(d_raw_rgb, d_raw_density, M, sc, dz_sc_scratch_, st));
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, w16_ ? x.f16 : x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st, w16_));
+      NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st,
+                                        cur->f16, sc));
     }
     // The trunk's dgrad chain is one fused kernel in both tensor-core modes.  In the fp32-accurate mode it moves half the
     // bytes of the per-layer launches (each dZ is written once instead of written and re-read) and, since the next layer's
@@ -347,7 +376,7 @@ class TcMlp : public MlpEngine {
     const int D = s_.D, W = s_.W;
     if (dzs_.empty()) {  // first training step through this path
       dzs_.resize(D);
-      for (int j = 0; j < D; j++) NERF_TRY(alloc_plane(&dzs_[j], max_rows_, W));
+      for (int j = 0; j < D; j++) NERF_TRY(alloc_plane(&dzs_[j], max_rows_, W, w16_ ? PLANE_F16_ONLY : PLANE_DEFAULT));
     }
     NERF_TRY(ensure_fconsts(params, st));
     const int head_d_off = D * 256 + 128, n_consts = head_d_off + 260 + 3 * 128 + 4;
@@ -358,7 +387,7 @@ class TcMlp : public MlpEngine {
     for (int j = 0; j < D; j++) {
       const int l = j == 0 ? D + 1 : D - j;  // the layer whose dgrad step j performs; it produces dZ of trunk layer D-1-j
       wt[j] = wtp_[l].hi; wt_pitch[j] = wtp_[l].pitch;
-      dz_out[j] = dzs_[j].hi; masks[j] = lv.bits[D - 1 - j];
+      dz_out[j] = w16_ ? dzs_[j].f16 : dzs_[j].hi; masks[j] = lv.bits[D - 1 - j];
     }
     {
       ProfScope ps(PC_MLP_DGRAD, st);
@@ -367,12 +396,14 @@ class TcMlp : public MlpEngine {
         std::vector<__nv_bfloat16*> dz_lo(D);
         for (int j = 0; j < D; j++) { wt_lo[j] = wtp_[j == 0 ? D + 1 : D - j].lo; dz_lo[j] = dzs_[j].lo; }
         NERF_TRY(launch_mlp_fused_dgrad_split(dz_cond.hi, dz_cond.lo, dz_cond.pitch, wt.data(), wt_lo.data(), wt_pitch.data(), D, W, s_.Wc, M,
-                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), pair(), st));
+                                              fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), pair(), st,
+                                              w16_ ? dz_sc_ + 2 * level : nullptr));
       } else {
         NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                         d_raw_density, dz_out.data(), masks.data(), pair(), st));
       }
     }
+    wgrad_unscale_ = w16_ ? dz_sc_ + 2 * level + 1 : nullptr;
     {  // condition layer
       const LayerInfo& L = s_.layers[D + 1];
       ProfScope ps(PC_MLP_WGRAD, st);
@@ -382,8 +413,9 @@ class TcMlp : public MlpEngine {
       const LayerInfo& L = s_.layers[D];
       const Plane& x = lv.acts[D - 1];
       ProfScope ps(PC_MLP_HEADS_BWD, st);
-      NERF_TRY(launch_thin_wgrad_planes(d_raw_density, x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 1, W, ws_, st));
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_density, w16_ ? x.f16 : x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 1, W, ws_, st, w16_));
     }
+    wgrad_unscale_ = w16_ ? dz_sc_ + 2 * level + 1 : nullptr;  // the fp16 dZ planes carry the level's scale: the reductions divide it out
     for (int i = D - 1; i >= 0; i--) {
       const LayerInfo& L = s_.layers[i];
       const Plane& in = i == 0 ? lv.enc_pos : lv.acts[i - 1];
@@ -412,8 +444,16 @@ class TcMlp : public MlpEngine {
 
   bool needs_dgrad(int l) const { return (l > 0 && l < s_.D) || (l > s_.D && l <= s_.D + s_.C); }
 
-  int alloc_plane(Plane* p, long rows, int pitch) {
+  int alloc_plane(Plane* p, long rows, int pitch, PlaneKind kind = PLANE_DEFAULT) {
     const size_t bytes = (size_t)rows * pitch * sizeof(__nv_bfloat16);
+    p->pitch = pitch;
+    if (kind != PLANE_DEFAULT) {
+      NERF_CUDA(cudaMalloc(&p->f16, bytes));
+      owned_.push_back(p->f16);
+      NERF_CUDA(cudaMemset(p->f16, 0, bytes));
+      bytes_ += bytes;
+      if (kind == PLANE_F16_ONLY) return 0;
+    }
     NERF_CUDA(cudaMalloc(&p->hi, bytes));
     owned_.push_back(p->hi);
     NERF_CUDA(cudaMemset(p->hi, 0, bytes));
@@ -532,12 +572,20 @@ class TcMlp : public MlpEngine {
       memset(&p, 0, sizeof(p));
       const int BN = K > 256 ? 256 : round_up(K, 64);
       const int xcols = round_up(K, 64) <= x->pitch ? round_up(K, 64) : x->pitch;
-      NERF_TRY(tc_make_tmap(&p.maps[0], dz.hi, M, N, dz.pitch, 64));
-      if (split_) NERF_TRY(tc_make_tmap(&p.maps[1], dz.lo, M, N, dz.pitch, 64));
-      NERF_TRY(tc_make_tmap(&p.maps[4], x->hi, M, xcols, x->pitch, 64));
-      if (split_) NERF_TRY(tc_make_tmap(&p.maps[5], x->lo, M, xcols, x->pitch, 64));
+      if (w16_) {  // one fp16 plane per operand, one pass; dZ carries the level's scale (wgrad_unscale_ divides it out)
+        if (!dz.f16 || !x->f16) { set_error("wgrad: fp16 planes missing"); return 100001; }
+        NERF_TRY(tc_make_tmap(&p.maps[0], dz.f16, M, N, dz.pitch, 64));
+        NERF_TRY(tc_make_tmap(&p.maps[4], x->f16, M, xcols, x->pitch, 64));
+        p.f16_ops = 1;
+      } else {
+        NERF_TRY(tc_make_tmap(&p.maps[0], dz.hi, M, N, dz.pitch, 64));
+        if (split_) NERF_TRY(tc_make_tmap(&p.maps[1], dz.lo, M, N, dz.pitch, 64));
+        NERF_TRY(tc_make_tmap(&p.maps[4], x->hi, M, xcols, x->pitch, 64));
+        if (split_) NERF_TRY(tc_make_tmap(&p.maps[5], x->lo, M, xcols, x->pitch, 64));
+      }
       int pa[3][2];
-      p.n_pass = passes(pa);
+      p.n_pass = w16_ ? 1 : passes(pa);
+      if (w16_) { pa[0][0] = 0; pa[0][1] = 0; }
       for (int q = 0; q < p.n_pass; q++) { p.pass_a[q] = (int8_t)pa[q][0]; p.pass_b[q] = (int8_t)(4 + pa[q][1]); }
       int splits; long split_len;
       wgrad_split(N, K, M, &splits, &split_len);
@@ -556,6 +604,7 @@ class TcMlp : public MlpEngine {
       ReduceJob job;
       job.ws = wsp; job.out = dW; job.ws2 = bias_here ? bias_ws : nullptr; job.out2 = db; job.stride = p.split_stride; job.stride2 = N;
       job.splits = splits; job.rows = N; job.cols = K; job.ldw = ldf; job.ldo = ldw; job.coff = coff; job.n2 = bias_here ? N : 0;
+      job.mul = w16_ ? wgrad_unscale_ : nullptr;
       if (defer_reduce_) pending_ = job;
       else NERF_TRY(launch_reduce_job(job, st));
     }
@@ -565,6 +614,10 @@ class TcMlp : public MlpEngine {
   bool pair() const { return !(flags_ & NERF_FLAG_NO_WEIGHT_MULTICAST); }
 
   bool split_;
+  bool w16_ = false;                  // fp32-accurate mode: wgrad operands as fp16 planes (see init)
+  float* dz_sc_ = nullptr;            // w16: per level [s, 1/s], then 2 scratch words of launch_dz_scale
+  unsigned* dz_sc_scratch_ = nullptr;
+  const float* wgrad_unscale_ = nullptr;  // w16: device scalar the wgrad reductions of the level being walked multiply by
   unsigned flags_ = 0;
   MlpShape s_;
   long max_rows_ = 0;

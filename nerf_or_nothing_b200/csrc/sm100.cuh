@@ -204,5 +204,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with fp16 A/B (a_format = b_format = 0): the wgrad GEMMs of the fp32-accurate mode multiply fp16 planes
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return make_idesc_bf16(M, N, a_mn_major, b_mn_major) & ~((7u << 7) | (7u << 10));
+}
+// two floats -> packed fp16 pair (low half = a), round to nearest, overflow clamps to +-65504 instead of producing inf
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 }  // namespace sm100
 }  // namespace nerf
