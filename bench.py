@@ -600,7 +600,7 @@ def ours_arm(args):
             w = measure_train(job, args, "fp32_tc", R, host_batches, dev_batches, want_e2e=True, want_dataset=False,
                               engine_flags=args.engine_flags | W16_FLAG)
             wk, wrf = train_record(w, args, R, W16_MODE, job)
-            extra["modes"][W16_MODE] = dict(mode_record(w, wk, wrf), note="fp32-accurate forward and dgrad chain (three-term bf16 products); "
+            extra["modes"][W16_MODE] = dict(mode_record(w, wk, wrf), note="fp32-accurate forward (fp16 + E4M3 correction products) and dgrad chain (three-term bf16 products); "
                                             "wgrad reads ONE fp16 plane per operand: not the default, its gradient meets 1e-4 on real steps only")
         extra["render"] = {p: {k: v for k, v in measure_render(job, args, p, steps=3).items() if k != "kernels"} for p in ("bf16", "fp32_tc")}
         if job.world == 1:

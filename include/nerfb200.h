@@ -68,7 +68,7 @@ typedef struct nerf_config {
   uint32_t engine_flags;   /* NERF_FLAG_*: A/B switches of the tensor-core engine (0 = the shipped schedule) */
 } nerf_config;
 
-/* engine_flags: bits 0-4 and 6 select the slower, simpler path the default replaced, bits 5 and 7 alternatives that are not the default — parity tests compare them. */
+/* engine_flags: bits 0-4, 6 and 8 select the slower, simpler path the default replaced, bits 5 and 7 alternatives that are not the default — parity tests compare them. */
 #define NERF_FLAG_NO_FUSED_FORWARD 1u       /* render / forward-only: one GEMM launch per layer instead of the fused kernel */
 #define NERF_FLAG_NO_FUSED_TRAIN_FORWARD 2u /* training forward: per-layer launches */
 #define NERF_FLAG_NO_FUSED_DGRAD 4u         /* backward: per-layer dgrad launches instead of the fused chain */
@@ -87,6 +87,12 @@ typedef struct nerf_config {
                                               * traffic of the backward pass.  Forward, dgrad chain and everything per-ray are unchanged.
                                               * Gradient accuracy: ~1e-5 of the gradient's scale on a real step (sums over ~5e5 samples),
                                               * up to ~1e-3 on sums that cancel like a random walk — outside the mode's 1e-4, so not the default */
+
+#define NERF_FLAG_NO_FP8_CORRECTIONS 256u   /* fp32-accurate mode: the fused forward kernels multiply with three bf16 MMAs per product (hi*hi +
+                                              * lo*hi + hi*lo) instead of one fp16 MMA plus two E4M3 correction MMAs at twice the rate onto the
+                                              * same accumulator.  The default form is as accurate at the outputs (measured, profiles/README.md)
+                                              * and holds for |activation| < 2047, |weight| < 64 (beyond, values saturate instead of overflowing);
+                                              * it runs in rendering, and in training when NERF_FLAG_WGRAD_FP16 is set */
 
 typedef struct nerf_mipnerf nerf_mipnerf;   /* AcceleratedMipNeRF + its embedded AcceleratedMLP */
 typedef struct nerf_adam nerf_adam;         /* AcceleratedAdamOptimizer */

@@ -46,7 +46,8 @@ __device__ __forceinline__ void f4_add(float4& s, const float4 v) { s.x += v.x; 
 __device__ __forceinline__ void reduce_job_slot(const ReduceJob& j, long idx) {
   const int c4 = (j.cols + 3) >> 2;
   const long n1 = (long)j.rows * c4;
-  const float mul = j.mul ? __ldg(j.mul) : 1.0f;  // a power of two: exact
+  const float mul = j.mul ? __ldg(j.mul) : 1.0f;  // powers of two: exact
+  const float mul2 = j.mul2 ? __ldg(j.mul2) : 1.0f;
   if (idx < n1) {
     const int i = (int)(idx / c4), c = (int)(idx % c4) * 4;
     const float* src = j.ws + (long)i * j.ldw + c;
@@ -79,7 +80,7 @@ __device__ __forceinline__ void reduce_job_slot(const ReduceJob& j, long idx) {
     if (z < j.splits) s0 += src[(long)z * j.stride2];
     if (z + 1 < j.splits) s1 += src[(long)(z + 1) * j.stride2];
     if (z + 2 < j.splits) s2 += src[(long)(z + 2) * j.stride2];
-    j.out2[jb] += ((s0 + s1) + (s2 + s3)) * mul;
+    j.out2[jb] += ((s0 + s1) + (s2 + s3)) * mul2;
   }
 }
 
@@ -586,7 +587,7 @@ template <int NN, bool F16>
 __global__ void __launch_bounds__(256)
 k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int ldx,
                             const float* __restrict__ dZ, long M, int N, int K, long chunk, float* __restrict__ part,
-                            float* __restrict__ partb) {
+                            float* __restrict__ partb, float x_mul) {
   __shared__ float red[8][3][256 + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long m0 = (long)blockIdx.x * chunk, m1 = min(M, m0 + chunk);
@@ -624,7 +625,7 @@ k_thin_wgrad_planes_partial(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
       for (int q = 0; q < 4; q++) {
         if (F16) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
-          x[2 * q] = f.x; x[2 * q + 1] = f.y;
+          x[2 * q] = f.x * x_mul; x[2 * q + 1] = f.y * x_mul;  // x_mul: the power of two the plane carries (exact)
         } else {
           x[2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
           x[2 * q + 1] = __uint_as_float(hw[q] & 0xFFFF0000u) + __uint_as_float(lw[q] & 0xFFFF0000u);
@@ -1034,7 +1035,7 @@ long thin_wgrad_chunk(long M) {  // ~4 blocks per SM, at least 256 rows each
 }
 
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
-                             long M, int N, int K, float* workspace, cudaStream_t st, bool x_f16) {
+                             long M, int N, int K, float* workspace, cudaStream_t st, bool x_f16, float x_mul) {
   if (N > 4) { set_error("thin_wgrad_planes: N=%d", N); return 100001; }
   if (N > 3 || K % 8) { set_error("thin_wgrad_planes: N=%d K=%d unsupported", N, K); return 100001; }
   const long chunk = thin_wgrad_chunk(M);
@@ -1044,10 +1045,10 @@ int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __n
   for (int k0 = 0; k0 < K; k0 += 256) {  // the kernel covers 256 columns (8 per lane) per pass
     const int kp = K - k0 < 256 ? K - k0 : 256;
     const __nv_bfloat16* xlk = xl ? xl + k0 : nullptr;
-    if (N == 1 && x_f16) k_thin_wgrad_planes_partial<1, true><<<chunks, 256, 0, st>>>(xh + k0, nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
-    else if (N == 3 && x_f16) k_thin_wgrad_planes_partial<3, true><<<chunks, 256, 0, st>>>(xh + k0, nullptr, ldx, dZ, M, N, kp, chunk, part, partb);
-    else if (N == 1) k_thin_wgrad_planes_partial<1, false><<<chunks, 256, 0, st>>>(xh + k0, xlk, ldx, dZ, M, N, kp, chunk, part, partb);
-    else if (N == 3) k_thin_wgrad_planes_partial<3, false><<<chunks, 256, 0, st>>>(xh + k0, xlk, ldx, dZ, M, N, kp, chunk, part, partb);
+    if (N == 1 && x_f16) k_thin_wgrad_planes_partial<1, true><<<chunks, 256, 0, st>>>(xh + k0, nullptr, ldx, dZ, M, N, kp, chunk, part, partb, x_mul);
+    else if (N == 3 && x_f16) k_thin_wgrad_planes_partial<3, true><<<chunks, 256, 0, st>>>(xh + k0, nullptr, ldx, dZ, M, N, kp, chunk, part, partb, x_mul);
+    else if (N == 1) k_thin_wgrad_planes_partial<1, false><<<chunks, 256, 0, st>>>(xh + k0, xlk, ldx, dZ, M, N, kp, chunk, part, partb, 1.0f);
+    else if (N == 3) k_thin_wgrad_planes_partial<3, false><<<chunks, 256, 0, st>>>(xh + k0, xlk, ldx, dZ, M, N, kp, chunk, part, partb, 1.0f);
     else { set_error("thin_wgrad_planes: N=%d unsupported", N); return 100001; }
     NERF_CHECK_LAUNCH();
     NERF_TRY(launch_reduce_partials2(part, chunks, (long)N * kp, N, kp, kp, dW, K, k0, (db && k0 == 0) ? partb : nullptr, N, N, db, st));
@@ -1061,7 +1062,7 @@ namespace {
 // max |x| over the head gradients of a level -> the power-of-two scale of its fp16 dZ planes.  Non-negative floats order like
 // their bit patterns, so the block maxima meet in one atomicMax; the last block (ticket) turns the maximum into
 // s = 2^-floor(log2 max), 1/s and re-zeroes the scratch for the next launch.
-__global__ void __launch_bounds__(256) k_dz_scale(const float* __restrict__ a, long na, const float* __restrict__ b, long nb,
+__global__ void __launch_bounds__(256) k_dz_scale(const float* __restrict__ a, long na, const float* __restrict__ b, long nb, float act_scale,
                                                   float* __restrict__ out, unsigned* __restrict__ scratch) {
   __shared__ unsigned red[8];
   unsigned m = 0u;
@@ -1095,6 +1096,7 @@ __global__ void __launch_bounds__(256) k_dz_scale(const float* __restrict__ a, l
       if (e > 253u) e = 253u;
       out[0] = __uint_as_float((254u - e) << 23);  // 2^(127 - e)
       out[1] = __uint_as_float(e << 23);           // 2^(e - 127)
+      out[2] = out[1] * act_scale;
     }
   }
 }
@@ -1110,12 +1112,12 @@ __global__ void __launch_bounds__(256) k_f32_to_f16_plane(const float* __restric
 
 }  // namespace
 
-int launch_dz_scale(const float* d_raw_rgb, const float* d_raw_density, long M, float* out, unsigned* scratch, cudaStream_t st) {
+int launch_dz_scale(const float* d_raw_rgb, const float* d_raw_density, long M, float act_scale, float* out, unsigned* scratch, cudaStream_t st) {
   if (((uintptr_t)d_raw_rgb | (uintptr_t)d_raw_density) & 15) { set_error("dz_scale: head gradients must be 16-byte aligned"); return 100001; }
   long blocks = cdiv(M, 256 * 4);
   if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
-  k_dz_scale<<<(unsigned)blocks, 256, 0, st>>>(d_raw_rgb, 3 * M, d_raw_density, M, out, scratch);
+  k_dz_scale<<<(unsigned)blocks, 256, 0, st>>>(d_raw_rgb, 3 * M, d_raw_density, M, act_scale, out, scratch);
   NERF_CHECK_LAUNCH();
   return 0;
 }
@@ -1124,6 +1126,50 @@ int launch_f32_to_f16_plane(const float* src, int src_pitch, long rows, int cols
   const long n = rows * dst_cols;
   if (n <= 0) return 0;
   k_f32_to_f16_plane<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(src, src_pitch, rows, cols, static_cast<__half*>(dst), dst_pitch, dst_cols);
+  NERF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------- weight planes of the fp16 + fp8-correction representation
+namespace {
+
+// One thread per (row n, column k) of a layer's weight matrix W [rows, cols] (mlp_fused_split.cu, REP = 1):
+//   k <  enc_from  (multiplies the tensor-memory-resident activations)   p0[n, k] = fp16(2^10 w) = 2^10 wh;
+//                  p1, seen as bytes, per 64-column k-block b: byte 128 b + j = E4M3(2^6 wh), byte 128 b + 64 + j = E4M3(2^15 wl)
+//   k >= enc_from  (multiplies the bf16 hi/lo encodings from shared memory) p0 / p1 = bf16 hi / lo of 2^15 w
+//   k >= cols      zero padding up to kpad
+__global__ void __launch_bounds__(256) k_f32_to_f8c_planes(const __grid_constant__ F8cJobs jobs) {
+  const F8cJobs::Job& j = jobs.job[blockIdx.y];
+  const long total = (long)j.rows * j.kpad;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / j.kpad), k = (int)(idx % j.kpad);
+    const float w = k < j.cols ? j.src[(long)n * j.cols + k] : 0.f;
+    uint16_t* p0 = reinterpret_cast<uint16_t*>(j.p0) + (long)n * j.kpad;
+    if (k < j.enc_from) {
+      const float t = w * 1024.f;
+      const uint16_t hb = (uint16_t)(pack_f16x2_sat(t, 0.f) & 0xFFFFu);  // |w| >= 64 saturates instead of becoming inf
+      const float hf = __half2float(__ushort_as_half(hb));
+      p0[k] = hb;
+      uint8_t* row8 = reinterpret_cast<uint8_t*>(j.p1) + (long)n * j.kpad * 2;
+      const int b = k >> 6, jj = k & 63;
+      row8[128 * b + jj] = (uint8_t)(pack_e4m3x2_f32(hf * 0.0625f, 0.f) & 0xFFu);             // 2^6 wh = 2^-4 (2^10 wh)
+      row8[128 * b + 64 + jj] = (uint8_t)(pack_e4m3x2_f32((t - hf) * 32.f, 0.f) & 0xFFu);      // 2^15 wl = 2^5 (2^10 wl)
+    } else {
+      const float sw = w * 32768.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(sw);
+      p0[k] = __bfloat16_as_ushort(hi);
+      reinterpret_cast<uint16_t*>(j.p1)[(long)n * j.kpad + k] = __bfloat16_as_ushort(__float2bfloat16_rn(sw - __bfloat162float(hi)));
+    }
+  }
+}
+
+}  // namespace
+
+int launch_f32_to_f8c_planes(const F8cJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  for (int i = 0; i < jobs.n; i++)
+    if (jobs.job[i].enc_from % 64 || jobs.job[i].kpad % 64) { set_error("f8c planes: k-blocks of 64 columns"); return 100001; }
+  k_f32_to_f8c_planes<<<dim3(64, (unsigned)jobs.n), 256, 0, st>>>(jobs);
   NERF_CHECK_LAUNCH();
   return 0;
 }

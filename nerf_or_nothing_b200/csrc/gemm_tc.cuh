@@ -23,7 +23,8 @@ struct ReduceJob {
   float* out2;
   long stride, stride2;
   int splits, rows, cols, ldw, ldo, coff, n2;
-  const float* mul;  // optional device scalar: the sums are multiplied by *mul (the power-of-two un-scaling of fp16 dZ planes)
+  const float *mul, *mul2;  // optional device scalars: the sums (mul2: the bias segment) are multiplied by them — the power-of-two
+                            // un-scaling of fp16 dZ / activation planes
 };
 
 struct alignas(64) TcParams {
@@ -105,7 +106,14 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
                                    uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st,
-                                   bool act_f16 = false);
+                                   bool act_f16 = false, bool fp8c = false);
+// fp8c: the activations stay on chip as fp16 + two E4M3 correction planes and w_hi / w_lo are the matching W16 / W8 weight planes
+// (launch_f32_to_f8c_planes): two MMA-equivalents per product instead of three (mlp_fused_split.cu, REP = 1)
+struct F8cJobs {
+  struct Job { const float* src; __nv_bfloat16 *p0, *p1; int rows, cols, enc_from, kpad; } job[16];
+  int n;
+};
+int launch_f32_to_f8c_planes(const F8cJobs& jobs, cudaStream_t st);
 // act_f16 (training): act_hi[s] is ONE fp16 plane per layer (act_lo unused) — the X operands of the fp16 wgrad GEMMs
 // pair: run as 2-CTA clusters sharing every weight stage by TMA multicast (halves the L2 weight traffic; mlp_fused_split.cu)
 
@@ -144,10 +152,11 @@ int launch_thin_dgrad_planes(const float* dZ, const float* W, long M, int N, int
                              const float* scale16 = nullptr);
 // x_f16: xh is one fp16 plane (xl ignored)
 int launch_thin_wgrad_planes(const float* dZ, const __nv_bfloat16* xh, const __nv_bfloat16* xl, int ldx, float* dW, float* db,
-                             long M, int N, int K, float* workspace, cudaStream_t st, bool x_f16 = false);
+                             long M, int N, int K, float* workspace, cudaStream_t st, bool x_f16 = false, float x_mul = 1.0f);
 // Device scalars for the fp16 dZ planes of one level: out[0] = s = 2^-floor(log2(max |d_raw|)) (so that the largest head gradient
-// lands in [1, 2)), out[1] = 1 / s.  scratch: 2 zero-initialised words (left zeroed).  One launch, no host round trip.
-int launch_dz_scale(const float* d_raw_rgb, const float* d_raw_density, long M, float* out, unsigned* scratch, cudaStream_t st);
+// lands in [1, 2)), out[1] = 1 / s, out[2] = act_scale / s (act_scale: the power of two the level's activation planes carry).
+// scratch: 2 zero-initialised words (left zeroed).  One launch, no host round trip.
+int launch_dz_scale(const float* d_raw_rgb, const float* d_raw_density, long M, float act_scale, float* out, unsigned* scratch, cudaStream_t st);
 // fp32 [rows, cols] (pitch src_pitch) -> one fp16 plane (pitch dst_pitch, zero padded up to dst_cols)
 int launch_f32_to_f16_plane(const float* src, int src_pitch, long rows, int cols, void* dst, int dst_pitch, int dst_cols, cudaStream_t st);
 // db[n] += sum_m (hi + lo)[m, n]

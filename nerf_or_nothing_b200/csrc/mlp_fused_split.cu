@@ -14,6 +14,7 @@
 // (training) ship them through 64-byte-swizzled [32 x 32] boxes with their own TMA stores.  The encodings of layer 0,
 // the skip layer and the condition layer stream through the same ring as shared-memory A operands.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstring>
 
@@ -138,6 +139,70 @@ __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint3
   }
 }
 
+// REP = 1, the "fp16 + fp8 corrections" representation of the same three-term product (forward kernels):
+//   a w ~= ah wh + al wh + ah wl   with ah = fp16(a), al = a - ah (|al| <= 2^-12 |a|), likewise w.
+// The two correction terms are 2^-12 of the product, so 4 significant bits of their factors keep the total error at 2^-16: they
+// run as E4M3 MMAs (kind::f8f6f4, K = 32 per instruction = twice the bf16 rate) onto the SAME accumulator — two MMA-equivalents
+// per product instead of three.  E4M3 spans 2^-9 .. 448 only, so every factor carries a power of two and the accumulator holds
+// 2^15 x the true sum (undone by the epilogue's FFMA):
+//   tensor memory  ACT16 [0,128)  fp16(32 a), two per column       x  W16 = fp16(2^10 w)                       (kind::f16)
+//                  ACT8 [128,256) per 64-wide k-block 16 columns E4M3(2^9 al), then 16 columns E4M3(ah)
+//                                                                  x  W8 = per k-block 64 bytes E4M3(2^6 wh), 64 bytes E4M3(2^15 wl)
+// and the encoding k-blocks (shared-memory A operands, bf16 hi/lo as before) multiply weight columns stored as bf16 hi/lo of
+// 2^15 w.  A ring stage is still 32 KB: the W16 tile [128 x 64] and the W8 tile [128 x 128 bytes] of the (half, k-block).
+// One 32-column chunk: t = 32 relu(z) -> 16 fp16 pairs (hw), 8 words E4M3(2^9 al) (l8), 8 words E4M3(ah) (h8).
+template <bool BITS>
+__device__ __forceinline__ uint32_t f8c_chunk(const uint32_t (&r)[32], const float* bias32, int head_n, const float* head_w, float (&head)[3],
+                                              uint32_t* hw, uint32_t* l8, uint32_t* h8) {
+  float t[32];
+  const float4* bv = reinterpret_cast<const float4*>(bias32);
+  constexpr float kAcc = 1.0f / 1024.0f;  // accumulator = 2^15 z; t = 32 z + 32 b
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 bb = bv[q];
+    t[4 * q] = fmaf(__uint_as_float(r[4 * q]), kAcc, bb.x); t[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), kAcc, bb.y);
+    t[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), kAcc, bb.z); t[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), kAcc, bb.w);
+  }
+  uint32_t mask = 0u;
+  if (BITS) {
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int e = 7; e >= 0; e--) m[g] = __funnelshift_l(__float_as_uint(t[8 * g + e]), m[g], 1);
+    mask = ~__byte_perm(__byte_perm(m[0], m[1], 0x0040), __byte_perm(m[2], m[3], 0x0040), 0x5410);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) t[j] = fmaxf(t[j], 0.f);
+  if (head_n) {  // on 32 a: the caller scales the head sums by 2^-5
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+      if (n < head_n) {
+        const float4* hv = reinterpret_cast<const float4*>(head_w + n * 128);
+        float a = head[n];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float4 w = hv[q];
+          a = fmaf(t[4 * q], w.x, a); a = fmaf(t[4 * q + 1], w.y, a);
+          a = fmaf(t[4 * q + 2], w.z, a); a = fmaf(t[4 * q + 3], w.w, a);
+        }
+        head[n] = a;
+      }
+  }
+  const __half2 k32nd = __floats2half2_rn(0.03125f, 0.03125f);
+#pragma unroll
+  for (int q = 0; q < 8; q++) {  // four values per E4M3 word
+    const uint32_t h0 = pack_f16x2_sat(t[4 * q], t[4 * q + 1]), h1 = pack_f16x2_sat(t[4 * q + 2], t[4 * q + 3]);
+    hw[2 * q] = h0; hw[2 * q + 1] = h1;
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+    l8[q] = pack_e4m3x2_f32((t[4 * q] - f0.x) * 16.f, (t[4 * q + 1] - f0.y) * 16.f) |
+            (pack_e4m3x2_f32((t[4 * q + 2] - f1.x) * 16.f, (t[4 * q + 3] - f1.y) * 16.f) << 16);
+    const __half2 g0 = __hmul2(*reinterpret_cast<const __half2*>(&h0), k32nd), g1 = __hmul2(*reinterpret_cast<const __half2*>(&h1), k32nd);
+    h8[q] = pack_e4m3x2_f16x2(*reinterpret_cast<const uint32_t*>(&g0)) | (pack_e4m3x2_f16x2(*reinterpret_cast<const uint32_t*>(&g1)) << 16);
+  }
+  return mask;
+}
+
 // One CTA walks 128-row tiles.  A layer is two N-halves with their own accumulator columns: while the MMAs of the second
 // half run, the eight epilogue warps (TMEM lane quarter = warp % 4, 64 of the half's 128 columns each) finish the first
 // half into registers; its hi/lo words are written into ACT — in place — only after the second half's MMAs have read
@@ -161,10 +226,11 @@ __device__ __forceinline__ void dgrad_split_chunk(const uint32_t (&r)[32], uint3
 // F16 (training modes): what leaves the SM for the wgrad GEMMs is ONE fp16 plane per layer (activations, or dZ times the level's
 // power-of-two scale) instead of the hi + lo bf16 planes — half the store traffic here, half the read traffic and one MMA
 // instead of three there.  Everything on chip (ACT_hi | ACT_lo, the three-term products) is unchanged.
-template <int MODE, int CL, bool F16>
+template <int MODE, int CL, bool F16, int REP = 0>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
   static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
   static_assert(!F16 || MODE != 0, "the fp16 planes exist in the training kernels only");
+  static_assert(REP == 0 || MODE == 0 || (MODE == 1 && F16), "fp8 corrections: inference forward, or training forward with fp16 planes out");
   constexpr bool TRAIN = MODE != 0;
   constexpr bool DGRAD = MODE == 2;
   constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
@@ -192,7 +258,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     for (int b = 0; b < 2; b++) { mbar_init(&enc_ready[b], kEncWarpsS); mbar_init(&enc_free[b], 1); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_consts; i += blockDim.x) s_const[i] = __ldg(p.consts + i);
+  // REP = 1: the biases (everything before the density head's weights) are staged as 32 b, see f8c_chunk
+  for (int i = threadIdx.x; i < p.n_consts; i += blockDim.x) s_const[i] = __ldg(p.consts + i) * ((REP == 1 && i < p.head_d_off) ? 32.f : 1.f);
   if (warp == kEpiWarps) {
     tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
@@ -253,6 +320,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     const uint64_t desc0 = make_smem_desc(0, 16, 1024);
     const uint32_t ring_base = smem_u32(w_ring);
     const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
+    const uint32_t idesc_h = make_idesc_f16(128, 128, false, false), idesc_8 = make_idesc_e4m3(128, 128);
     uint32_t it = 0, n_acc[2] = {0, 0}, n_act = 0, tl = 0;
     // a ring slot is released in EVERY CTA of the cluster: the peer may multicast into this CTA's slot only when both are done
     auto release = [&](uint64_t* bar) {
@@ -288,7 +356,12 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             tc_fence_after_sync();
             const uint64_t dbh = desc0 + ((ring_base + ws * kStageB) >> 4), dbl = dbh + (16384 >> 4);
             if (leader) {
-              if (from_act) {
+              if (from_act && REP == 1) {  // fp16 main product, then the two E4M3 correction products (K = 32 each)
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc_h, (kb | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_f8_ts(acc, ACT_LO + kb * 32 + k * 8, dbl + 2 * k, idesc_8, 1u);
+              } else if (from_act) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {  // hi*hi + lo*hi + hi*lo
                   umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
@@ -388,7 +461,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           if (DGRAD && row_ok && col_t < st.n_cols) mk = __ldg(reinterpret_cast<const uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)));
           const float* v1 = (DGRAD && s == 0) ? s_const + p.head_d_off + col_t : nullptr;
           uint32_t fw[F16 ? 16 : 1];  // F16: the chunk as fp16 pairs, shipped at once
-          auto chunk = [&](const uint32_t (&r)[32], int c, uint32_t* hw_, uint32_t* lw_) -> uint32_t {
+          // REP = 1: hw_ = 16 fp16 pairs of 32 a (also what F16 ships), lw_ = 8 words E4M3(2^9 al), h8_ = 8 words E4M3(ah)
+          auto chunk = [&](const uint32_t (&r)[32], int c, uint32_t* hw_, uint32_t* lw_, uint32_t* h8_) -> uint32_t {
+            if (REP == 1) return f8c_chunk<MODE == 1>(r, bias + c * 32, st.head, head_w + c * 32, head, hw_, lw_, h8_);
             if (DGRAD) {
               dgrad_split_chunk<F16>(r, c == 0 ? mk.x : mk.y, r1v, v1 ? v1 + c * 32 : nullptr, hw_, lw_, fw, s16);
               return 0u;
@@ -415,19 +490,26 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             if (unpark) mbar_arrive(&act_lo_ready);     // the next layer's k-blocks 0,1 may start
           }
           if (!last_half) {
-            m0 = chunk(r0, 0, held_h, held_l);
-            ship(col_t, held_h, held_l, fw);
-            m1 = chunk(r1, 1, held_h + 16, held_l + 16);
-            ship(col_t + 32, held_h + 16, held_l + 16, fw);
+            // REP = 1: held_l = [E4M3(al) chunk 0 | chunk 1 | E4M3(ah) chunk 0 | chunk 1] = the 32 ACT8 columns of this k-block
+            m0 = chunk(r0, 0, held_h, held_l, held_l + 16);
+            ship(col_t, held_h, held_l, REP == 1 ? held_h : fw);
+            m1 = chunk(r1, 1, held_h + 16, held_l + (REP == 1 ? 8 : 16), held_l + 24);
+            ship(col_t + 32, held_h + 16, held_l + 16, REP == 1 ? held_h + 16 : fw);
           } else {
             uint32_t hw[16], lw[16];
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
-            m0 = chunk(r0, 0, hw, lw);
-            if (st.produces) { tmem_st_16(ACT_HI + out, hw); tmem_st_16(ACT_LO + out, lw); }
-            ship(col_t, hw, lw, fw);
-            m1 = chunk(r1, 1, hw, lw);
+            m0 = chunk(r0, 0, hw, lw, lw + 8);
             if (st.produces) {
-              tmem_st_16(ACT_HI + out + 16, hw); tmem_st_16(ACT_LO + out + 16, lw);
+              tmem_st_16(ACT_HI + out, hw);
+              if (REP == 1) { tmem_st_8(ACT_LO + out, lw); tmem_st_8(ACT_LO + out + 16, lw + 8); }
+              else tmem_st_16(ACT_LO + out, lw);
+            }
+            ship(col_t, hw, lw, REP == 1 ? hw : fw);
+            m1 = chunk(r1, 1, hw, lw, lw + 8);
+            if (st.produces) {
+              tmem_st_16(ACT_HI + out + 16, hw);
+              if (REP == 1) { tmem_st_8(ACT_LO + out + 8, lw); tmem_st_8(ACT_LO + out + 24, lw + 8); }
+              else tmem_st_16(ACT_LO + out + 16, lw);
               tmem_st_wait();
               tc_fence_before_sync();
               __syncwarp();
@@ -436,7 +518,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
                 mbar_arrive(&act_ready);
               }
             }
-            ship(col_t + 32, hw, lw, fw);
+            ship(col_t + 32, hw, lw, REP == 1 ? hw : fw);
           }
           if (MODE == 1 && row_ok && col_t < st.n_cols) *reinterpret_cast<uint2*>(p.bits[s] + row * (st.n_cols >> 5) + (col_t >> 5)) = make_uint2(m0, m1);
         }
@@ -444,11 +526,12 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           if (ch == 1) { head_part[row_t][0] = head[0]; head_part[row_t][1] = head[1]; head_part[row_t][2] = head[2]; }
           named_barrier_sync(1 + qtr, 64);
           if (ch == 0 && row_ok) {
+            constexpr float hs = REP == 1 ? 0.03125f : 1.0f;  // REP = 1: the head sums ran on 32 a
             if (st.head == 1) {
-              p.raw_density[row] = head[0] + head_part[row_t][0] + s_const[p.head_d_off + 256];
+              p.raw_density[row] = (head[0] + head_part[row_t][0]) * hs + s_const[p.head_d_off + 256];
             } else {
 #pragma unroll
-              for (int n = 0; n < 3; n++) p.raw_rgb[row * 3 + n] = head[n] + head_part[row_t][n] + s_const[p.head_rgb_off + 3 * 128 + n];
+              for (int n = 0; n < 3; n++) p.raw_rgb[row * 3 + n] = (head[n] + head_part[row_t][n]) * hs + s_const[p.head_rgb_off + 3 * 128 + n];
             }
           }
           named_barrier_sync(1 + qtr, 64);  // head_part may be rewritten
@@ -465,9 +548,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
 }
 
 
-template <int MODE, bool F16>
+template <int MODE, bool F16, int REP = 0>
 int launch_split(const SplitParams& p, int grid, int threads, size_t smem, bool pair, cudaStream_t st) {
-  const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2, F16> : (const void*)k_mlp_fused_split<MODE, 1, F16>;
+  const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2, F16, REP> : (const void*)k_mlp_fused_split<MODE, 1, F16, REP>;
   SplitParams pp = p;
   return launch_persistent_clusters(kern, grid, threads, smem, 218 * 1024, pair ? 2 : 1, &pp, st);
 }
@@ -482,7 +565,9 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
                                    uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st,
-                                   bool act_f16) {
+                                   bool act_f16, bool fp8c) {
+  // fp8c: w_hi[s] / w_lo[s] are the W16 / W8 planes of f8c_chunk's representation (launch_f32_to_f8c_planes); training needs act_f16
+  if (fp8c && act_hi && !act_f16) { set_error("fused forward: fp8 corrections in training need the fp16 activation planes"); return 100001; }
   if (act_f16 && (!act_hi || rays)) { set_error("fused forward: fp16 activation planes are a training option with the encode kernel"); return 100001; }
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D + 1 > kMaxStepsS || pos_pitch != 128 || dir_pitch != 64) {
     set_error("fused forward supports widths 256/128 and 128/64 (trunk / condition), position pitch 128, direction pitch 64");
@@ -537,6 +622,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
+  if (fp8c) return train ? launch_split<1, true, 1>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0, false, 1>(p, grid, kThreadsSE, smem, pair, st);
   if (act_f16) return launch_split<1, true>(p, grid, kThreadsSE, smem, pair, st);
   return train ? launch_split<1, false>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0, false>(p, grid, kThreadsSE, smem, pair, st);
 }

@@ -55,12 +55,17 @@ class TcMlp : public MlpEngine {
       set_error("NERF_FLAG_WGRAD_FP16 needs NERF_PRECISION_FP32_TC with the fused training kernels (widths 256/128 or 128/64, no per-layer / encoder-warp flags)");
       return 100001;
     }
+    // fp32-accurate mode, fused forward kernels: the three-term product as one fp16 MMA plus two E4M3 correction MMAs at twice
+    // the rate (mlp_fused_split.cu, REP = 1) — measured as accurate as the bf16x3 split at the outputs (rendered rgb 9e-7 vs
+    // 7e-7 against fp64) and 14 % faster on an 800x800 render.  Rendering by default; training when the activations leave as
+    // fp16 planes anyway (NERF_FLAG_WGRAD_FP16).  NERF_FLAG_NO_FP8_CORRECTIONS keeps the bf16x3 kernels everywhere.
+    f8c_ = split_ && can_fuse_forward() && !(flags_ & NERF_FLAG_NO_FP8_CORRECTIONS);
     levels_.resize(n_levels);
     if (w16_) {
-      NERF_CUDA(cudaMalloc(&dz_sc_, (size_t)n_levels * 2 * sizeof(float) + 2 * sizeof(unsigned)));
+      NERF_CUDA(cudaMalloc(&dz_sc_, (size_t)n_levels * 4 * sizeof(float) + 2 * sizeof(unsigned)));
       owned_.push_back(dz_sc_);
-      NERF_CUDA(cudaMemset(dz_sc_, 0, (size_t)n_levels * 2 * sizeof(float) + 2 * sizeof(unsigned)));
-      dz_sc_scratch_ = reinterpret_cast<unsigned*>(dz_sc_ + (size_t)n_levels * 2);
+      NERF_CUDA(cudaMemset(dz_sc_, 0, (size_t)n_levels * 4 * sizeof(float) + 2 * sizeof(unsigned)));
+      dz_sc_scratch_ = reinterpret_cast<unsigned*>(dz_sc_ + (size_t)n_levels * 4);
     }
     for (auto& lv : levels_) {
       NERF_TRY(alloc_plane(&lv.enc_pos, max_rows, pos_pitch_, w16_ ? PLANE_PLUS_F16 : PLANE_DEFAULT));
@@ -85,6 +90,10 @@ class TcMlp : public MlpEngine {
       const LayerInfo& L = s_.layers[l];
       if (L.out <= 4) { ws = std::max(ws, (size_t)cdiv(max_rows, 256) * L.out * (L.in_a + 1) + 64); continue; }
       NERF_TRY(alloc_plane(&wp_[l], L.out, round_up(L.in_a + L.in_b, 64)));
+      if (f8c_ && (l < s_.D || l == s_.D + 1)) {
+        if (wf_.empty()) wf_.resize(s_.L);
+        NERF_TRY(alloc_plane(&wf_[l], L.out, round_up(L.in_a + L.in_b, 64)));  // hi / lo = the W16 / W8 planes
+      }
       if (needs_dgrad(l)) NERF_TRY(alloc_plane(&wtp_[l], L.in_a, L.out));
       for (int src = 0; src < 2; src++) {
         const int K = src == 0 ? L.in_a : L.in_b;
@@ -148,6 +157,20 @@ class TcMlp : public MlpEngine {
       if (needs_dgrad(l)) add(params + L.w_off, K, L.out, L.in_a, wtp_[l], L.out, true, L.in_a);  // WT[k, n] = W[n, k] for k < in_a
     }
     NERF_TRY(launch_f32_to_planes_batch(jobs, st));
+    if (f8c_) {
+      F8cJobs fj;
+      fj.n = 0;
+      for (int l = 0; l < s_.L; l++) {
+        if (!(l < s_.D || l == s_.D + 1)) continue;
+        const LayerInfo& L = s_.layers[l];
+        if (fj.n == 16) { NERF_TRY(launch_f32_to_f8c_planes(fj, st)); fj.n = 0; }
+        F8cJobs::Job& j = fj.job[fj.n++];
+        j.src = params + L.w_off; j.p0 = wf_[l].hi; j.p1 = wf_[l].lo; j.rows = L.out; j.cols = L.in_a + L.in_b;
+        j.enc_from = l == 0 ? 0 : L.in_a;  // layer 0 multiplies the position encoding only
+        j.kpad = wf_[l].pitch;
+      }
+      NERF_TRY(launch_f32_to_f8c_planes(fj, st));
+    }
     return 0;
   }
 
@@ -276,6 +299,7 @@ class TcMlp : public MlpEngine {
     const int head_d_off = D * 256 + 128, head_rgb_off = head_d_off + 260, n_consts = head_rgb_off + 3 * 128 + 4;
     NERF_TRY(ensure_fconsts(params, st));
     const bool f16 = train && w16_;  // training in the w16 mode: every layer's activations leave as one fp16 plane
+    const bool f8c = f8c_ && split_ && (!train || f16);
     std::vector<__nv_bfloat16*> act_out(D + 1);
     for (int s = 0; s <= D; s++) act_out[s] = f16 ? lv.acts[s].f16 : lv.acts[s].hi;
     ProfScope ps(PC_MLP_FWD, st);
@@ -283,10 +307,13 @@ class TcMlp : public MlpEngine {
       std::vector<const __nv_bfloat16*> wlo(D + 1);
       std::vector<__nv_bfloat16*> act_lo(D + 1);
       for (int s = 0; s <= D; s++) { wlo[s] = wp_[s < D ? s : D + 1].lo; act_lo[s] = lv.acts[s].lo; }
+      if (f8c)
+        for (int s = 0; s <= D; s++) { wpl[s] = wf_[s < D ? s : D + 1].hi; wlo[s] = wf_[s < D ? s : D + 1].lo; }
+      if (train) act_x_scale_ = f8c ? 0.03125f : 1.0f;  // the fp16 planes the backward pass will read then hold 32 a
       return launch_mlp_fused_forward_split(epos.hi, epos.lo, pos_pitch_, edir.hi, edir.lo, dir_pitch_, wpl.data(),
                                             wlo.data(), kpad.data(), in_b.data(), D, s_.W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                             head_rgb_off, bias_off.data(), raw_density, raw_rgb, train ? act_out.data() : nullptr,
-                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st, f16);
+                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st, f16, f8c);
     }
     return launch_mlp_fused_forward(epos.hi, pos_pitch_, edir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
@@ -313,13 +340,16 @@ class TcMlp : public MlpEngine {
     const int D = s_.D, C = s_.C, W = s_.W, Wc = s_.Wc;
     Plane* cur = &dz_[0];
     Plane* nxt = &dz_[1];
-    float* sc = w16_ ? dz_sc_ + 2 * level : nullptr;  // [s, 1/s]: power-of-two scale of this level's fp16 dZ planes
+    // [s, 1/s, x/s]: power-of-two scale of this level's fp16 dZ planes, its inverse, and the inverse times the scale x the level's
+    // activation planes carry (1, or 1/32 when the fp8-correction forward wrote 32 a)
+    float* sc = w16_ ? dz_sc_ + 4 * level : nullptr;
     {  // rgb head
       const LayerInfo& L = s_.layers[D + C + 1];
       const Plane& x = lv.acts[D + C - 1];
       ProfScope ps(PC_MLP_HEADS_BWD, st);
-      if (w16_) NERF_TRY(launch_dz_scale(d_raw_rgb, d_raw_density, M, sc, dz_sc_scratch_, st));
-      NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, w16_ ? x.f16 : x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st, w16_));
+      if (w16_) NERF_TRY(launch_dz_scale(d_raw_rgb, d_raw_density, M, act_x_scale_, sc, dz_sc_scratch_, st));
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_rgb, w16_ ? x.f16 : x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 3, Wc, ws_, st, w16_,
+                                        act_x_scale_));
       NERF_TRY(launch_thin_dgrad_planes(d_raw_rgb, params + L.w_off, M, 3, Wc, lv.bits[D + C - 1], Wc / 32, cur->hi, cur->lo, cur->pitch, st,
                                         cur->f16, sc));
     }
@@ -397,30 +427,30 @@ class TcMlp : public MlpEngine {
         for (int j = 0; j < D; j++) { wt_lo[j] = wtp_[j == 0 ? D + 1 : D - j].lo; dz_lo[j] = dzs_[j].lo; }
         NERF_TRY(launch_mlp_fused_dgrad_split(dz_cond.hi, dz_cond.lo, dz_cond.pitch, wt.data(), wt_lo.data(), wt_pitch.data(), D, W, s_.Wc, M,
                                               fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), pair(), st,
-                                              w16_ ? dz_sc_ + 2 * level : nullptr));
+                                              w16_ ? dz_sc_ + 4 * level : nullptr));
       } else {
         NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                         d_raw_density, dz_out.data(), masks.data(), pair(), st));
       }
     }
-    wgrad_unscale_ = w16_ ? dz_sc_ + 2 * level + 1 : nullptr;
+    wgrad_unscale_ = w16_ ? dz_sc_ + 4 * level + 1 : nullptr;
     {  // condition layer
       const LayerInfo& L = s_.layers[D + 1];
       ProfScope ps(PC_MLP_WGRAD, st);
-      NERF_TRY(gemm_wgrad(dz_cond, lv.acts[D - 1], L.in_a, &lv.enc_dir, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
+      NERF_TRY(gemm_wgrad(dz_cond, lv.acts[D - 1], L.in_a, &lv.enc_dir, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st, true));
     }
     {  // density head
       const LayerInfo& L = s_.layers[D];
       const Plane& x = lv.acts[D - 1];
       ProfScope ps(PC_MLP_HEADS_BWD, st);
-      NERF_TRY(launch_thin_wgrad_planes(d_raw_density, w16_ ? x.f16 : x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 1, W, ws_, st, w16_));
+      NERF_TRY(launch_thin_wgrad_planes(d_raw_density, w16_ ? x.f16 : x.hi, x.lo, x.pitch, grads + L.w_off, grads + L.b_off, M, 1, W, ws_, st, w16_,
+                                        act_x_scale_));
     }
-    wgrad_unscale_ = w16_ ? dz_sc_ + 2 * level + 1 : nullptr;  // the fp16 dZ planes carry the level's scale: the reductions divide it out
     for (int i = D - 1; i >= 0; i--) {
       const LayerInfo& L = s_.layers[i];
       const Plane& in = i == 0 ? lv.enc_pos : lv.acts[i - 1];
       ProfScope ps(PC_MLP_WGRAD, st);
-      NERF_TRY(gemm_wgrad(dzs_[D - 1 - i], in, L.in_a, L.in_b ? &lv.enc_pos : nullptr, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st));
+      NERF_TRY(gemm_wgrad(dzs_[D - 1 - i], in, L.in_a, L.in_b ? &lv.enc_pos : nullptr, L.in_b, grads + L.w_off, grads + L.b_off, M, L.out, st, i > 0));
     }
     return 0;
   }
@@ -561,8 +591,9 @@ class TcMlp : public MlpEngine {
   }
 
   // dW[N, k1+k2] += dZ^T [X1|X2]; db += colsum(dZ).  MN-major operands, reduction over the M samples split over CTAs.
+  // x1_act (w16): x1 is an activation plane of the level (it may carry the fp8-correction forward's factor 32), not an encoding
   int gemm_wgrad(const Plane& dz, const Plane& x1, int k1, const Plane* x2, int k2, float* dW, float* db, long M, int N,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool x1_act = false) {
     const int ldw = k1 + k2;
     for (int src = 0; src < 2; src++) {
       const Plane* x = src == 0 ? &x1 : x2;
@@ -604,7 +635,10 @@ class TcMlp : public MlpEngine {
       ReduceJob job;
       job.ws = wsp; job.out = dW; job.ws2 = bias_here ? bias_ws : nullptr; job.out2 = db; job.stride = p.split_stride; job.stride2 = N;
       job.splits = splits; job.rows = N; job.cols = K; job.ldw = ldf; job.ldo = ldw; job.coff = coff; job.n2 = bias_here ? N : 0;
-      job.mul = w16_ ? wgrad_unscale_ : nullptr;
+      // w16: the fp16 dZ planes carry the level's scale s and an activation plane may carry 32: [1/s, x/s] at wgrad_unscale_.
+      // The bias gradient rides with src 0 and has no X factor, so it takes 1/s whatever x1 is.
+      job.mul = w16_ ? wgrad_unscale_ + ((src == 0 && x1_act) ? 1 : 0) : nullptr;
+      job.mul2 = w16_ ? wgrad_unscale_ : nullptr;
       if (defer_reduce_) pending_ = job;
       else NERF_TRY(launch_reduce_job(job, st));
     }
@@ -615,6 +649,9 @@ class TcMlp : public MlpEngine {
 
   bool split_;
   bool w16_ = false;                  // fp32-accurate mode: wgrad operands as fp16 planes (see init)
+  bool f8c_ = false;                  // fp32-accurate mode: fused forward with fp16 + E4M3 correction products (see init)
+  std::vector<Plane> wf_;             // f8c: W16 / W8 planes of the trunk layers and the condition layer
+  float act_x_scale_ = 1.0f;          // w16 + f8c: the activation planes hold 32 a
   float* dz_sc_ = nullptr;            // w16: per level [s, 1/s], then 2 scratch words of launch_dz_scale
   unsigned* dz_sc_scratch_ = nullptr;
   const float* wgrad_unscale_ = nullptr;  // w16: device scalar the wgrad reductions of the level being walked multiply by

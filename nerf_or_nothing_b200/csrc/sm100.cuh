@@ -215,5 +215,39 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
   return r;
 }
 
+// ---------------------------------------------------------------- fp8 (E4M3) correction products: kind::f8f6f4
+// Validated on the B200 by scripts/f8_mma_probe.cu: A in tensor memory = lane per row, FOUR consecutive k per 32-bit column
+// (byte 0 = lowest k), K = 32 per MMA = 8 columns; B in shared memory K-major, one 128-byte swizzled row = 128 k, +32 bytes per
+// K = 32 step; and MMAs of kind::f8f6f4 accumulate onto the same fp32 accumulator as MMAs of kind::f16.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {  // a_format = b_format = 0 (E4M3), both K-major
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// two values -> two E4M3 bytes (low byte = lo), round to nearest, saturating
+__device__ __forceinline__ uint32_t pack_e4m3x2_f32(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x2_f16x2(uint32_t h2) {  // h2: packed fp16 pair (low half first)
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+  return r;
+}
+
 }  // namespace sm100
 }  // namespace nerf

@@ -26,12 +26,14 @@ R, S = 512, 128
 # "fp32_tc+wgrad_fp16": the fp32-accurate mode with NERF_FLAG_WGRAD_FP16 (wgrad operands as fp16 planes, opt-in): same forward
 # bits, and on this real step the same 1e-4 on the gradient — whole vector AND every tensor against its own scale (CPU
 # simulation scripts/wgrad_fp16_precision.py: 7.7e-6 / worst tensor 5.1e-5)
-TOL = {"fp32_tc": 1e-4, "bf16": 2e-2, "fp32_tc+wgrad_fp16": 1e-4}
+FAST = "fp32_tc+wgrad_fp16(bf16x3 forward)"  # the same option with the fp8-correction forward switched off
+TOL = {"fp32_tc": 1e-4, "bf16": 2e-2, "fp32_tc+wgrad_fp16": 1e-4, FAST: 1e-4}
 # fraction of ReLU masks that may differ from fp64 (~ forward error / spread of the pre-activations)
-MAX_FLIPS = {"fp32_tc": 2e-5, "bf16": 1e-2, "fp32_tc+wgrad_fp16": 2e-5}  # measured 3.1e-6 / 1.1e-3
+MAX_FLIPS = {"fp32_tc": 2e-5, "bf16": 1e-2, "fp32_tc+wgrad_fp16": 2e-5, FAST: 2e-5}  # measured 3.1e-6 / 1.1e-3 / 4.8e-6 / 3.1e-6
 # whole-step gradient against the PLAIN fp64 gradient (masks free): kink-limited, see the module docstring
-RAW_TOL = {"fp32_tc": 1e-4, "bf16": 0.15, "fp32_tc+wgrad_fp16": 1e-4}  # fp32 path: north_star's 1e-4 holds on the plain gradient too at this batch size (1.9e-5 measured)
-MODES = {"fp32_tc": ("fp32_tc", 0), "bf16": ("bf16", 0), "fp32_tc+wgrad_fp16": ("fp32_tc", nb.FLAG_WGRAD_FP16)}
+RAW_TOL = {"fp32_tc": 1e-4, "bf16": 0.15, "fp32_tc+wgrad_fp16": 1e-4, FAST: 1e-4}  # fp32 path: north_star's 1e-4 holds on the plain gradient too at this batch size (1.9e-5 measured)
+MODES = {"fp32_tc": ("fp32_tc", 0), "bf16": ("bf16", 0), "fp32_tc+wgrad_fp16": ("fp32_tc", nb.FLAG_WGRAD_FP16),
+         FAST: ("fp32_tc", nb.FLAG_WGRAD_FP16 | nb.FLAG_NO_FP8_CORRECTIONS)}
 
 
 class _IntView:
@@ -62,7 +64,7 @@ def _torch_gradient(ocfg, params, rays, pix, t_levels, masks_levels=None, want_m
     return float(loss), g.cpu().numpy(), mo
 
 
-@pytest.mark.parametrize("precision", ["fp32_tc", "bf16", "fp32_tc+wgrad_fp16"])
+@pytest.mark.parametrize("precision", ["fp32_tc", "bf16", "fp32_tc+wgrad_fp16", FAST])
 def test_bench_configuration_whole_step_vs_fp64(precision):
     ncfg, ocfg = configs_pair(n_rays=R, precision=nb.PRECISIONS[MODES[precision][0]], n_samples=S, engine_flags=MODES[precision][1])
     assert (ncfg.net_depth, ncfg.net_width, ncfg.net_width_condition) == (8, 256, 128)  # the bench's network
@@ -110,7 +112,7 @@ def test_bench_configuration_whole_step_vs_fp64(precision):
     assert flipped / units <= MAX_FLIPS[precision]
     assert e_masked <= tol
     assert e_raw <= RAW_TOL[precision] if precision != "bf16" else np.linalg.norm(g - o64["grads"]) / np.linalg.norm(o64["grads"]) <= RAW_TOL[precision]
-    if precision == "fp32_tc+wgrad_fp16":
+    if precision in ("fp32_tc+wgrad_fp16", FAST):
         assert worst[0] <= tol, f"tensor {worst[1]}: {worst[0]:.2e} of its own scale"
 
 
@@ -126,7 +128,7 @@ def test_config1_loss_curve_against_cpu_oracle():
     ocfg = orc.default_config(n_samples=Ss)
     from nerf_or_nothing_b200.scene import synthetic_rays
 
-    models = {p: nb.AcceleratedMipNeRF(nb.default_config(n_rays=Rr, n_samples=Ss, precision=MODES[p][0], engine_flags=MODES[p][1])) for p in MODES}
+    models = {p: nb.AcceleratedMipNeRF(nb.default_config(n_rays=Rr, n_samples=Ss, precision=MODES[p][0], engine_flags=MODES[p][1])) for p in ("fp32_tc", "fp32_tc+wgrad_fp16", "bf16")}
     opts = {p: nb.AcceleratedAdamOptimizer(mm.GetLayerSizes()) for p, mm in models.items()}
     params = orc.init_params(ocfg, 7)
     for mm in models.values():

@@ -151,8 +151,9 @@ LAYERED = nb.FLAG_NO_FUSED_FORWARD | nb.FLAG_NO_FUSED_TRAIN_FORWARD | nb.FLAG_NO
 # + direction PE built by encoder warps inside the fused forward kernels) and the one with the stand-alone encode kernel
 ENC_ALL = nb.FLAG_FUSED_ENCODE_TRAIN  # encoder warps in the training forward too (rendering has them by default)
 SCHEDULES = [("bf16", 0), ("fp32_tc", 0), ("bf16", ENC_ALL), ("fp32_tc", ENC_ALL), ("bf16", nb.FLAG_NO_FUSED_ENCODE), ("fp32_tc", nb.FLAG_NO_FUSED_ENCODE),
-             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST)]
-SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast"]
+             ("fp32_tc", nb.FLAG_NO_WEIGHT_MULTICAST), ("bf16", nb.FLAG_NO_WEIGHT_MULTICAST), ("fp32_tc", nb.FLAG_NO_FP8_CORRECTIONS)]
+SCHED_IDS = ["bf16", "fp32_tc", "bf16-encoder-warps", "fp32_tc-encoder-warps", "bf16-encode-kernel", "fp32_tc-encode-kernel", "fp32_tc-no-multicast", "bf16-no-multicast",
+             "fp32_tc-bf16x3-render"]
 
 
 @pytest.mark.parametrize("net", list(NETS))
@@ -369,8 +370,9 @@ def test_wgrad_fp16_option_against_the_three_term_wgrad(net, S, R):
     pixels are the SAME BITS as without the flag — and on a real step (every gradient element a sum over thousands of samples)
     the parameter gradient stays within the mode's 1e-4 of the default three-term wgrad and of the fp64 oracle."""
     kw = dict(NETS[net], n_samples=S)
-    m, ncfg, ocfg = _model(R, "fp32_tc", engine_flags=W16, **kw)
-    m2, _, _ = _model(R, "fp32_tc", **kw)
+    bf16x3 = nb.FLAG_NO_FP8_CORRECTIONS  # the same forward kernels on both sides (the option alone also switches the forward products)
+    m, ncfg, ocfg = _model(R, "fp32_tc", engine_flags=W16 | bf16x3, **kw)
+    m2, _, _ = _model(R, "fp32_tc", engine_flags=bf16x3, **kw)
     rays, pix, u = batch(R, S)
     params = _params_with_biases(ocfg)
     g1, l1 = _gradient_step(m, params, rays, pix, u)
@@ -391,9 +393,10 @@ def test_wgrad_fp16_option_against_the_three_term_wgrad(net, S, R):
 def test_wgrad_fp16_option_is_reproducible_and_cluster_independent(R):
     """The fp16 planes go through the same per-warp TMA boxes: bit-identical between 2-CTA clusters and single CTAs, between
     runs, with more tiles than CTAs and on a ragged last tile."""
-    m, ncfg, ocfg = _model(R, "fp32_tc", engine_flags=W16, **NET)
-    m2, _, _ = _model(R, "fp32_tc", engine_flags=W16 | nb.FLAG_NO_WEIGHT_MULTICAST, **NET)
-    m3, _, _ = _model(R, "fp32_tc", **NET)
+    bf16x3 = nb.FLAG_NO_FP8_CORRECTIONS
+    m, ncfg, ocfg = _model(R, "fp32_tc", engine_flags=W16 | bf16x3, **NET)
+    m2, _, _ = _model(R, "fp32_tc", engine_flags=W16 | bf16x3 | nb.FLAG_NO_WEIGHT_MULTICAST, **NET)
+    m3, _, _ = _model(R, "fp32_tc", engine_flags=bf16x3, **NET)
     rays, pix, u = batch(R, ncfg.n_samples)
     params = _params_with_biases(ocfg)
     g1, l1 = _gradient_step(m, params, rays, pix, u)
@@ -449,3 +452,63 @@ def test_wgrad_fp16_option_needs_the_fused_fp32_accurate_path():
             continue
         with pytest.raises(nb.NerfError):
             nb.AcceleratedMipNeRF(nb.default_config(n_rays=8, precision=prec, engine_flags=flags, **NET))
+
+
+# ---------------------------------------------------------------------------------------------- fp16 + fp8-correction products
+NO_F8C = nb.FLAG_NO_FP8_CORRECTIONS
+
+
+@pytest.mark.parametrize("net", list(NETS))
+@pytest.mark.parametrize("flags", [0, nb.FLAG_NO_WEIGHT_MULTICAST, nb.FLAG_NO_FUSED_ENCODE], ids=["clusters", "single-ctas", "encode-kernel"])
+@pytest.mark.parametrize("R", [200, 700, 1], ids=["R200", "R700-many-tiles", "R1"])
+def test_fp8_corrections_render(R, flags, net):
+    """Rendering in the fp32-accurate mode computes a w as fp16 x fp16 plus two E4M3 correction products onto the same accumulator
+    (mlp_fused_split.cu, REP = 1; NERF_FLAG_NO_FP8_CORRECTIONS keeps the three bf16 products).  Rendered pixels must stay within
+    the mode's 1e-4 of the fp64 oracle — measured: as close as the bf16x3 kernels — and close to those kernels; ragged tiles,
+    more tiles than CTAs, clusters or single CTAs, encoder warps or the encode kernel."""
+    m, ncfg, ocfg = _model(64, "fp32_tc", engine_flags=flags, **NETS[net])
+    m2, _, _ = _model(64, "fp32_tc", engine_flags=NO_F8C, **NETS[net])
+    S = ncfg.n_samples
+    rays, pix, _ = batch(R, S)
+    params = _params_with_biases(ocfg)
+    m.set_params(params)
+    m2.set_params(params)
+    args = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    rgb, depth, acc = m.render(*args)
+    rgb2, depth2, acc2 = m2.render(*args)
+    ocfg.randomized = 0
+    o = orc.train_gradient(ocfg, params, rays, pix, np.zeros((2, R, S + 1), np.float32), with_backward=False, prec="f64")
+    print(f"{net} R={R}: fp8-corrections vs f64: rgb {np.abs(rgb - o['comp_rgb'][1]).max():.2e} acc {np.abs(acc - o['acc'][1]).max():.2e}; "
+          f"bf16x3 vs f64: rgb {np.abs(rgb2 - o['comp_rgb'][1]).max():.2e}; fp8-corrections vs bf16x3 {np.abs(rgb - rgb2).max():.2e}")
+    assert np.isfinite(rgb).all()
+    np.testing.assert_allclose(rgb, o["comp_rgb"][1], atol=1e-4)
+    np.testing.assert_allclose(acc, o["acc"][1], atol=1e-4)
+    np.testing.assert_allclose(depth, o["depth"][1], atol=1e-4 * float(rays["fars"].max()))
+    np.testing.assert_allclose(rgb, rgb2, atol=5e-5)
+    again = m.render(*args)
+    np.testing.assert_array_equal(again[0], rgb)
+
+
+@pytest.mark.parametrize("net", list(NETS))
+@pytest.mark.parametrize("S,R", [(64, 64), (128, 40)], ids=["S64", "S128"])
+def test_fp8_corrections_training_step(net, S, R):
+    """Training with NERF_FLAG_WGRAD_FP16 runs the fp8-correction forward too: it writes fp16(32 a) planes (the wgrad GEMMs divide
+    the factor out).  Against the same option on the bf16x3 forward the loss agrees to fp32 noise and the gradient to the few
+    ReLU masks that differ between two forward arithmetics (tests/test_bench_config_parity_gpu.py measures them: 4.8e-6 against
+    fp64, gradient on the same branches 7.6e-6)."""
+    kw = dict(NETS[net], n_samples=S)
+    m, ncfg, ocfg = _model(R, "fp32_tc", engine_flags=W16, **kw)
+    m2, _, _ = _model(R, "fp32_tc", engine_flags=W16 | NO_F8C, **kw)
+    rays, pix, u = batch(R, S)
+    params = _params_with_biases(ocfg)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
+    g1b, l1b = _gradient_step(m, params, rays, pix, u)
+    o64 = orc.train_gradient(ocfg, params, rays, pix, u, prec="f64")
+    per = _per_tensor(m, g1, g2)
+    print(f"{net} S={S}: fp8-corrections + fp16-wgrad vs default: loss {l1:.8f} / {l2:.8f} (f64 {o64['total_loss']:.8f}), gradient whole {rel_err(g1, g2):.2e}, "
+          f"worst tensor {max(per):.2e}; vs fp64 {rel_err(g1, o64['grads']):.2e} (default {rel_err(g2, o64['grads']):.2e})")
+    assert l1 == l1b
+    np.testing.assert_array_equal(g1, g1b)
+    assert abs(l1 - o64["total_loss"]) <= 1e-4 * o64["total_loss"]
+    assert np.isfinite(g1).all() and rel_err(g1, g2) <= 1e-3  # same bound as fused vs per-layer forward (test_fused_training_forward_matches_layered)
