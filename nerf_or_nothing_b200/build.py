@@ -19,7 +19,7 @@ OBJ = HERE / "_obj"
 LIB = HERE / "libnerfb200.so"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-                     "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+                     "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NERF_NVCC_DEFS", "").split()  # A/B builds: -DNAME=0
 
 
 def _nvcc() -> str:

@@ -34,6 +34,10 @@ constexpr int kWStageBytes = 128 * 128;           // [128 rows (N half) x 64 bf1
 constexpr int kEncBytes = 2 * 16384 + 16384;      // per tile: position encoding 2 boxes of [128 x 64], direction 1 box
 constexpr int kMaxSteps = 12;
 constexpr int kStageSlot = 4096;                  // per epilogue warp: one [32 rows x 64 bf16] store box
+#ifndef NERF_LATE_SHIP
+#define NERF_LATE_SHIP 1
+#endif
+constexpr bool kLateShipF = NERF_LATE_SHIP != 0;  // second-half epilogue: TMA-store the chunks after act_ready instead of between them
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -422,7 +426,11 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
             }
             const uint32_t out = act + h * 64;
             const float* hw = head_w + (st.head == 3 ? 0 : h * 128);
-            uint32_t ra[32], rb[32], pk[16];
+            // TRAIN with kLateShipF: the packed words wait in `held` (free here: the parked half went into ACT above) and the
+            // restaging + TMA stores of all four chunks move BEHIND the act_ready signal the next layer's k-blocks 2.. wait for
+            constexpr bool late = kLateShipF && TRAIN;
+            uint32_t ra[32], rb[32], pk1[16];
+            uint32_t* pk0 = late ? held : pk1; uint32_t* pkA = late ? held + 16 : pk1; uint32_t* pkB = late ? held + 32 : pk1; uint32_t* pkC = late ? held + 48 : pk1;
             tmem_ld_32x32(acc, ra);
             tmem_ld_wait();
             if (unpark) {  // the next layer's k-blocks 0,1 may start
@@ -432,26 +440,26 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
               if (lane == 0) mbar_arrive(&act_lo_ready);
             }
             tmem_ld_32x32(acc + 32, rb);
-            m0 = chunk(ra, 0, hw, pk);
-            if (st.produces) tmem_st_16(out, pk);
-            ship(h * 128, 0, pk);
+            m0 = chunk(ra, 0, hw, pk0);
+            if (st.produces) tmem_st_16(out, pk0);
+            if (!late) ship(h * 128, 0, pk0);
             tmem_ld_wait();
             tmem_ld_32x32(acc + 64, ra);
-            m1 = chunk(rb, 1, hw, pk);
-            if (st.produces) tmem_st_16(out + 16, pk);
-            ship(h * 128, 1, pk);
+            m1 = chunk(rb, 1, hw, pkA);
+            if (st.produces) tmem_st_16(out + 16, pkA);
+            if (!late) ship(h * 128, 1, pkA);
             tmem_ld_wait();
             tmem_ld_32x32(acc + 96, rb);
-            m2 = chunk(ra, 2, hw, pk);
-            if (st.produces) tmem_st_16(out + 32, pk);
-            ship(h * 128 + 64, 0, pk);
+            m2 = chunk(ra, 2, hw, pkB);
+            if (st.produces) tmem_st_16(out + 32, pkB);
+            if (!late) ship(h * 128 + 64, 0, pkB);
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty);
-            m3 = chunk(rb, 3, hw, pk);
+            m3 = chunk(rb, 3, hw, pkC);
             if (st.produces) {
-              tmem_st_16(out + 48, pk);
+              tmem_st_16(out + 48, pkC);
               tmem_st_wait();
               tc_fence_before_sync();
               __syncwarp();
@@ -460,7 +468,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsF : kThreadsFE, 1) k_mlp_f
                 mbar_arrive(&act_ready);
               }
             }
-            ship(h * 128 + 64, 1, pk);
+            if (late) { ship(h * 128, 0, pk0); ship(h * 128, 1, pkA); ship(h * 128 + 64, 0, pkB); }
+            ship(h * 128 + 64, 1, pkC);
           }
           if (MODE == 1 && row_ok) {
             uint32_t* bw = p.bits[s] + row * (st.n_cols >> 5) + h * 4;

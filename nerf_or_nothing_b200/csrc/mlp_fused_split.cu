@@ -35,6 +35,10 @@ constexpr int kNSInfer = 6, kNSTrain = 5;  // operand ring: 32 KB stages (a weig
 constexpr int kStageB = 256 * 128;        // 32 KB
 constexpr int kSlotB = 2 * 2048;          // per epilogue warp: one [32 x 32] hi box + one lo box
 constexpr int kMaxStepsS = 12;
+#ifndef NERF_LATE_SHIP
+#define NERF_LATE_SHIP 1
+#endif
+constexpr bool kLateShip = NERF_LATE_SHIP != 0;  // second-half epilogue: TMA-store the chunks after act_ready instead of between them
 
 __device__ __forceinline__ uint32_t pack2s(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -495,6 +499,33 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             ship(col_t, held_h, held_l, REP == 1 ? held_h : fw);
             m1 = chunk(r1, 1, held_h + 16, held_l + (REP == 1 ? 8 : 16), held_l + 24);
             ship(col_t + 32, held_h + 16, held_l + 16, REP == 1 ? held_h + 16 : fw);
+          } else if (kLateShip && TRAIN && !(F16 && REP == 0)) {
+            // The next layer's k-blocks 2.. wait for act_ready: everything that is not needed for it — restaging the two chunks
+            // in shared memory, waiting for the previous box to be read out, issuing the TMA stores — moves BEHIND the signal.
+            // The words wait in held_h / held_l, which are free here (the parked half went into ACT above).
+            const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
+            uint32_t* hw0 = held_h; uint32_t* lw0 = held_l; uint32_t* hw1 = held_h + 16; uint32_t* lw1 = held_l + 16;
+            m0 = chunk(r0, 0, hw0, lw0, lw0 + 8);
+            if (st.produces) {
+              tmem_st_16(ACT_HI + out, hw0);
+              if (REP == 1) { tmem_st_8(ACT_LO + out, lw0); tmem_st_8(ACT_LO + out + 16, lw0 + 8); }
+              else tmem_st_16(ACT_LO + out, lw0);
+            }
+            m1 = chunk(r1, 1, hw1, lw1, lw1 + 8);
+            if (st.produces) {
+              tmem_st_16(ACT_HI + out + 16, hw1);
+              if (REP == 1) { tmem_st_8(ACT_LO + out + 8, lw1); tmem_st_8(ACT_LO + out + 24, lw1 + 8); }
+              else tmem_st_16(ACT_LO + out + 16, lw1);
+              tmem_st_wait();
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) {
+                if (st.n_halves == 1) mbar_arrive(&act_lo_ready);
+                mbar_arrive(&act_ready);
+              }
+            }
+            ship(col_t, hw0, lw0, hw0);       // F16 here means REP == 1: the fp16 words are hw
+            ship(col_t + 32, hw1, lw1, hw1);
           } else {
             uint32_t hw[16], lw[16];
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
