@@ -38,6 +38,10 @@ constexpr int kMaxStepsS = 12;
 #ifndef NERF_LATE_SHIP
 #define NERF_LATE_SHIP 1
 #endif
+#ifndef NERF_DOUBLE_BOX
+#define NERF_DOUBLE_BOX 1
+#endif
+constexpr bool kDoubleBox = NERF_DOUBLE_BOX != 0;  // F16 kernels: two alternating store boxes per warp
 constexpr bool kLateShip = NERF_LATE_SHIP != 0;  // second-half epilogue: TMA-store the chunks after act_ready instead of between them
 
 __device__ __forceinline__ uint32_t pack2s(float a, float b) {
@@ -417,8 +421,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     // ------------------------------------------------------------------ epilogue: lane quarter warp % 4, column half warp / 4
     const int qtr = warp & 3, ch = warp >> 2;
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    uint8_t* slot = stage_buf + warp * kSlotB;   // TRAIN: [32 x 32] hi box + lo box
+    uint8_t* slot = stage_buf + warp * kSlotB;   // TRAIN: [32 x 32] hi box + lo box; F16: two alternating fp16 boxes
     uint8_t* slot_row = slot + lane * 64;
+    uint32_t n_ship = 0;                         // F16: boxes shipped by this warp (selects the half of the slot)
     const int swz = (lane >> 1) & 3;             // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
     uint32_t n_full[2] = {0, 0};
     for (int ti = 0, tile = blockIdx.x; ti < tiles_per_cta; ti++, tile += gridDim.x) {
@@ -435,12 +440,19 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
         // TRAIN: ship one 32-column chunk (both planes) of this warp's 32 rows
         auto ship = [&](int col, const uint32_t* hw, const uint32_t* lw, const uint32_t* fw) {
           if (!TRAIN) return;
-          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous box (pair) has been read out
+          // the box (pair) this one overwrites has been read out.  F16: one fp16 box is half a slot, so two boxes alternate and the
+          // warp only waits for the box before the previous one — the TMA engine's read-out latency leaves the warp's path
+          const uint32_t boff = (F16 && kDoubleBox) ? (n_ship & 1u) * 2048u : 0u;
+          n_ship++;
+          if (lane == 0) {
+            if (F16 && kDoubleBox) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (F16) {
-              *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(fw[4 * q], fw[4 * q + 1], fw[4 * q + 2], fw[4 * q + 3]);
+              *reinterpret_cast<uint4*>(slot_row + boff + ((q ^ swz) << 4)) = make_uint4(fw[4 * q], fw[4 * q + 1], fw[4 * q + 2], fw[4 * q + 3]);
             } else {
               *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
               *reinterpret_cast<uint4*>(slot_row + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.map_act[s][0], slot, col, row_w);
+            tma_store_2d(&p.map_act[s][0], slot + boff, col, row_w);
             if (!F16) tma_store_2d(&p.map_act[s][1], slot + 2048, col, row_w);
             tma_store_commit();
           }
