@@ -487,7 +487,10 @@ def measure_render(job, args, precision, steps=None):
     model.close()
     del db, rgb, depth, acc
     torch.cuda.empty_cache()
-    return {"value": total / (ms / 1e3), "unit": UNIT, "ms_per_image": ms, "steps": steps, "precision": precision, "rays": total,
+    arith = {"bf16": "bf16 products, fp32 accumulate", "fp32": "fp32 FFMA",
+             "fp32_tc": ("fp32-accurate split on tcgen05: fp16 x fp16 plus two E4M3 correction products per term onto one fp32 accumulator"
+                         if not (args.engine_flags & 256) else "fp32-accurate split on tcgen05: three bf16 products per term")}[precision]
+    return {"value": total / (ms / 1e3), "unit": UNIT, "ms_per_image": ms, "steps": steps, "precision": precision, "arithmetic": arith, "rays": total,
             "rays_per_gpu": n, "chunk_rays": chunk, "gpu_launches": int(launches), "clocks": clk,
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": n * 9 * 4, "d2h_bytes_per_step": n * 5 * 4},
             "from_pose": {"value": total / (ms_pose / 1e3), "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n * 5 * 4,

@@ -32,8 +32,15 @@ constexpr int kEncWarpsS = 2;             // forward kernels: + 2 encoder warps 
 constexpr int kThreadsSE = kThreadsS + 32 * kEncWarpsS;
 constexpr int kEpiWarps = 8;
 constexpr int kNSInfer = 6, kNSTrain = 5;  // operand ring: 32 KB stages (a weight plane tile [<=256 x 64], or an encoding k-block's hi|lo tiles)
+#ifndef NERF_DOUBLE_BOX_SPLIT
+#define NERF_DOUBLE_BOX_SPLIT 0
+#endif
+// hi/lo planes out (not F16): two alternating box PAIRS per warp (8 KB slots) paid for with one ring stage.  Measured (r02ab2, A/B in
+// one call): forward 3.39 vs 3.33 ms, dgrad chain 2.83 vs 2.86, step 10.86 vs 10.87 — no gain, compiled out
+constexpr bool kDoubleBoxSplit = NERF_DOUBLE_BOX_SPLIT != 0;
+__host__ __device__ constexpr int train_stages(bool f16) { return (!f16 && kDoubleBoxSplit) ? kNSTrain - 1 : kNSTrain; }
+__host__ __device__ constexpr int train_slot_bytes(bool f16) { return (!f16 && kDoubleBoxSplit) ? 8192 : 4096; }
 constexpr int kStageB = 256 * 128;        // 32 KB
-constexpr int kSlotB = 2 * 2048;          // per epilogue warp: one [32 x 32] hi box + one lo box
 constexpr int kMaxStepsS = 12;
 #ifndef NERF_LATE_SHIP
 #define NERF_LATE_SHIP 1
@@ -241,7 +248,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
   static_assert(REP == 0 || MODE == 0 || (MODE == 1 && F16), "fp8 corrections: inference forward, or training forward with fp16 planes out");
   constexpr bool TRAIN = MODE != 0;
   constexpr bool DGRAD = MODE == 2;
-  constexpr int NS = TRAIN ? kNSTrain : kNSInfer;
+  constexpr int NS = TRAIN ? train_stages(F16) : kNSInfer;
+  constexpr int kSlot = train_slot_bytes(F16);
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[NS], w_empty[NS], acc_full[2], acc_empty[2], act_ready, act_lo_ready, enc_ready[2], enc_free[2];
   __shared__ uint32_t tmem_base_smem;
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* w_ring = smem;                         // NS x 32 KB
   uint8_t* stage_buf = smem + NS * kStageB;       // TRAIN: 8 x 4 KB
-  float* s_const = reinterpret_cast<float*>(stage_buf + (TRAIN ? kEpiWarps * kSlotB : 0));
+  float* s_const = reinterpret_cast<float*>(stage_buf + (TRAIN ? kEpiWarps * kSlot : 0));
 
   const int n_tiles = (int)((p.M + 127) / 128);
   const int tiles_per_cta = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;  // the same for every CTA: rings stay in lock-step
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     // ------------------------------------------------------------------ epilogue: lane quarter warp % 4, column half warp / 4
     const int qtr = warp & 3, ch = warp >> 2;
     const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-    uint8_t* slot = stage_buf + warp * kSlotB;   // TRAIN: [32 x 32] hi box + lo box; F16: two alternating fp16 boxes
+    uint8_t* slot = stage_buf + warp * kSlot;    // TRAIN: two alternating [32 x 32] hi + lo box pairs; F16: two alternating fp16 boxes
     uint8_t* slot_row = slot + lane * 64;
     uint32_t n_ship = 0;                         // F16: boxes shipped by this warp (selects the half of the slot)
     const int swz = (lane >> 1) & 3;             // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
@@ -442,10 +450,11 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           if (!TRAIN) return;
           // the box (pair) this one overwrites has been read out.  F16: one fp16 box is half a slot, so two boxes alternate and the
           // warp only waits for the box before the previous one — the TMA engine's read-out latency leaves the warp's path
-          const uint32_t boff = (F16 && kDoubleBox) ? (n_ship & 1u) * 2048u : 0u;
+          constexpr bool dbl = F16 ? kDoubleBox : kDoubleBoxSplit;
+          const uint32_t boff = dbl ? (n_ship & 1u) * (F16 ? 2048u : 4096u) : 0u;
           n_ship++;
           if (lane == 0) {
-            if (F16 && kDoubleBox) tma_store_wait_read<1>();
+            if (dbl) tma_store_wait_read<1>();
             else tma_store_wait_read<0>();
           }
           __syncwarp();
@@ -454,15 +463,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             if (F16) {
               *reinterpret_cast<uint4*>(slot_row + boff + ((q ^ swz) << 4)) = make_uint4(fw[4 * q], fw[4 * q + 1], fw[4 * q + 2], fw[4 * q + 3]);
             } else {
-              *reinterpret_cast<uint4*>(slot_row + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-              *reinterpret_cast<uint4*>(slot_row + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+              *reinterpret_cast<uint4*>(slot_row + boff + ((q ^ swz) << 4)) = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+              *reinterpret_cast<uint4*>(slot_row + boff + 2048 + ((q ^ swz) << 4)) = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
             }
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&p.map_act[s][0], slot + boff, col, row_w);
-            if (!F16) tma_store_2d(&p.map_act[s][1], slot + 2048, col, row_w);
+            if (!F16) tma_store_2d(&p.map_act[s][1], slot + boff + 2048, col, row_w);
             tma_store_commit();
           }
         };
@@ -617,7 +626,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
     return 100001;
   }
   const bool train = act_hi != nullptr;
-  const size_t smem = (size_t)(train ? kNSTrain : kNSInfer) * kStageB + (train ? kEpiWarps * kSlotB : 0) + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
+  const size_t smem = (size_t)(train ? train_stages(act_f16) : kNSInfer) * kStageB + (train ? kEpiWarps * train_slot_bytes(act_f16) : 0) +
+                      (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   const int sms = device_sm_count();
   if (smem > 218 * 1024) { set_error("fused forward: %zu bytes of shared memory needed", smem); return 100001; }
   SplitParams p;
@@ -681,7 +691,8 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   const bool f16 = dz_scale_f16 != nullptr;  // dz_out_hi[s] is then ONE fp16 plane holding dZ * *dz_scale_f16 (dz_out_lo unused)
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
-  const size_t smem = (size_t)kNSTrain * kStageB + kEpiWarps * kSlotB + (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
+  const size_t smem = (size_t)train_stages(dz_scale_f16 != nullptr) * kStageB + kEpiWarps * train_slot_bytes(dz_scale_f16 != nullptr) +
+                      (size_t)((n_consts + 3) / 4 * 4) * sizeof(float) + 1024;
   if (smem > 218 * 1024) { set_error("fused dgrad: %zu bytes of shared memory needed", smem); return 100001; }
   SplitParams p;
   memset(&p, 0, sizeof(p));
