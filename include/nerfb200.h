@@ -94,6 +94,9 @@ typedef struct nerf_config {
                                               * and holds for |activation| < 2047, |weight| < 64 (beyond, values saturate instead of overflowing);
                                               * it runs in rendering, and in training when NERF_FLAG_WGRAD_FP16 is set */
 
+#define NERF_FLAG_PAIR_MMA 512u              /* fp32-accurate fused kernels: the 2-CTA clusters issue tcgen05.mma.cta_group::2 (one MMA for both
+                                              * tiles, each SM holding half of every weight tile) instead of sharing whole tiles by multicast */
+
 typedef struct nerf_mipnerf nerf_mipnerf;   /* AcceleratedMipNeRF + its embedded AcceleratedMLP */
 typedef struct nerf_adam nerf_adam;         /* AcceleratedAdamOptimizer */
 typedef struct nerf_gradcalc nerf_gradcalc; /* AcceleratedGradientCalculator */

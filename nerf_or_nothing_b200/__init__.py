@@ -30,7 +30,7 @@ PRECISIONS = {"fp32": PRECISION_FP32, "fp32_tc": PRECISION_FP32_TC, "bf16": PREC
 COMM_ID_BYTES = 128
 # nerf_config.engine_flags (include/nerfb200.h)
 FLAG_NO_FUSED_FORWARD, FLAG_NO_FUSED_TRAIN_FORWARD, FLAG_NO_FUSED_DGRAD, FLAG_NO_DEFERRED_REDUCE, FLAG_NO_FUSED_ENCODE = 1, 2, 4, 8, 16
-FLAG_FUSED_ENCODE_TRAIN, FLAG_NO_WEIGHT_MULTICAST, FLAG_WGRAD_FP16, FLAG_NO_FP8_CORRECTIONS = 32, 64, 128, 256
+FLAG_FUSED_ENCODE_TRAIN, FLAG_NO_WEIGHT_MULTICAST, FLAG_WGRAD_FP16, FLAG_NO_FP8_CORRECTIONS, FLAG_PAIR_MMA = 32, 64, 128, 256, 512
 
 
 class NerfError(RuntimeError):

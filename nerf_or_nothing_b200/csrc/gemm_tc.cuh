@@ -106,7 +106,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
                                    uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st,
-                                   bool act_f16 = false, bool fp8c = false);
+                                   bool act_f16 = false, bool fp8c = false, bool pair_mma = false);
 // fp8c: the activations stay on chip as fp16 + two E4M3 correction planes and w_hi / w_lo are the matching W16 / W8 weight planes
 // (launch_f32_to_f8c_planes): two MMA-equivalents per product instead of three (mlp_fused_split.cu, REP = 1)
 struct F8cJobs {
@@ -121,7 +121,8 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, cudaStream_t st, const float* dz_scale_f16 = nullptr);
+                                 bool pair, cudaStream_t st, const float* dz_scale_f16 = nullptr, bool pair_mma = false);
+// pair_mma (with pair): the 2-CTA clusters run tcgen05.mma.cta_group::2 — each SM holds half of every weight tile (mlp_fused_split.cu, PM)
 // dz_scale_f16 != nullptr: dz_out_hi[s] is ONE fp16 plane that receives dZ * *dz_scale_f16 (device scalar, launch_dz_scale)
 
 // helpers on bf16 planes ------------------------------------------------------------------------------

@@ -23,6 +23,17 @@
 #include "sm100.cuh"
 
 namespace nerf {
+#ifdef NERF_SPLIT_DBG
+// debug builds only (scripts/split_stamps.py): clock64 stamps of epilogue warp 0 / MMA warp of CTA 0 for its 4th tile
+__device__ unsigned long long g_split_dbg[16 * 2 * 8];
+__device__ unsigned long long g_split_dbg_mma[16 * 2 * 4];
+#define DBG_STAMP(cond, s_, h_, i_) do { if ((cond) && lane == 0) g_split_dbg[((s_) * 2 + (h_)) * 8 + (i_)] = clock64(); } while (0)
+#define DBG_STAMP_MMA(cond, s_, h_, i_) do { if ((cond) && leader) g_split_dbg_mma[((s_) * 2 + (h_)) * 4 + (i_)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(cond, s_, h_, i_) do { } while (0)
+#define DBG_STAMP_MMA(cond, s_, h_, i_) do { } while (0)
+#endif
+
 namespace {
 
 using namespace sm100;
@@ -61,6 +72,7 @@ __device__ __forceinline__ uint32_t pack2s(float a, float b) {
 struct alignas(64) SplitParams {
   CUtensorMap map_pos[2], map_dir[2];         // [hi, lo] encodings [M, 128] / [M, 64], box {64, 128}
   CUtensorMap map_w[kMaxStepsS][2];           // [hi, lo] weight planes [N, Kpad], box {64, 128}
+  CUtensorMap map_w64[kMaxStepsS][2];         // the same planes, box {64, 64}: pair-MMA kernels, each CTA of a pair fetches 64 rows of a tile
   CUtensorMap map_act[kMaxStepsS][2];         // training: [hi, lo] activation planes [M, N], box {32, 32} (SWIZZLE_64B)
   uint32_t* bits[kMaxStepsS];                 // training: ReLU bit planes [M, N/32]
   struct Step {
@@ -80,6 +92,7 @@ struct alignas(64) SplitParams {
   // F16 kernels (the wgrad GEMMs multiply fp16 planes, see mlp_tc.cu): map_act[s][0] views ONE fp16 plane per layer; the dgrad
   // chain stores fp16(dZ * *dz_scale), a power of two chosen per level from the head gradients (launch_dz_scale)
   const float* dz_scale;
+  int pair_mma;  // host: launch the PM kernels (cta_group::2 MMAs; needs the 2-CTA clusters)
   // forward only — in-kernel cast_rays + IPE + direction PE (see FusedParams::enc_mode in mlp_fused.cu): 0 = planes written by
   // another kernel, 1 = the encoder warps write the level's hi/lo planes, 2 = a per-CTA double-buffered scratch (128 rows each)
   int enc_mode;
@@ -241,9 +254,18 @@ __device__ __forceinline__ uint32_t f8c_chunk(const uint32_t (&r)[32], const flo
 // F16 (training modes): what leaves the SM for the wgrad GEMMs is ONE fp16 plane per layer (activations, or dZ times the level's
 // power-of-two scale) instead of the hi + lo bf16 planes — half the store traffic here, half the read traffic and one MMA
 // instead of three there.  Everything on chip (ACT_hi | ACT_lo, the three-term products) is unchanged.
-template <int MODE, int CL, bool F16, int REP = 0>
+// PM (pair MMA, CL = 2): the cluster's rank-0 CTA issues every MMA for BOTH tiles with tcgen05.mma.cta_group::2 (M = 256: its own 128
+// rows and the peer's, each CTA's A operand and accumulator in its own tensor memory), and each CTA holds only ITS 64 rows of a
+// stage's [128 x 64] weight tile — the tensor core reads the two halves from the two shared memories.  Every SM then pulls
+// half the weight bytes through L2 (the CL = 2 multicast kernels still deliver the whole tile to each SM; in-kernel stamps
+// showed their MMAs paced by that stream, 83 cycles per MMA instead of 64).  Protocol differences: a stage's TMA loads of both
+// CTAs signal the LEADER's w_full (cp.async.bulk.tensor ... cta_group::2); the leader's commits release the slot and publish
+// the accumulators in both CTAs (multicast); the peer's epilogue warps arrive on the leader's acc_empty / act_lo_ready / act_ready
+// (counts doubled) through the cluster address; the leader returns the peer's encoding scratch buffer too.
+template <int MODE, int CL, bool F16, int REP = 0, bool PM = false>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_fused_split(const __grid_constant__ SplitParams p) {
   static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
+  static_assert(!PM || CL == 2, "pair MMA needs the 2-CTA cluster");
   static_assert(!F16 || MODE != 0, "the fp16 planes exist in the training kernels only");
   static_assert(REP == 0 || MODE == 0 || (MODE == 1 && F16), "fp8 corrections: inference forward, or training forward with fp16 planes out");
   constexpr bool TRAIN = MODE != 0;
@@ -267,21 +289,23 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
   constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
-    for (int h = 0; h < 2; h++) { mbar_init(&acc_full[h], 1); mbar_init(&acc_empty[h], kEpiWarps); }
-    mbar_init(&act_ready, kEpiWarps);
-    mbar_init(&act_lo_ready, kEpiWarps);
+    constexpr int kEpiArrivals = PM ? 2 * kEpiWarps : kEpiWarps;  // PM: the leader's MMA warp waits for both CTAs' epilogues
+    for (int s = 0; s < NS; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], PM ? 1 : CL); }
+    for (int h = 0; h < 2; h++) { mbar_init(&acc_full[h], 1); mbar_init(&acc_empty[h], kEpiArrivals); }
+    mbar_init(&act_ready, kEpiArrivals);
+    mbar_init(&act_lo_ready, kEpiArrivals);
     for (int b = 0; b < 2; b++) { mbar_init(&enc_ready[b], kEncWarpsS); mbar_init(&enc_free[b], 1); }
     fence_barrier_init();
   }
   // REP = 1: the biases (everything before the density head's weights) are staged as 32 b, see f8c_chunk
   for (int i = threadIdx.x; i < p.n_consts; i += blockDim.x) s_const[i] = __ldg(p.consts + i) * ((REP == 1 && i < p.head_d_off) ? 32.f : 1.f);
   if (warp == kEpiWarps) {
-    tmem_alloc<512>(&tmem_base_smem);
+    if (PM) tmem_alloc_pair<512>(&tmem_base_smem);
+    else tmem_alloc<512>(&tmem_base_smem);
     if (lane == 0) {
       for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_pos[q]); if (!DGRAD) prefetch_tmap(&p.map_dir[q]); }
       for (int s = 0; s < p.n_steps; s++)
-        for (int q = 0; q < 2; q++) { prefetch_tmap(&p.map_w[s][q]); if (TRAIN && (q == 0 || !F16)) prefetch_tmap(&p.map_act[s][q]); }
+        for (int q = 0; q < 2; q++) { prefetch_tmap(PM ? &p.map_w64[s][q] : &p.map_w[s][q]); if (TRAIN && (q == 0 || !F16)) prefetch_tmap(&p.map_act[s][q]); }
     }
   }
   tc_fence_before_sync();
@@ -308,15 +332,30 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
               if (kb >= st.n_act_kb) {  // encoding k-block: A_hi | A_lo
                 const int ws = it % NS;
                 mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);
-                mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
                 const CUtensorMap* me = st.enc_kind == 2 ? p.map_dir : p.map_pos;
                 const int ecol = (kb - st.n_act_kb) * 64;
-                tma_load_2d(w_ring + (size_t)ws * kStageB, &me[0], ecol, row0, &w_full[ws]);
-                tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &me[1], ecol, row0, &w_full[ws]);
+                if (PM) {  // each CTA its own rows; all four boxes of the pair complete on the leader's barrier
+                  if (cta_rank == 0) mbar_arrive_expect_tx(&w_full[ws], 4 * 16384);
+                  const uint32_t lb = map_to_cta(&w_full[ws], 0);
+                  tma_load_2d_pair(w_ring + (size_t)ws * kStageB, &me[0], ecol, row0, lb);
+                  tma_load_2d_pair(w_ring + (size_t)ws * kStageB + 16384, &me[1], ecol, row0, lb);
+                } else {
+                  mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);
+                  tma_load_2d(w_ring + (size_t)ws * kStageB, &me[0], ecol, row0, &w_full[ws]);
+                  tma_load_2d(w_ring + (size_t)ws * kStageB + 16384, &me[1], ecol, row0, &w_full[ws]);
+                }
                 it++;
               }
               const int ws = it % NS;  // W_hi | W_lo rows [128 h, 128 h + 128) of this k-block
               mbar_wait(&w_empty[ws], ((it / NS) & 1) ^ 1);   // every CTA of the cluster has consumed this slot
+              if (PM) {  // this CTA's 64 rows of W_hi | W_lo (8 KB each); the pair's four boxes complete on the leader's barrier
+                if (cta_rank == 0) mbar_arrive_expect_tx(&w_full[ws], 4 * 8192);
+                const uint32_t lb = map_to_cta(&w_full[ws], 0);
+                tma_load_2d_pair(w_ring + (size_t)ws * kStageB, &p.map_w64[s][0], kb * 64, h * 128 + (int)cta_rank * 64, lb);
+                tma_load_2d_pair(w_ring + (size_t)ws * kStageB + 8192, &p.map_w64[s][1], kb * 64, h * 128 + (int)cta_rank * 64, lb);
+                it++;
+                continue;
+              }
               mbar_arrive_expect_tx(&w_full[ws], 2 * 16384);  // both boxes land here, whoever fetches them
               if (CL == 1) {
                 tma_load_2d(w_ring + (size_t)ws * kStageB, &p.map_w[s][0], kb * 64, h * 128, &w_full[ws]);
@@ -332,34 +371,42 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     }
   } else if (warp == kEpiWarps + 1) {
     // ------------------------------------------------------------------ MMA issuer (uniform warp, one elected lane issues)
-    const bool leader = elect_one();
+    const bool leader = elect_one() && (!PM || cta_rank == 0);  // PM: the peer's MMA warp issues nothing
     const uint64_t desc0 = make_smem_desc(0, 16, 1024);
     const uint32_t ring_base = smem_u32(w_ring);
-    const uint32_t idesc = make_idesc_bf16(128, 128, false, false);
-    const uint32_t idesc_h = make_idesc_f16(128, 128, false, false), idesc_8 = make_idesc_e4m3(128, 128);
+    constexpr int kM = PM ? 256 : 128;                 // PM: one MMA covers both CTAs' tiles
+    constexpr uint32_t kLoOff = PM ? 8192 : 16384;     // W_lo (W8) tile behind W_hi (W16) in a stage: 64 or 128 rows of 128 bytes
+    const uint32_t idesc = make_idesc_bf16(kM, 128, false, false);
+    const uint32_t idesc_h = make_idesc_f16(kM, 128, false, false), idesc_8 = make_idesc_e4m3(kM, 128);
     uint32_t it = 0, n_acc[2] = {0, 0}, n_act = 0, tl = 0;
     // a ring slot is released in EVERY CTA of the cluster: the peer may multicast into this CTA's slot only when both are done
     auto release = [&](uint64_t* bar) {
-      if (CL == 1) umma_commit(bar);
+      if (PM) umma_pair_commit(bar, kAllCtas);
+      else if (CL == 1) umma_commit(bar);
       else umma_commit_multicast(bar, kAllCtas);
     };
-    for (; (int)tl < tiles_per_cta; tl++) {
+    auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t accf) { if (PM) umma_pair_ts(d, a, b, id, accf); else umma_bf16_ts(d, a, b, id, accf); };
+    auto mma_ts8 = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t accf) { if (PM) umma_pair_f8_ts(d, a, b, id, accf); else umma_f8_ts(d, a, b, id, accf); };
+    auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accf) { if (PM) umma_pair_ss(d, a, b, id, accf); else umma_bf16(d, a, b, id, accf); };
+    auto wait_epi = [&](uint64_t* bar, uint32_t parity) { if (PM) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };  // PM: the peer's epilogue arrives too
+    for (; (int)tl < tiles_per_cta && (!PM || cta_rank == 0); tl++) {
       for (int s = 0; s < p.n_steps; s++) {
         const SplitParams::Step st = p.steps[s];
         const int n_kb = st.n_act_kb + st.n_enc_kb;
         for (int h = 0; h < st.n_halves; h++) {
-          mbar_wait(&acc_empty[h], (n_acc[h] & 1) ^ 1);
+          wait_epi(&acc_empty[h], (n_acc[h] & 1) ^ 1);
           n_acc[h]++;
           // the layer below rewrites ACT in two instalments: its first N-half (= this layer's k-blocks 0,1; parked in
           // registers during its second half's MMAs) lands as soon as those MMAs are complete, its second N-half when that
           // half's epilogue is done — this layer's first k-blocks run under that epilogue instead of after it
           const bool wait_act = h == 0 && st.n_act_kb > 0;
-          if (wait_act) mbar_wait(&act_lo_ready, n_act & 1);
+          if (wait_act) wait_epi(&act_lo_ready, n_act & 1);
           tc_fence_after_sync();
           const uint32_t acc = ACC + 128 * h;
+          DBG_STAMP_MMA(blockIdx.x == 0 && tl == 3 && MODE == 1, s, h, 0);
           for (int kb = 0; kb < n_kb; kb++) {
             const bool from_act = kb < st.n_act_kb;
-            if (wait_act && kb == st.n_act_kb / 2) { mbar_wait(&act_ready, n_act & 1); tc_fence_after_sync(); }
+            if (wait_act && kb == st.n_act_kb / 2) { DBG_STAMP_MMA(blockIdx.x == 0 && tl == 3 && MODE == 1, s, h, 1); wait_epi(&act_ready, n_act & 1); tc_fence_after_sync(); DBG_STAMP_MMA(blockIdx.x == 0 && tl == 3 && MODE == 1, s, h, 2); }
             uint32_t a_stage = 0, a_hi = 0;
             if (!from_act) {  // the encoding tiles of this k-block arrive in their own stage
               a_stage = it % NS;
@@ -370,27 +417,27 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             const uint32_t ws = it % NS;
             mbar_wait(&w_full[ws], (it / NS) & 1);
             tc_fence_after_sync();
-            const uint64_t dbh = desc0 + ((ring_base + ws * kStageB) >> 4), dbl = dbh + (16384 >> 4);
+            const uint64_t dbh = desc0 + ((ring_base + ws * kStageB) >> 4), dbl = dbh + (kLoOff >> 4);
             if (leader) {
               if (from_act && REP == 1) {  // fp16 main product, then the two E4M3 correction products (K = 32 each)
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc_h, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < 4; k++) mma_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc_h, (kb | k) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; k++) umma_f8_ts(acc, ACT_LO + kb * 32 + k * 8, dbl + 2 * k, idesc_8, 1u);
+                for (int k = 0; k < 4; k++) mma_ts8(acc, ACT_LO + kb * 32 + k * 8, dbl + 2 * k, idesc_8, 1u);
               } else if (from_act) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {  // hi*hi + lo*hi + hi*lo
-                  umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                  umma_bf16_ts(acc, ACT_LO + kb * 32 + k * 8, dbh + 2 * k, idesc, 1u);
-                  umma_bf16_ts(acc, ACT_HI + kb * 32 + k * 8, dbl + 2 * k, idesc, 1u);
+                  mma_ts(acc, ACT_HI + kb * 32 + k * 8, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                  mma_ts(acc, ACT_LO + kb * 32 + k * 8, dbh + 2 * k, idesc, 1u);
+                  mma_ts(acc, ACT_HI + kb * 32 + k * 8, dbl + 2 * k, idesc, 1u);
                 }
               } else {
                 const uint64_t dah = desc0 + (a_hi >> 4), dal = dah + (16384 >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                  umma_bf16(acc, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                  umma_bf16(acc, dal + 2 * k, dbh + 2 * k, idesc, 1u);
-                  umma_bf16(acc, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+                  mma_ss(acc, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                  mma_ss(acc, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+                  mma_ss(acc, dah + 2 * k, dbl + 2 * k, idesc, 1u);
                 }
                 release(&w_empty[a_stage]);
               }
@@ -399,11 +446,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             it++;
           }
           if (wait_act) n_act++;
-          if (leader) umma_commit(&acc_full[h]);
+          if (leader) { if (PM) umma_pair_commit(&acc_full[h], kAllCtas); else umma_commit(&acc_full[h]); }  // PM: both CTAs' epilogues
+          DBG_STAMP_MMA(blockIdx.x == 0 && tl == 3 && MODE == 1, s, h, 3);
         }
       }
       // every encoding stage of this tile has been waited for (w_full): its rows have left the scratch buffer tl & 1
-      if (!DGRAD && p.enc_mode && leader) mbar_arrive(&enc_free[tl & 1]);
+      if (!DGRAD && p.enc_mode && leader) {
+        mbar_arrive(&enc_free[tl & 1]);
+        if (PM) mbar_arrive_cluster(map_to_cta(&enc_free[tl & 1], 1));  // the peer's tile went through the same w_full barriers
+      }
     }
     __syncwarp();
   } else if (warp >= kEpiWarps + 2) {
@@ -434,6 +485,11 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
     uint32_t n_ship = 0;                         // F16: boxes shipped by this warp (selects the half of the slot)
     const int swz = (lane >> 1) & 3;             // SWIZZLE_64B: 16-byte chunk index ^ address bits [7:8]
     uint32_t n_full[2] = {0, 0};
+    // signals to the MMA warp: this CTA's, or (PM) the leader's through its cluster address — the leader issues for both tiles
+    auto arrive_mma = [&](uint64_t* bar) {
+      if (PM) mbar_arrive_cluster(map_to_cta(bar, 0));
+      else mbar_arrive(bar);
+    };
     for (int ti = 0, tile = blockIdx.x; ti < tiles_per_cta; ti++, tile += gridDim.x) {
       const int row_w = tile * 128 + qtr * 32;
       const int row_t = qtr * 32 + lane;         // row within the tile
@@ -495,9 +551,12 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             }
             return split_chunk<MODE == 1, F16>(r, bias + c * 32, st.head, head_w + c * 32, head, hw_, lw_, fw);
           };
+          const bool dbg = blockIdx.x == 0 && ti == 3 && warp == 0 && MODE == 1;
+          DBG_STAMP(dbg, s, h, 0);
           mbar_wait(&acc_full[h], n_full[h] & 1);
           n_full[h]++;
           tc_fence_after_sync();
+          DBG_STAMP(dbg, s, h, 1);
           const bool unpark = last_half && st.n_halves == 2 && st.produces;
           if (unpark) {  // every MMA of the layer is complete: ACT is rewritten in place
             tmem_st_16(ACT_HI + lane_off + ch * 32, held_h); tmem_st_16(ACT_HI + lane_off + ch * 32 + 16, held_h + 16);
@@ -511,15 +570,20 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(&acc_empty[h]);                 // accumulator half in registers: its next MMAs may start
-            if (unpark) mbar_arrive(&act_lo_ready);     // the next layer's k-blocks 0,1 may start
+            arrive_mma(&acc_empty[h]);                  // accumulator half in registers: its next MMAs may start
+            if (unpark) arrive_mma(&act_lo_ready);      // the next layer's k-blocks 0,1 may start
           }
+          DBG_STAMP(dbg, s, h, 2);
           if (!last_half) {
             // REP = 1: held_l = [E4M3(al) chunk 0 | chunk 1 | E4M3(ah) chunk 0 | chunk 1] = the 32 ACT8 columns of this k-block
             m0 = chunk(r0, 0, held_h, held_l, held_l + 16);
+            DBG_STAMP(dbg, s, h, 3);
             ship(col_t, held_h, held_l, REP == 1 ? held_h : fw);
+            DBG_STAMP(dbg, s, h, 4);
             m1 = chunk(r1, 1, held_h + 16, held_l + (REP == 1 ? 8 : 16), held_l + 24);
+            DBG_STAMP(dbg, s, h, 5);
             ship(col_t + 32, held_h + 16, held_l + 16, REP == 1 ? held_h + 16 : fw);
+            DBG_STAMP(dbg, s, h, 6);
           } else if (kLateShip && TRAIN && !(F16 && REP == 0)) {
             // The next layer's k-blocks 2.. wait for act_ready: everything that is not needed for it — restaging the two chunks
             // in shared memory, waiting for the previous box to be read out, issuing the TMA stores — moves BEHIND the signal.
@@ -527,6 +591,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
             uint32_t* hw0 = held_h; uint32_t* lw0 = held_l; uint32_t* hw1 = held_h + 16; uint32_t* lw1 = held_l + 16;
             m0 = chunk(r0, 0, hw0, lw0, lw0 + 8);
+            DBG_STAMP(dbg, s, h, 3);
             if (st.produces) {
               tmem_st_16(ACT_HI + out, hw0);
               if (REP == 1) { tmem_st_8(ACT_LO + out, lw0); tmem_st_8(ACT_LO + out + 16, lw0 + 8); }
@@ -541,12 +606,15 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) {
-                if (st.n_halves == 1) mbar_arrive(&act_lo_ready);
-                mbar_arrive(&act_ready);
+                if (st.n_halves == 1) arrive_mma(&act_lo_ready);
+                arrive_mma(&act_ready);
               }
             }
+            DBG_STAMP(dbg, s, h, 4);
             ship(col_t, hw0, lw0, hw0);       // F16 here means REP == 1: the fp16 words are hw
+            DBG_STAMP(dbg, s, h, 5);
             ship(col_t + 32, hw1, lw1, hw1);
+            DBG_STAMP(dbg, s, h, 6);
           } else {
             uint32_t hw[16], lw[16];
             const uint32_t out = lane_off + (uint32_t)(col_t >> 1);
@@ -566,8 +634,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) {
-                if (st.n_halves == 1) mbar_arrive(&act_lo_ready);  // a one-half layer has no parked first instalment
-                mbar_arrive(&act_ready);
+                if (st.n_halves == 1) arrive_mma(&act_lo_ready);  // a one-half layer has no parked first instalment
+                arrive_mma(&act_ready);
               }
             }
             ship(col_t + 32, hw, lw, REP == 1 ? hw : fw);
@@ -596,13 +664,14 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsS : kThreadsSE, 1) k_mlp_f
   tc_fence_before_sync();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
-  if (warp == kEpiWarps) tmem_dealloc<512>(tmem_base);
+  if (warp == kEpiWarps) { if (PM) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
 
 template <int MODE, bool F16, int REP = 0>
 int launch_split(const SplitParams& p, int grid, int threads, size_t smem, bool pair, cudaStream_t st) {
-  const void* kern = pair ? (const void*)k_mlp_fused_split<MODE, 2, F16, REP> : (const void*)k_mlp_fused_split<MODE, 1, F16, REP>;
+  const void* kern = pair ? (p.pair_mma ? (const void*)k_mlp_fused_split<MODE, 2, F16, REP, true> : (const void*)k_mlp_fused_split<MODE, 2, F16, REP, false>)
+                          : (const void*)k_mlp_fused_split<MODE, 1, F16, REP, false>;
   SplitParams pp = p;
   return launch_persistent_clusters(kern, grid, threads, smem, 218 * 1024, pair ? 2 : 1, &pp, st);
 }
@@ -617,7 +686,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
                                    const float* consts_dev, int n_consts, int head_d_off, int head_rgb_off, const int* bias_off,
                                    float* raw_density, float* raw_rgb, __nv_bfloat16* const* act_hi, __nv_bfloat16* const* act_lo,
                                    uint32_t* const* bits_out, const RaySource* rays, long enc_scratch_rows, bool pair, cudaStream_t st,
-                                   bool act_f16, bool fp8c) {
+                                   bool act_f16, bool fp8c, bool pair_mma) {
   // fp8c: w_hi[s] / w_lo[s] are the W16 / W8 planes of f8c_chunk's representation (launch_f32_to_f8c_planes); training needs act_f16
   if (fp8c && act_hi && !act_f16) { set_error("fused forward: fp8 corrections in training need the fp16 activation planes"); return 100001; }
   if (act_f16 && (!act_hi || rays)) { set_error("fused forward: fp16 activation planes are a training option with the encode kernel"); return 100001; }
@@ -657,6 +726,8 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
     const int N = s < D ? W : Wc;
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], w_hi[s], N, kpad[s], kpad[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], w_lo[s], N, kpad[s], kpad[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_w64[s][0], w_hi[s], N, kpad[s], kpad[s], 64));
+    NERF_TRY(tc_make_tmap(&p.map_w64[s][1], w_lo[s], N, kpad[s], kpad[s], 64));
     if (train) {
       NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], act_hi[s], M, N, N, 32, 32));  // act_f16: the layer's ONE fp16 plane
       if (!act_f16) NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], act_lo[s], M, N, N, 32, 32));
@@ -675,6 +746,7 @@ int launch_mlp_fused_forward_split(const __nv_bfloat16* pos_hi, const __nv_bfloa
   p.n_steps = D + 1; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
   p.head_d_off = head_d_off; p.head_rgb_off = head_rgb_off;
   p.raw_density = raw_density; p.raw_rgb = raw_rgb;
+  p.pair_mma = (pair && pair_mma) ? 1 : 0;
   if (fp8c) return train ? launch_split<1, true, 1>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0, false, 1>(p, grid, kThreadsSE, smem, pair, st);
   if (act_f16) return launch_split<1, true>(p, grid, kThreadsSE, smem, pair, st);
   return train ? launch_split<1, false>(p, grid, kThreadsSE, smem, pair, st) : launch_split<0, false>(p, grid, kThreadsSE, smem, pair, st);
@@ -687,7 +759,7 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
                                  const __nv_bfloat16* const* wt_hi, const __nv_bfloat16* const* wt_lo, const int* wt_pitch, int D, int W,
                                  int Wc, long M, const float* consts_dev, int n_consts, int head_d_off, const float* d_raw_density,
                                  __nv_bfloat16* const* dz_out_hi, __nv_bfloat16* const* dz_out_lo, const uint32_t* const* mask_bits,
-                                 bool pair, cudaStream_t st, const float* dz_scale_f16) {
+                                 bool pair, cudaStream_t st, const float* dz_scale_f16, bool pair_mma) {
   const bool f16 = dz_scale_f16 != nullptr;  // dz_out_hi[s] is then ONE fp16 plane holding dZ * *dz_scale_f16 (dz_out_lo unused)
   if (!((W == 256 && Wc == 128) || (W == 128 && Wc == 64)) || D > kMaxStepsS || D < 2) { set_error("fused dgrad supports widths 256/128 and 128/64"); return 100001; }
   const int sms = device_sm_count();
@@ -701,6 +773,8 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
   for (int s = 0; s < D; s++) {
     NERF_TRY(tc_make_tmap(&p.map_w[s][0], wt_hi[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
     NERF_TRY(tc_make_tmap(&p.map_w[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 128));
+    NERF_TRY(tc_make_tmap(&p.map_w64[s][0], wt_hi[s], W, s == 0 ? Wc : W, wt_pitch[s], 64));
+    NERF_TRY(tc_make_tmap(&p.map_w64[s][1], wt_lo[s], W, s == 0 ? Wc : W, wt_pitch[s], 64));
     NERF_TRY(tc_make_tmap_box(&p.map_act[s][0], dz_out_hi[s], M, W, W, 32, 32));
     if (!f16) NERF_TRY(tc_make_tmap_box(&p.map_act[s][1], dz_out_lo[s], M, W, W, 32, 32));
     p.bits[s] = const_cast<uint32_t*>(mask_bits[s]);
@@ -713,10 +787,20 @@ int launch_mlp_fused_dgrad_split(const __nv_bfloat16* dz_cond_hi, const __nv_bfl
     stp.head = 0; stp.bias_off = 0;
   }
   p.n_steps = D; p.M = M; p.consts = consts_dev; p.n_consts = n_consts;
-  p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density; p.dz_scale = dz_scale_f16;
+  p.head_d_off = head_d_off; p.head_rgb_off = 0; p.r1 = d_raw_density; p.dz_scale = dz_scale_f16; p.pair_mma = (pair && pair_mma) ? 1 : 0;
   const int tiles = (int)cdiv(M, 128);
   if (f16) return launch_split<2, true>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
   return launch_split<2, false>(p, tiles < sms ? tiles : sms, kThreadsS, smem, pair, st);
 }
 
 }  // namespace nerf
+
+#ifdef NERF_SPLIT_DBG
+extern "C" int nerf_debug_split_stamps(unsigned long long* epi, unsigned long long* mma) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(epi, nerf::g_split_dbg, sizeof(nerf::g_split_dbg)) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(mma, nerf::g_split_dbg_mma, sizeof(nerf::g_split_dbg_mma)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
+

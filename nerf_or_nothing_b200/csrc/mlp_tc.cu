@@ -313,7 +313,7 @@ class TcMlp : public MlpEngine {
       return launch_mlp_fused_forward_split(epos.hi, epos.lo, pos_pitch_, edir.hi, edir.lo, dir_pitch_, wpl.data(),
                                             wlo.data(), kpad.data(), in_b.data(), D, s_.W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                             head_rgb_off, bias_off.data(), raw_density, raw_rgb, train ? act_out.data() : nullptr,
-                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st, f16, f8c);
+                                            train ? act_lo.data() : nullptr, train ? lv.bits.data() : nullptr, rays, scr_rows, pair(), st, f16, f8c, pair_mma());
     }
     return launch_mlp_fused_forward(epos.hi, pos_pitch_, edir.hi, dir_pitch_, wpl.data(), kpad.data(), in_b.data(), D, s_.W,
                                     s_.Wc, M, fconsts_, n_consts, head_d_off, head_rgb_off, bias_off.data(), raw_density, raw_rgb,
@@ -427,7 +427,7 @@ class TcMlp : public MlpEngine {
         for (int j = 0; j < D; j++) { wt_lo[j] = wtp_[j == 0 ? D + 1 : D - j].lo; dz_lo[j] = dzs_[j].lo; }
         NERF_TRY(launch_mlp_fused_dgrad_split(dz_cond.hi, dz_cond.lo, dz_cond.pitch, wt.data(), wt_lo.data(), wt_pitch.data(), D, W, s_.Wc, M,
                                               fconsts_, n_consts, head_d_off, d_raw_density, dz_out.data(), dz_lo.data(), masks.data(), pair(), st,
-                                              w16_ ? dz_sc_ + 4 * level : nullptr));
+                                              w16_ ? dz_sc_ + 4 * level : nullptr, pair_mma()));
       } else {
         NERF_TRY(launch_mlp_fused_dgrad(dz_cond.hi, dz_cond.pitch, wt.data(), wt_pitch.data(), D, W, s_.Wc, M, fconsts_, n_consts, head_d_off,
                                         d_raw_density, dz_out.data(), masks.data(), pair(), st));
@@ -646,6 +646,7 @@ class TcMlp : public MlpEngine {
   }
 
   bool pair() const { return !(flags_ & NERF_FLAG_NO_WEIGHT_MULTICAST); }
+  bool pair_mma() const { return pair() && (flags_ & NERF_FLAG_PAIR_MMA) != 0; }
 
   bool split_;
   bool w16_ = false;                  // fp32-accurate mode: wgrad operands as fp16 planes (see init)

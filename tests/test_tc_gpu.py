@@ -512,3 +512,25 @@ def test_fp8_corrections_training_step(net, S, R):
     np.testing.assert_array_equal(g1, g1b)
     assert abs(l1 - o64["total_loss"]) <= 1e-4 * o64["total_loss"]
     assert np.isfinite(g1).all() and rel_err(g1, g2) <= 1e-3  # same bound as fused vs per-layer forward (test_fused_training_forward_matches_layered)
+
+
+# ---------------------------------------------------------------------------------------------- NERF_FLAG_PAIR_MMA
+@pytest.mark.parametrize("flags", [0, nb.FLAG_NO_FP8_CORRECTIONS, nb.FLAG_WGRAD_FP16], ids=["default", "bf16x3-render", "wgrad-fp16"])
+@pytest.mark.parametrize("R", [700, 37, 2], ids=["R700-many-tiles", "R37-ragged", "R2-one-tile"])
+def test_pair_mma_is_bit_identical_to_multicast_clusters(R, flags):
+    """NERF_FLAG_PAIR_MMA: the 2-CTA clusters of the fp32-accurate fused kernels issue tcgen05.mma.cta_group::2 — one MMA for both
+    tiles, each SM holding only its half of every weight tile — instead of sharing whole tiles by multicast.  Every output row is
+    the same sequence of products, so render, loss and gradients are the same bits; more tiles than CTAs, an odd tile count
+    (phantom tile), fewer tiles than a cluster."""
+    m, ncfg, ocfg = _model(R, "fp32_tc", engine_flags=flags | nb.FLAG_PAIR_MMA, **NET)
+    m2, _, _ = _model(R, "fp32_tc", engine_flags=flags, **NET)
+    rays, pix, u = batch(R, ncfg.n_samples)
+    params = _params_with_biases(ocfg)
+    rargs = (rays["origins"], rays["directions"], rays["radii"], rays["nears"], rays["fars"])
+    out1, out2 = m.render(*rargs), m2.render(*rargs)
+    for a, b in zip(out1, out2):
+        np.testing.assert_array_equal(a, b)
+    g1, l1 = _gradient_step(m, params, rays, pix, u)
+    g2, l2 = _gradient_step(m2, params, rays, pix, u)
+    assert l1 == l2
+    np.testing.assert_array_equal(g1, g2)
