@@ -157,7 +157,16 @@ class TcMlp : public MlpEngine {
       if (needs_dgrad(l)) add(params + L.w_off, K, L.out, L.in_a, wtp_[l], L.out, true, L.in_a);  // WT[k, n] = W[n, k] for k < in_a
     }
     NERF_TRY(launch_f32_to_planes_batch(jobs, st));
-    if (f8c_) {
+    wf_dirty_ = true;  // the fp8-correction planes are refreshed by the first forward that multiplies with them (ensure_f8c_planes)
+    return 0;
+  }
+
+  // W16 / W8 planes of the fp16 + E4M3 representation, once per parameter version and only when a forward uses them (a training
+  // step in the default mode never does)
+  int ensure_f8c_planes(const float* params, cudaStream_t st) {
+    if (!wf_dirty_) return 0;
+    ProfScope ps(PC_CAST, st);
+    {
       F8cJobs fj;
       fj.n = 0;
       for (int l = 0; l < s_.L; l++) {
@@ -171,6 +180,7 @@ class TcMlp : public MlpEngine {
       }
       NERF_TRY(launch_f32_to_f8c_planes(fj, st));
     }
+    wf_dirty_ = false;
     return 0;
   }
 
@@ -300,6 +310,7 @@ class TcMlp : public MlpEngine {
     NERF_TRY(ensure_fconsts(params, st));
     const bool f16 = train && w16_;  // training in the w16 mode: every layer's activations leave as one fp16 plane
     const bool f8c = f8c_ && split_ && (!train || f16);
+    if (f8c) NERF_TRY(ensure_f8c_planes(params, st));
     std::vector<__nv_bfloat16*> act_out(D + 1);
     for (int s = 0; s <= D; s++) act_out[s] = f16 ? lv.acts[s].f16 : lv.acts[s].hi;
     ProfScope ps(PC_MLP_FWD, st);
@@ -652,6 +663,7 @@ class TcMlp : public MlpEngine {
   bool w16_ = false;                  // fp32-accurate mode: wgrad operands as fp16 planes (see init)
   bool f8c_ = false;                  // fp32-accurate mode: fused forward with fp16 + E4M3 correction products (see init)
   std::vector<Plane> wf_;             // f8c: W16 / W8 planes of the trunk layers and the condition layer
+  bool wf_dirty_ = true;              // ... stale since the last prepare()
   float act_x_scale_ = 1.0f;          // w16 + f8c: the activation planes hold 32 a
   float* dz_sc_ = nullptr;            // w16: per level [s, 1/s], then 2 scratch words of launch_dz_scale
   unsigned* dz_sc_scratch_ = nullptr;

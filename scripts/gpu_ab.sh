@@ -1,4 +1,6 @@
 #!/bin/bash
+# The B build is NOT kept in the tree: make it first, e.g.
+#   NERF_NVCC_DEFS=-DNERF_LATE_SHIP=0 python -m nerf_or_nothing_b200.build --force && mkdir -p scratch && cp nerf_or_nothing_b200/libnerfb200.so scratch/libnerfb200_early.so && python -m nerf_or_nothing_b200.build --force
 # generic A/B of two builds in one call: nerf_or_nothing_b200/libnerfb200.so (A) vs scratch/libnerfb200_early.so (B); $2 = extra bench flags
 tag=${1:-r02ab}
 out=gpurun_out

@@ -1,4 +1,6 @@
 #!/bin/bash
+# The B build is NOT kept in the tree: make it first, e.g.
+#   NERF_NVCC_DEFS=-DNERF_LATE_SHIP=0 python -m nerf_or_nothing_b200.build --force && mkdir -p scratch && cp nerf_or_nothing_b200/libnerfb200.so scratch/libnerfb200_early.so && python -m nerf_or_nothing_b200.build --force
 # late ship (TMA stores of the second-half epilogue behind act_ready) vs the previous order: A/B in one call, then the tensor-core tests
 tag=${1:-r02y2}
 out=gpurun_out

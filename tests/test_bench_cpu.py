@@ -49,6 +49,22 @@ def test_gemm_byte_model_matches_design_md():
     assert f32["mlp_wgrad_gemm"] == 2 * b16["mlp_wgrad_gemm"]
 
 
+def test_byte_model_of_the_fp16_wgrad_option():
+    """NERF_FLAG_WGRAD_FP16: the planes that exist only for wgrad (activations, dZ) are one fp16 plane — 2 B per element like bf16 —
+    while the encodings and dZ of the condition layer, which the fused forward / dgrad chain also read, stay hi + lo."""
+    R, S = 4096, 128
+    M = R * S * 2
+    f32, b16, w16 = (bench.gemm_bytes(R, S, p) for p in ("fp32_tc", "bf16", bench.W16_MODE))
+    assert w16["mlp_wgrad_gemm"] == b16["mlp_wgrad_gemm"] == f32["mlp_wgrad_gemm"] // 2       # 9.3 GB per step instead of 18.6
+    assert w16["mlp_fwd_gemm"] - b16["mlp_fwd_gemm"] == M * 2 * (128 + 64)                      # the encodings are still read as hi + lo
+    assert w16["mlp_dgrad_gemm"] - b16["mlp_dgrad_gemm"] == M * 2 * 128                         # and so is dZ of the condition layer
+    assert b16["mlp_bwd_heads"] < w16["mlp_bwd_heads"] < f32["mlp_bwd_heads"]
+    total = lambda d: sum(d.values())
+    assert total(w16) < 0.55 * total(f32)                                                       # 21.7 of 40.4 GB per step
+    k = bench.kernel_table({"mlp_wgrad_gemm": (19.5, 240), "mlp_fwd_gemm": (27.0, 20)}, 10, R, S, bench.W16_MODE, 6455.9, 1404.3)
+    assert "frac_tensor_issued" not in k["mlp_wgrad_gemm"] and "frac_tensor_issued" in k["mlp_fwd_gemm"]  # wgrad is ONE MMA per product there
+
+
 def test_layer_table_is_the_reference_network():
     lay = bench.layer_table()  # SURVEY §2.3: 8 x 256 trunk with a skip at layer 4, density head, 128-wide view layer, rgb head
     assert len(lay) == 11
