@@ -130,3 +130,17 @@ def test_header_is_plain_c_and_every_entry_links_from_c(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout.split()
     assert out == [str(len(names)), "100", "128", str(ctypes.sizeof(nb.default_config()))], out
+
+
+def test_engine_flag_values_agree_between_header_and_python():
+    """nerf_config.engine_flags: every NERF_FLAG_* of include/nerfb200.h has the same value as nb.FLAG_*, and the bits are distinct."""
+    import re
+
+    import nerf_or_nothing_b200 as nb
+
+    text = (ROOT / "include" / "nerfb200.h").read_text()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define NERF_FLAG_(\w+)\s+(\d+)u", text)}
+    assert len(flags) >= 10 and len(set(flags.values())) == len(flags)
+    assert all(v and v & (v - 1) == 0 for v in flags.values())  # single bits
+    for name, value in flags.items():
+        assert getattr(nb, "FLAG_" + name) == value, name
