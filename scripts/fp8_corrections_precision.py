@@ -1,4 +1,6 @@
-"""CPU simulation: forward error of alternative split products through the 8x256 MLP (vs fp64)."""
+"""CPU simulation: forward error of alternative split products through the 8x256 MLP (vs fp64).
+    python scripts/fp8_corrections_precision.py [weight scale]      f8c_gpu = the representation the fused forward kernels use
+(fp16 main product + two E4M3 correction products with the kernel's powers of two); bf16x3 = hi*hi + lo*hi + hi*lo in bf16."""
 import sys, numpy as np, torch
 sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
 from oracle import oracle as orc
@@ -31,6 +33,11 @@ def prod(a, W, mode):
         return ah @ wh.T + al @ wh.T + ah @ wl.T
     if mode == "bf16": return bf(a) @ bf(W).T
     if mode == "f16": return h16(a) @ h16(W).T
+    if mode == "f8c_gpu":  # exactly the scales of mlp_fused_split.cu REP = 1 (accumulator = 2^15 x the sum); saturating conversions
+        sat16 = lambda x: f32(x).clamp(-65504, 65504).to(torch.float16).to(torch.float64)
+        ah, wh = sat16(a * 32) / 32, sat16(W * 1024) / 1024
+        al, wl = a - ah, W - wh
+        return ah @ wh.T + (e4(al, 2.0 ** 9) @ e4(wh, 2.0 ** 6).T) + (e4(ah, 1.0) @ e4(wl, 2.0 ** 15).T)
     if mode == "f8c":  # constrained scales: the two factors of each correction product multiply to 1
         ah, wh = h16(a), h16(W); al, wl = a - ah, W - wh
         return ah @ wh.T + e5(al, 2.0 ** 4) @ e5(wh, 2.0 ** -4).T + e5(ah, 2.0 ** -8) @ e5(wl, 2.0 ** 8).T
@@ -63,7 +70,7 @@ if WSCALE != 1.0:
     tp = tp.clone(); tp[:nW] *= WSCALE
 c0, w0, z0 = mlp("f64")
 print("weight scale", WSCALE, "act max per layer", [round(float(torch.relu(z).max()), 2) for z in z0])
-for mode in ("bf16x3", "f8c", "f16+e5m2", "f16"):
+for mode in ("bf16x3", "f8c_gpu", "f8c", "f16"):
     c, w, zs = mlp(mode)
     flips = sum(int(((a > 0) != (b > 0)).sum()) for a, b in zip(zs, z0)); n = sum(a.numel() for a in z0)
     print(f"{mode:10s} comp_rgb {rel(c, c0):.2e} weights {rel(w, w0):.2e} z7 {rel(zs[-1], z0[-1]):.2e} mask flips {flips / n:.2e}")
