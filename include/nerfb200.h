@@ -68,7 +68,8 @@ typedef struct nerf_config {
   uint32_t engine_flags;   /* NERF_FLAG_*: A/B switches of the tensor-core engine (0 = the shipped schedule) */
 } nerf_config;
 
-/* engine_flags: bits 0-4, 6 and 8 select the slower, simpler path the default replaced, bits 5 and 7 alternatives that are not the default — parity tests compare them. */
+/* engine_flags: bits 0-4, 6 and 8 select the slower, simpler path the default replaced; bits 5, 7 and 9 are alternatives that are not the default
+ * (5 and 9 measured slower, 7 trades wgrad accuracy for bandwidth) — parity tests compare every one of them with the default. */
 #define NERF_FLAG_NO_FUSED_FORWARD 1u       /* render / forward-only: one GEMM launch per layer instead of the fused kernel */
 #define NERF_FLAG_NO_FUSED_TRAIN_FORWARD 2u /* training forward: per-layer launches */
 #define NERF_FLAG_NO_FUSED_DGRAD 4u         /* backward: per-layer dgrad launches instead of the fused chain */
@@ -84,7 +85,8 @@ typedef struct nerf_config {
 #define NERF_FLAG_WGRAD_FP16 128u           /* fp32-accurate mode, opt-in: the wgrad operands (activations, encodings, dZ times a per-level
                                               * power of two) leave the fused kernels as ONE fp16 plane each instead of hi + lo bf16 planes,
                                               * and the wgrad GEMMs run one fp16 MMA per product instead of three bf16 ones: half the HBM
-                                              * traffic of the backward pass.  Forward, dgrad chain and everything per-ray are unchanged.
+                                              * traffic of the backward pass.  The dgrad chain and everything per-ray are unchanged; the training
+                                              * forward switches to the fp8-correction products (see NERF_FLAG_NO_FP8_CORRECTIONS).
                                               * Gradient accuracy: ~1e-5 of the gradient's scale on a real step (sums over ~5e5 samples),
                                               * up to ~1e-3 on sums that cancel like a random walk — outside the mode's 1e-4, so not the default */
 
@@ -94,8 +96,9 @@ typedef struct nerf_config {
                                               * and holds for |activation| < 2047, |weight| < 64 (beyond, values saturate instead of overflowing);
                                               * it runs in rendering, and in training when NERF_FLAG_WGRAD_FP16 is set */
 
-#define NERF_FLAG_PAIR_MMA 512u              /* fp32-accurate fused kernels: the 2-CTA clusters issue tcgen05.mma.cta_group::2 (one MMA for both
-                                              * tiles, each SM holding half of every weight tile) instead of sharing whole tiles by multicast */
+#define NERF_FLAG_PAIR_MMA 512u             /* fp32-accurate fused kernels: the 2-CTA clusters issue tcgen05.mma.cta_group::2 (one MMA for both
+                                              * tiles, each SM holding half of every weight tile) instead of sharing whole tiles by multicast.
+                                              * Same bits; measured slower (profiles/README.md, r02p) */
 
 typedef struct nerf_mipnerf nerf_mipnerf;   /* AcceleratedMipNeRF + its embedded AcceleratedMLP */
 typedef struct nerf_adam nerf_adam;         /* AcceleratedAdamOptimizer */
